@@ -1,0 +1,101 @@
+// Shared host/device helpers for the ftb200 extension (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ftb200.h"
+
+namespace ftb {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define FTB_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      ::ftb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));      \
+      return FTB_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+#define FTB_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::ftb::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define FTB_TRY(expr)             \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != FTB_OK) return _s;  \
+  } while (0)
+
+// Checks the launch that was just issued (launch-config errors only; async
+// faults surface at the next synchronising call of the caller).
+#define FTB_CHECK_LAUNCH() FTB_CHECK_CUDA(cudaGetLastError())
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Bump allocator over the caller's workspace.  With base == nullptr it only
+// measures (used by *_workspace_bytes).
+struct Arena {
+  char* base;
+  int64_t cap;
+  int64_t off = 0;
+  bool overflow = false;
+  Arena(void* b, int64_t c) : base((char*)b), cap(c) {}
+  template <typename T>
+  T* take(int64_t n) {
+    off = align_up(off, 256);
+    int64_t bytes = n * (int64_t)sizeof(T);
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += bytes;
+    if (base && off > cap) overflow = true;
+    return p;
+  }
+  int64_t mark() const { return off; }
+  void reset(int64_t m) { off = m; }
+};
+
+int sm_count();  // SM count of the current device (cached)
+
+// ---- device helpers -------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) {
+  // accurate to ~1e-7 abs: tanh(x) = 1 - 2/(exp(2x)+1); __expf overflow -> inf is benign
+  float e = __expf(2.f * x);
+  return 1.f - 2.f / (e + 1.f);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <typename T>
+struct ActIO;
+template <>
+struct ActIO<float> {
+  static __device__ __forceinline__ float load(const float* p) { return *p; }
+  static __device__ __forceinline__ void store(float* p, float v) { *p = v; }
+};
+template <>
+struct ActIO<__nv_bfloat16> {
+  static __device__ __forceinline__ float load(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+}  // namespace ftb

@@ -1,0 +1,286 @@
+// Small bandwidth-bound kernels around the GEMMs: embedding lookup, CBHG max-pool,
+// highway gate mix, pitch/energy conditioning, the N=1 predictor heads, LayerNorm,
+// positional encoding, and the one-time weight preparation kernels.
+#include "kernels.cuh"
+
+namespace ftb {
+
+// ---- embedding: nn.Embedding, no padding_idx (models/forward_tacotron.py:31,125) ----------
+template <typename OutT>
+__global__ void embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ table, OutT* __restrict__ out,
+                             int64_t rows, int C, int ldo, int num_chars) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i % C);
+    int64_t id = tok[r];
+    id = id < 0 ? 0 : (id >= num_chars ? num_chars - 1 : id);  // the reference would raise; never read out of bounds
+    ActIO<OutT>::store(out + r * ldo + c, table[id * C + c]);
+  }
+}
+
+// ---- MaxPool1d(2,1,1)[:S] along t on channel-last data, in place (common_layers.py:73,100) --
+// out[t] = max(in[t-1], in[t]), out[0] = in[0].  One thread per (b, 8-channel group) walks t
+// downward so the in-place update never reads an overwritten value.
+template <typename T>
+__global__ void maxpool_inplace_kernel(T* __restrict__ x, int B, int S, int C) {
+  const int64_t total = (int64_t)B * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / C;
+    const int c = (int)(i % C);
+    T* p = x + (b * S) * C + c;
+    float cur = ActIO<T>::load(p + (int64_t)(S - 1) * C);
+    for (int t = S - 1; t >= 1; --t) {
+      const float prev = ActIO<T>::load(p + (int64_t)(t - 1) * C);
+      ActIO<T>::store(p + (int64_t)t * C, fmaxf(prev, cur));
+      cur = prev;
+    }
+  }
+}
+
+// ---- highway mix (common_layers.py:30-35): y = g*relu(x1) + (1-g)*x, g = sigmoid(x2) --------
+// t12: (M, 2C) f32 = [W1 x + b1 | W2 x + b2]
+template <typename T>
+__global__ void highway_mix_kernel(const float* __restrict__ t12, const T* __restrict__ x, T* __restrict__ y,
+                                   int64_t M, int C) {
+  const int64_t total = M * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / C;
+    const int c = (int)(i % C);
+    const float x1 = t12[m * 2 * C + c], x2 = t12[m * 2 * C + C + c];
+    const float g = 1.f / (1.f + __expf(-x2));
+    const float xv = ActIO<T>::load(x + i);
+    ActIO<T>::store(y + i, g * fmaxf(x1, 0.f) + (1.f - g) * xv);
+  }
+}
+
+// ---- conditioning (forward_tacotron.py:308-314): x += ps*conv3(pitch) + es*conv3(energy) ----
+// w: (C,1,3), b: (C).  series: (B,T) f32.
+template <typename T>
+__global__ void cond_add_kernel(T* __restrict__ x, const float* __restrict__ pitch, const float* __restrict__ energy,
+                                const float* __restrict__ wp, const float* __restrict__ bp,
+                                const float* __restrict__ we, const float* __restrict__ be, float ps, float es, int B,
+                                int Tn, int C) {
+  const int64_t total = (int64_t)B * Tn * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t bt = i / C;
+    const int t = (int)(bt % Tn);
+    const float* pr = pitch + (bt - t);
+    const float* er = energy + (bt - t);
+    const float p0 = t > 0 ? pr[t - 1] : 0.f, p1 = pr[t], p2 = t + 1 < Tn ? pr[t + 1] : 0.f;
+    const float e0 = t > 0 ? er[t - 1] : 0.f, e1 = er[t], e2 = t + 1 < Tn ? er[t + 1] : 0.f;
+    // same association as the reference: (x + pitch_proj*ps) + energy_proj*es
+    const float pv = fmaf(wp[c * 3 + 2], p2, fmaf(wp[c * 3 + 1], p1, wp[c * 3] * p0)) + bp[c];
+    const float ev = fmaf(we[c * 3 + 2], e2, fmaf(we[c * 3 + 1], e1, we[c * 3] * e0)) + be[c];
+    float v = ActIO<T>::load(x + i);
+    v = v + pv * ps;
+    v = v + ev * es;
+    ActIO<T>::store(x + i, v);
+  }
+}
+
+// ---- predictor head: Linear(C -> 1) / alpha, one warp per row (forward_tacotron.py:54-55) ---
+__global__ void head1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                             float inv_alpha_is_div, float alpha, float* __restrict__ out, int64_t rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s = fmaf(x[r * C + c], w[c], s);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = (s + b[0]) / alpha;  // true division like `x / alpha`
+  (void)inv_alpha_is_div;
+}
+
+// ---- LayerNorm over the last dim (eps 1e-5), optional residual: y = LN(x + r) ---------------
+// one warp per row; C <= 1024.  (models/fast_pitch.py:70-71,84,91,116,128)
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, T* __restrict__ y, int64_t rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  constexpr int MAXV = 32;  // C <= 1024
+  float v[MAXV];
+  float s = 0.f;
+  int n = 0;
+  for (int c = lane; c < C; c += 32, ++n) {
+    float a = ActIO<T>::load(x + r * C + c);
+    if (res) a += ActIO<T>::load(res + r * C + c);
+    v[n] = a;
+    s += a;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + 1e-5f);
+  n = 0;
+  for (int c = lane; c < C; c += 32, ++n) ActIO<T>::store(y + r * C + c, (v[n] - mean) * rstd * gamma[c] + beta[c]);
+}
+
+// ---- x + scale * pe[:S]  (models/fast_pitch.py:32-34); pe: (max_len, E) ---------------------
+template <typename T>
+__global__ void posenc_add_kernel(T* __restrict__ x, const float* __restrict__ pe, const float* __restrict__ scale,
+                                  int B, int S, int E) {
+  const int64_t total = (int64_t)B * S * E;
+  const float sc = scale[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E);
+    const int t = (int)((i / E) % S);
+    ActIO<T>::store(x + i, ActIO<T>::load(x + i) + sc * pe[(int64_t)t * E + e]);
+  }
+}
+
+// ---- one-time weight preparation ------------------------------------------------------------
+// BN eval -> scale/shift (common_layers.py:52): scale = w / sqrt(var + 1e-5), shift = b - mean*scale
+__global__ void bn_fold_kernel(const float* w, const float* b, const float* mean, const float* var, float* scale,
+                               float* shift, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    const float sc = w[i] / sqrtf(var[i] + 1e-5f);
+    scale[i] = sc;
+    shift[i] = b[i] - mean[i] * sc;
+  }
+}
+// RNN input-projection bias for one direction: b_ih + b_hh on the first `fold` entries, b_ih alone after.
+__global__ void rnn_bias_kernel(const float* b_ih, const float* b_hh, float* out, int n, int fold) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = b_ih[i] + (i < fold ? b_hh[i] : 0.f);
+}
+__global__ void copy_f32_kernel(const float* in, float* out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i];
+}
+template <typename OutT>
+__global__ void cast_kernel(const float* __restrict__ in, OutT* __restrict__ out, int64_t rows, int C, int ldi,
+                            int ldo) {
+  const int64_t total = rows * ldo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ldo;
+    const int c = (int)(i % ldo);
+    ActIO<OutT>::store(out + i, c < C ? in[r * ldi + c] : 0.f);
+  }
+}
+template <typename InT>
+__global__ void to_f32_kernel(const InT* __restrict__ in, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = ActIO<InT>::load(in + i);
+}
+
+// ---- launch wrappers ------------------------------------------------------------------------
+static inline int ew_blocks(int64_t n) { return (int)std::min<int64_t>(cdiv(n, 256), 148 * 16); }
+
+template <typename T>
+int embed(const int64_t* tok, const float* table, T* out, int64_t rows, int C, int ldo, int num_chars,
+          cudaStream_t s) {
+  embed_kernel<T><<<ew_blocks(rows * C), 256, 0, s>>>(tok, table, out, rows, C, ldo, num_chars);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+template int embed<float>(const int64_t*, const float*, float*, int64_t, int, int, int, cudaStream_t);
+template int embed<__nv_bfloat16>(const int64_t*, const float*, __nv_bfloat16*, int64_t, int, int, int, cudaStream_t);
+
+template <typename T>
+int maxpool_inplace(T* x, int B, int S, int C, cudaStream_t s) {
+  maxpool_inplace_kernel<T><<<ew_blocks((int64_t)B * C), 256, 0, s>>>(x, B, S, C);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+template int maxpool_inplace<float>(float*, int, int, int, cudaStream_t);
+template int maxpool_inplace<__nv_bfloat16>(__nv_bfloat16*, int, int, int, cudaStream_t);
+
+template <typename T>
+int highway_mix(const float* t12, const T* x, T* y, int64_t M, int C, cudaStream_t s) {
+  highway_mix_kernel<T><<<ew_blocks(M * C), 256, 0, s>>>(t12, x, y, M, C);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+template int highway_mix<float>(const float*, const float*, float*, int64_t, int, cudaStream_t);
+template int highway_mix<__nv_bfloat16>(const float*, const __nv_bfloat16*, __nv_bfloat16*, int64_t, int,
+                                        cudaStream_t);
+
+template <typename T>
+int cond_add(T* x, const float* pitch, const float* energy, const float* wp, const float* bp, const float* we,
+             const float* be, float ps, float es, int B, int Tn, int C, cudaStream_t s) {
+  cond_add_kernel<T><<<ew_blocks((int64_t)B * Tn * C), 256, 0, s>>>(x, pitch, energy, wp, bp, we, be, ps, es, B, Tn, C);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+template int cond_add<float>(float*, const float*, const float*, const float*, const float*, const float*,
+                             const float*, float, float, int, int, int, cudaStream_t);
+template int cond_add<__nv_bfloat16>(__nv_bfloat16*, const float*, const float*, const float*, const float*,
+                                     const float*, const float*, float, float, int, int, int, cudaStream_t);
+
+int head1(const float* x, const float* w, const float* b, float alpha, float* out, int64_t rows, int C,
+          cudaStream_t s) {
+  head1_kernel<<<cdiv(rows, 8), 256, 0, s>>>(x, w, b, 0.f, alpha, out, rows, C);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+
+template <typename T>
+int layernorm(const T* x, const T* res, const float* gamma, const float* beta, T* y, int64_t rows, int C,
+              cudaStream_t s) {
+  FTB_REQUIRE(C <= 1024, FTB_ERR_UNSUPPORTED, "layernorm: C=%d > 1024", C);
+  layernorm_kernel<T><<<cdiv(rows, 8), 256, 0, s>>>(x, res, gamma, beta, y, rows, C);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+template int layernorm<float>(const float*, const float*, const float*, const float*, float*, int64_t, int,
+                              cudaStream_t);
+template int layernorm<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*, const float*, const float*,
+                                      __nv_bfloat16*, int64_t, int, cudaStream_t);
+
+template <typename T>
+int posenc_add(T* x, const float* pe, const float* scale, int B, int S, int E, cudaStream_t s) {
+  posenc_add_kernel<T><<<ew_blocks((int64_t)B * S * E), 256, 0, s>>>(x, pe, scale, B, S, E);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+template int posenc_add<float>(float*, const float*, const float*, int, int, int, cudaStream_t);
+template int posenc_add<__nv_bfloat16>(__nv_bfloat16*, const float*, const float*, int, int, int, cudaStream_t);
+
+int bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* shift, int C,
+            cudaStream_t s) {
+  bn_fold_kernel<<<cdiv(C, 128), 128, 0, s>>>(w, b, mean, var, scale, shift, C);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+int rnn_bias(const float* b_ih, const float* b_hh, float* out, int n, int fold, cudaStream_t s) {
+  rnn_bias_kernel<<<cdiv(n, 128), 128, 0, s>>>(b_ih, b_hh, out, n, fold);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+int copy_f32(const float* in, float* out, int64_t n, cudaStream_t s) {
+  copy_f32_kernel<<<ew_blocks(n), 256, 0, s>>>(in, out, n);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+template <typename T>
+int cast_rows(const float* in, T* out, int64_t rows, int C, int ldi, int ldo, cudaStream_t s) {
+  cast_kernel<T><<<ew_blocks(rows * ldo), 256, 0, s>>>(in, out, rows, C, ldi, ldo);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+template int cast_rows<float>(const float*, float*, int64_t, int, int, int, cudaStream_t);
+template int cast_rows<__nv_bfloat16>(const float*, __nv_bfloat16*, int64_t, int, int, int, cudaStream_t);
+
+template <typename T>
+int to_f32(const T* in, float* out, int64_t n, cudaStream_t s) {
+  to_f32_kernel<T><<<ew_blocks(n), 256, 0, s>>>(in, out, n);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+template int to_f32<float>(const float*, float*, int64_t, cudaStream_t);
+template int to_f32<__nv_bfloat16>(const __nv_bfloat16*, float*, int64_t, cudaStream_t);
+
+}  // namespace ftb

@@ -1,0 +1,403 @@
+// ForwardTacotron.generate (models/forward_tacotron.py:244-330) as a native runtime: weight
+// packing at create time, then two stages of kernel launches on the caller's stream.
+//   stage A  ftb_ft_predict    : dur / pitch / energy SeriesPredictors + duration fallback
+//   (host: pitch_function / energy_function callbacks, ftb_length_plan, D2H of frame counts)
+//   stage B  ftb_ft_synthesize : embedding -> CBHG prenet -> conditioning -> LengthRegulator ->
+//                                biLSTM -> lin -> CBHG postnet -> post_proj
+// Activation dtype T is bf16 (tcgen05 GEMMs) or float (gemm_mode 1, all-fp32 validation mode).
+// The duration predictor is always fp32 (bit-exact durations).
+#include "model_common.cuh"
+
+namespace ftb {
+
+struct SeriesW {  // SeriesPredictor, models/forward_tacotron.py:14-55
+  const float* emb = nullptr;
+  int E = 0, C = 0, H = 0;
+  Layer conv[3];
+  Rnn rnn;
+  const float* lin_w = nullptr;
+  const float* lin_b = nullptr;
+  bool f32_only = false;
+};
+
+struct CbhgW {  // CBHG, models/common_layers.py:55-119
+  int K = 0, Cin = 0, ch = 0, p0 = 0, p1 = 0, nhw = 0;
+  std::vector<Layer> bank;
+  Layer proj1, proj2, pre_hw;
+  std::vector<Layer> hw;  // W1 and W2 stacked: N = 2*ch
+  Rnn rnn;
+};
+
+}  // namespace ftb
+
+struct ftb_ft_handle : ftb::ModelBase {
+  ftb_ft_config cfg;
+  ftb::SeriesW series[3];
+  ftb::CbhgW prenet, postnet;
+  const float* embedding = nullptr;
+  const float *pitch_w = nullptr, *pitch_b = nullptr, *energy_w = nullptr, *energy_b = nullptr;
+  ftb::Rnn lstm;
+  ftb::Layer lin, post_proj;
+  bool bf16_mode() const { return cfg.gemm_mode == 0; }
+};
+
+namespace ftb {
+
+static int build_series(ftb_ft_handle* h, SeriesW& P, const std::string& p, int E, int C, int H, bool f32_only) {
+  P.E = E;
+  P.C = C;
+  P.H = H;
+  P.f32_only = f32_only;
+  const bool w16 = h->bf16_mode() && !f32_only, w32 = !w16;
+  FTB_TRY(h->get(p + ".embedding.weight", {h->cfg.num_chars, E}, &P.emb));
+  for (int i = 0; i < 3; ++i) {
+    const std::string c = p + ".convs." + std::to_string(i);
+    FTB_TRY(h->make_conv(P.conv[i], c + ".conv.weight", C, i ? C : E, 5, 2, true, c + ".bnorm", "", w32, w16));
+  }
+  FTB_REQUIRE(H == 64 || H == 128, FTB_ERR_UNSUPPORTED, "%s.rnn: hidden size %d not built (64, 128)", p.c_str(), H);
+  FTB_TRY(h->make_rnn(P.rnn, p + ".rnn", C, H, false, w32, w16));
+  FTB_TRY(h->get(p + ".lin.weight", {1, 2 * H}, &P.lin_w));
+  FTB_TRY(h->get(p + ".lin.bias", {1}, &P.lin_b));
+  return FTB_OK;
+}
+
+static int build_cbhg(ftb_ft_handle* h, CbhgW& W, const std::string& p, int K, int Cin, int ch, int p0, int p1,
+                      int nhw) {
+  W.K = K;
+  W.Cin = Cin;
+  W.ch = ch;
+  W.p0 = p0;
+  W.p1 = p1;
+  W.nhw = nhw;
+  const bool w16 = h->bf16_mode(), w32 = !w16;
+  FTB_REQUIRE(ch == 256, FTB_ERR_UNSUPPORTED, "%s: CBHG channels %d not built (GRU kernel is H=256)", p.c_str(), ch);
+  FTB_REQUIRE(p1 == Cin, FTB_ERR_INVALID, "%s: residual needs proj_channels[1] == in_channels", p.c_str());
+  W.bank.resize(K);
+  for (int i = 0; i < K; ++i) {
+    const std::string c = p + ".conv1d_bank." + std::to_string(i);
+    const int k = i + 1;
+    // even k: torch pads k/2 both sides and the reference drops the last output (common_layers.py:94)
+    FTB_TRY(h->make_conv(W.bank[i], c + ".conv.weight", ch, Cin, k, k / 2, true, c + ".bnorm", "", w32, w16));
+  }
+  FTB_TRY(h->make_conv(W.proj1, p + ".conv_project1.conv.weight", p0, K * ch, 3, 1, true, p + ".conv_project1.bnorm", "",
+                       w32, w16));
+  FTB_TRY(h->make_conv(W.proj2, p + ".conv_project2.conv.weight", p1, p0, 3, 1, false, p + ".conv_project2.bnorm", "",
+                       w32, w16));
+  FTB_TRY(h->make_conv(W.pre_hw, p + ".pre_highway.weight", ch, p1, 1, 0, false, "", "", w32, w16));
+  W.hw.resize(nhw);
+  for (int i = 0; i < nhw; ++i) {
+    const std::string q = p + ".highways." + std::to_string(i);
+    Layer& L = W.hw[i];
+    L.N = 2 * ch;
+    L.Cin = ch;
+    L.CinP = (int)align_up(ch, 64);
+    L.k = 1;
+    const float *w1, *w2, *b1, *b2;
+    FTB_TRY(h->get(q + ".W1.weight", {ch, ch}, &w1));
+    FTB_TRY(h->get(q + ".W2.weight", {ch, ch}, &w2));
+    FTB_TRY(h->get(q + ".W1.bias", {ch}, &b1));
+    FTB_TRY(h->get(q + ".W2.bias", {ch}, &b2));
+    const int64_t half = (int64_t)ch * L.CinP;
+    if (w32) L.w32 = h->dalloc<float>(2 * half);
+    if (w16) L.w16 = h->dalloc<bf16>(2 * half);
+    L.bias = h->dalloc<float>(2 * ch);
+    FTB_REQUIRE((!w32 || L.w32) && (!w16 || L.w16) && L.bias, FTB_ERR_CUDA, "out of device memory");
+    if (w32) {
+      FTB_TRY(ftb_pack_conv_weight(w1, L.w32, ch, ch, 1, ch, L.CinP, 0, h->prep));
+      FTB_TRY(ftb_pack_conv_weight(w2, L.w32 + half, ch, ch, 1, ch, L.CinP, 0, h->prep));
+    }
+    if (w16) {
+      FTB_TRY(ftb_pack_conv_weight(w1, L.w16, ch, ch, 1, ch, L.CinP, 1, h->prep));
+      FTB_TRY(ftb_pack_conv_weight(w2, L.w16 + half, ch, ch, 1, ch, L.CinP, 1, h->prep));
+    }
+    FTB_TRY(copy_f32(b1, L.bias, ch, h->prep));
+    FTB_TRY(copy_f32(b2, L.bias + ch, ch, h->prep));
+  }
+  FTB_TRY(h->make_rnn(W.rnn, p + ".rnn", ch, ch, false, w32, w16));
+  return FTB_OK;
+}
+
+// ---- workspace layouts ------------------------------------------------------------------
+template <typename T>
+struct SeriesBufs {
+  T *emb, *a, *b;
+  float *xg, *ro;
+};
+template <typename T>
+static SeriesBufs<T> plan_series(Arena& A, const SeriesW& P, int B, int Tn) {
+  SeriesBufs<T> w;
+  const int64_t M = (int64_t)B * Tn;
+  w.emb = A.take<T>(M * P.E);
+  w.a = A.take<T>(M * P.C);
+  w.b = A.take<T>(M * P.C);
+  w.xg = A.take<float>(M * 6 * P.H);
+  w.ro = A.take<float>(M * 2 * P.H);
+  return w;
+}
+
+template <typename T>
+struct CbhgBufs {
+  T *bank, *p1, *p2, *ha, *hb;
+  float *t12, *xg;
+  int ld2;
+};
+template <typename T>
+static CbhgBufs<T> plan_cbhg(Arena& A, const CbhgW& W, int B, int S) {
+  CbhgBufs<T> w;
+  const int64_t M = (int64_t)B * S;
+  w.ld2 = W.pre_hw.CinP;
+  w.bank = A.take<T>(M * W.K * W.ch);
+  w.p1 = A.take<T>(M * W.p0);
+  w.p2 = A.take<T>(M * w.ld2);
+  w.ha = A.take<T>(M * W.ch);
+  w.hb = A.take<T>(M * W.ch);
+  w.t12 = A.take<float>(M * 2 * W.ch);
+  w.xg = A.take<float>(M * 6 * W.ch);
+  return w;
+}
+
+// ---- stage runners ----------------------------------------------------------------------
+template <typename T>
+static int run_series(ftb_ft_handle* h, SeriesW& P, const int64_t* tok, int B, int Tn, float alpha, float* out,
+                      Arena& A, cudaStream_t s) {
+  const int64_t mark = A.mark();
+  SeriesBufs<T> w = plan_series<T>(A, P, B, Tn);
+  FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for SeriesPredictor");
+  const int64_t M = (int64_t)B * Tn;
+  FTB_TRY(embed<T>(tok, P.emb, w.emb, M, P.E, P.E, h->cfg.num_chars, s));
+  FTB_TRY(h->gemm<T>(P.conv[0], w.emb, P.E, B, Tn, act_out(w.a, P.C), nullptr, 0, 1.f, s));
+  FTB_TRY(h->gemm<T>(P.conv[1], w.a, P.C, B, Tn, act_out(w.b, P.C), nullptr, 0, 1.f, s));
+  FTB_TRY(h->gemm<T>(P.conv[2], w.b, P.C, B, Tn, act_out(w.a, P.C), nullptr, 0, 1.f, s));
+  FTB_TRY(h->gemm<T>(P.rnn.in, w.a, P.C, B, Tn, act_out(w.xg, 6 * P.H), nullptr, 0, 1.f, s));
+  FTB_TRY(rnn_bidir(w.xg, P.rnn.w_hh, P.rnn.b_hn, w.ro, B, Tn, P.H, 0, 0, s));
+  FTB_TRY(head1(w.ro, P.lin_w, P.lin_b, alpha, out, M, 2 * P.H, s));
+  h->launches += 3;
+  A.reset(mark);
+  return FTB_OK;
+}
+
+// x: (B,S,ldx) with ldx >= CinP of the bank convs and zero padding columns; out: (B,S,2*ch)
+template <typename T>
+static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int S, T* out, Arena& A, cudaStream_t s) {
+  const int64_t mark = A.mark();
+  CbhgBufs<T> w = plan_cbhg<T>(A, W, B, S);
+  FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for CBHG");
+  const int64_t M = (int64_t)B * S;
+  const int bank_c = W.K * W.ch;
+  for (int i = 0; i < W.K; ++i)
+    FTB_TRY(h->gemm<T>(W.bank[i], x, ldx, B, S, act_out(w.bank, bank_c, i * W.ch), nullptr, 0, 1.f, s));
+  FTB_TRY(maxpool_inplace<T>(w.bank, B, S, bank_c, s));
+  FTB_TRY(h->gemm<T>(W.proj1, w.bank, bank_c, B, S, act_out(w.p1, W.p0), nullptr, 0, 1.f, s));
+  if (w.ld2 != W.p1) FTB_CHECK_CUDA(cudaMemsetAsync(w.p2, 0, (size_t)M * w.ld2 * sizeof(T), s));
+  FTB_TRY(h->gemm<T>(W.proj2, w.p1, W.p0, B, S, act_out(w.p2, w.ld2), x, ldx, 1.f, s));  // + residual
+  FTB_TRY(h->gemm<T>(W.pre_hw, w.p2, w.ld2, B, S, act_out(w.ha, W.ch), nullptr, 0, 1.f, s));
+  T *cur = w.ha, *nxt = w.hb;
+  for (int i = 0; i < W.nhw; ++i) {
+    FTB_TRY(h->gemm<T>(W.hw[i], cur, W.ch, B, S, act_out(w.t12, 2 * W.ch), nullptr, 0, 1.f, s));
+    FTB_TRY(highway_mix<T>(w.t12, cur, nxt, M, W.ch, s));
+    std::swap(cur, nxt);
+  }
+  FTB_TRY(h->gemm<T>(W.rnn.in, cur, W.ch, B, S, act_out(w.xg, 6 * W.ch), nullptr, 0, 1.f, s));
+  FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, std::is_same<T, bf16>::value, s));
+  h->launches += 2 + W.nhw;
+  A.reset(mark);
+  return FTB_OK;
+}
+
+template <typename T>
+static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* cum, const float* pitch,
+                          const float* energy, int B, int Tn, int L, float* mel, float* mel_post, Arena& A,
+                          cudaStream_t s) {
+  const ftb_ft_config& c = h->cfg;
+  const int E = c.embed_dims, D = 2 * c.prenet_dims, RH = c.rnn_dims, NM = c.n_mels;
+  const int melP = (int)align_up(NM, 64);
+  const int64_t MT = (int64_t)B * Tn, ML = (int64_t)B * L;
+  T* x0 = A.take<T>(MT * E);
+  T* enc = A.take<T>(MT * D);
+  T* up = A.take<T>(ML * D);
+  float* xg = A.take<float>(ML * 8 * RH);
+  T* dec = A.take<T>(ML * 2 * RH);
+  T* mel_cl = A.take<T>(ML * melP);
+  T* post = A.take<T>(ML * 2 * c.postnet_dims);
+  FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for synthesize");
+
+  FTB_TRY(embed<T>(tok, h->embedding, x0, MT, E, E, c.num_chars, s));
+  FTB_TRY(run_cbhg<T>(h, h->prenet, x0, E, B, Tn, enc, A, s));
+  FTB_TRY(cond_add<T>(enc, pitch, energy, h->pitch_w, h->pitch_b, h->energy_w, h->energy_b, c.pitch_strength,
+                      c.energy_strength, B, Tn, D, s));
+  FTB_TRY(ftb_length_expand(enc, cum, up, B, Tn, L, D, (int)sizeof(T), s));
+  FTB_TRY(h->gemm<T>(h->lstm.in, up, D, B, L, act_out(xg, 8 * RH), nullptr, 0, 1.f, s));
+  FTB_TRY(rnn_bidir(xg, h->lstm.w_hh, nullptr, dec, B, L, RH, 1, std::is_same<T, bf16>::value, s));
+  if (melP != NM) FTB_CHECK_CUDA(cudaMemsetAsync(mel_cl, 0, (size_t)ML * melP * sizeof(T), s));
+  Out o = act_out(mel_cl, melP);
+  o.t = mel;  // 'mel' (B,80,L) and the channel-last copy the postnet reads, from one epilogue
+  FTB_TRY(h->gemm<T>(h->lin, dec, 2 * RH, B, L, o, nullptr, 0, 1.f, s));
+  FTB_TRY(run_cbhg<T>(h, h->postnet, mel_cl, melP, B, L, post, A, s));
+  Out op;
+  op.t = mel_post;
+  FTB_TRY(h->gemm<T>(h->post_proj, post, 2 * c.postnet_dims, B, L, op, nullptr, 0, 1.f, s));
+  h->launches += 4;
+  return FTB_OK;
+}
+
+template <typename T>
+static int64_t synth_bytes(const ftb_ft_handle* h, int B, int Tn, int L) {
+  const ftb_ft_config& c = h->cfg;
+  Arena A(nullptr, 0);
+  const int D = 2 * c.prenet_dims, RH = c.rnn_dims, melP = (int)align_up(c.n_mels, 64);
+  const int64_t MT = (int64_t)B * Tn, ML = (int64_t)B * L;
+  A.take<T>(MT * c.embed_dims);
+  A.take<T>(MT * D);
+  A.take<T>(ML * D);
+  A.take<float>(ML * 8 * RH);
+  A.take<T>(ML * 2 * RH);
+  A.take<T>(ML * melP);
+  A.take<T>(ML * 2 * c.postnet_dims);
+  const int64_t base = A.mark();
+  plan_cbhg<T>(A, h->prenet, B, Tn);
+  const int64_t pre = A.mark();
+  A.reset(base);
+  plan_cbhg<T>(A, h->postnet, B, L);
+  return std::max(pre, A.mark()) + 256;
+}
+
+template <typename T>
+static int64_t predict_bytes(const ftb_ft_handle* h, int B, int Tn) {
+  int64_t best = 0;
+  for (int i = 0; i < 3; ++i) {
+    Arena A(nullptr, 0);
+    A.take<char>(256);
+    if (h->series[i].f32_only || !h->bf16_mode())
+      plan_series<float>(A, h->series[i], B, Tn);
+    else
+      plan_series<T>(A, h->series[i], B, Tn);
+    best = std::max(best, A.mark());
+  }
+  return best + 256;
+}
+
+}  // namespace ftb
+
+using namespace ftb;
+
+extern "C" int ftb_ft_create(const ftb_ft_config* cfg, const ftb_tensor* tensors, int n_tensors, int device,
+                             ftb_ft_handle** out) {
+  FTB_REQUIRE(cfg && tensors && out && n_tensors > 0, FTB_ERR_INVALID, "ftb_ft_create: bad arguments");
+  int sms = 0, maj = 0, mnr = 0;
+  FTB_TRY(ftb_device_check(device, &sms, &maj, &mnr));
+  FTB_CHECK_CUDA(cudaSetDevice(device));
+  ftb_ft_handle* h = new ftb_ft_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  for (int i = 0; i < n_tensors; ++i) h->sd[tensors[i].name] = tensors[i];
+  const ftb_ft_config& c = h->cfg;
+  auto build = [&]() -> int {
+    FTB_REQUIRE(c.rnn_dims == 512, FTB_ERR_UNSUPPORTED, "rnn_dims %d not built (LSTM kernel is H=512)", c.rnn_dims);
+    FTB_REQUIRE(c.embed_dims % 64 == 0 && c.series_embed_dims % 64 == 0, FTB_ERR_UNSUPPORTED,
+                "embedding dims must be multiples of 64");
+    FTB_TRY(build_series(h, h->series[0], "dur_pred", c.series_embed_dims, c.durpred_conv_dims, c.durpred_rnn_dims, true));
+    FTB_TRY(build_series(h, h->series[1], "pitch_pred", c.series_embed_dims, c.pitch_conv_dims, c.pitch_rnn_dims, false));
+    FTB_TRY(build_series(h, h->series[2], "energy_pred", c.series_embed_dims, c.energy_conv_dims, c.energy_rnn_dims, false));
+    FTB_TRY(h->get("embedding.weight", {c.num_chars, c.embed_dims}, &h->embedding));
+    FTB_TRY(build_cbhg(h, h->prenet, "prenet", c.prenet_k, c.embed_dims, c.prenet_dims, c.prenet_dims, c.embed_dims,
+                       c.prenet_num_highways));
+    const int D = 2 * c.prenet_dims;
+    FTB_TRY(h->get("pitch_proj.weight", {D, 1, 3}, &h->pitch_w));
+    FTB_TRY(h->get("pitch_proj.bias", {D}, &h->pitch_b));
+    FTB_TRY(h->get("energy_proj.weight", {D, 1, 3}, &h->energy_w));
+    FTB_TRY(h->get("energy_proj.bias", {D}, &h->energy_b));
+    const bool w16 = h->bf16_mode(), w32 = !w16;
+    FTB_TRY(h->make_rnn(h->lstm, "lstm", D, c.rnn_dims, true, w32, w16));
+    FTB_TRY(h->make_conv(h->lin, "lin.weight", c.n_mels, 2 * c.rnn_dims, 1, 0, false, "", "lin.bias", w32, w16));
+    FTB_TRY(build_cbhg(h, h->postnet, "postnet", c.postnet_k, c.n_mels, c.postnet_dims, c.postnet_dims, c.n_mels,
+                       c.postnet_num_highways));
+    FTB_TRY(h->make_conv(h->post_proj, "post_proj.weight", c.n_mels, 2 * c.postnet_dims, 1, 0, false, "", "", w32, w16));
+    FTB_CHECK_CUDA(cudaStreamSynchronize(h->prep));
+    return FTB_OK;
+  };
+  const int st = build();
+  if (st != FTB_OK) {
+    delete h;
+    return st;
+  }
+  // after packing, only parameters that are read in their reference layout remain referenced
+  *out = h;
+  return FTB_OK;
+}
+
+extern "C" void ftb_ft_destroy(ftb_ft_handle* h) { delete h; }
+
+extern "C" int64_t ftb_ft_workspace_bytes(const ftb_ft_handle* h, int B, int T, int L) {
+  if (!h || B <= 0 || T <= 0) return -1;
+  int64_t p = h->bf16_mode() ? predict_bytes<bf16>(h, B, T) : predict_bytes<float>(h, B, T);
+  if (L > 0) p = std::max(p, h->bf16_mode() ? synth_bytes<bf16>(h, B, T, L) : synth_bytes<float>(h, B, T, L));
+  // sub-module entry points stage f32 inputs/outputs in the workspace as well
+  const int64_t S = std::max(T, L);
+  p += (int64_t)B * S * 4 * (2 * std::max(h->cfg.prenet_dims, h->cfg.postnet_dims) + 128) + 4096;
+  return p;
+}
+
+extern "C" int ftb_ft_series_predictor(ftb_ft_handle* h, int which, const int64_t* tokens, int B, int T, float alpha,
+                                       float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  FTB_REQUIRE(h && tokens && out && which >= 0 && which < 3 && B > 0 && T > 0, FTB_ERR_INVALID,
+              "ftb_ft_series_predictor: bad arguments");
+  FTB_REQUIRE(alpha != 0.f, FTB_ERR_INVALID, "alpha must be non-zero");
+  Arena A(workspace, workspace_bytes);
+  SeriesW& P = h->series[which];
+  if (P.f32_only || !h->bf16_mode()) return run_series<float>(h, P, tokens, B, T, alpha, out, A, (cudaStream_t)stream);
+  return run_series<bf16>(h, P, tokens, B, T, alpha, out, A, (cudaStream_t)stream);
+}
+
+extern "C" int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, int T, float alpha, float* dur,
+                              float* pitch, float* energy, void* workspace, int64_t workspace_bytes, void* stream) {
+  FTB_REQUIRE(h && tokens && dur && pitch && energy && workspace, FTB_ERR_INVALID, "ftb_ft_predict: bad arguments");
+  h->launches = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  // the fallback's 8-byte accumulator lives at the head of the workspace
+  FTB_REQUIRE(workspace_bytes >= 256, FTB_ERR_WORKSPACE, "workspace too small");
+  char* ws = (char*)workspace;
+  FTB_TRY(ftb_ft_series_predictor(h, 0, tokens, B, T, alpha, dur, ws + 256, workspace_bytes - 256, stream));
+  FTB_TRY(ftb_duration_fallback(dur, (int64_t)B * T, ws, s));
+  h->launches += 2;
+  FTB_TRY(ftb_ft_series_predictor(h, 1, tokens, B, T, 1.f, pitch, ws + 256, workspace_bytes - 256, stream));
+  FTB_TRY(ftb_ft_series_predictor(h, 2, tokens, B, T, 1.f, energy, ws + 256, workspace_bytes - 256, stream));
+  return FTB_OK;
+}
+
+extern "C" int ftb_ft_synthesize(ftb_ft_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
+                                 const float* energy, int B, int T, int L, float* mel, float* mel_post,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
+  FTB_REQUIRE(h && tokens && cum && pitch && energy && mel && mel_post && workspace, FTB_ERR_INVALID,
+              "ftb_ft_synthesize: bad arguments");
+  FTB_REQUIRE(B > 0 && T > 0 && L > 0, FTB_ERR_INVALID, "ftb_ft_synthesize: bad sizes B=%d T=%d L=%d", B, T, L);
+  h->launches = 0;
+  Arena A(workspace, workspace_bytes);
+  if (h->bf16_mode())
+    return run_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, (cudaStream_t)stream);
+  return run_synthesize<float>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, (cudaStream_t)stream);
+}
+
+extern "C" int ftb_ft_cbhg(ftb_ft_handle* h, int which, const float* x, int B, int S, float* out, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  FTB_REQUIRE(h && x && out && workspace && (which == 0 || which == 1) && B > 0 && S > 0, FTB_ERR_INVALID,
+              "ftb_ft_cbhg: bad arguments");
+  CbhgW& W = which ? h->postnet : h->prenet;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena A(workspace, workspace_bytes);
+  const int64_t M = (int64_t)B * S;
+  const int ldx = W.bank[0].CinP;
+  if (h->bf16_mode()) {
+    bf16* xi = A.take<bf16>(M * ldx);
+    bf16* yo = A.take<bf16>(M * 2 * W.ch);
+    FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small");
+    FTB_TRY(cast_rows<bf16>(x, xi, M, W.Cin, W.Cin, ldx, s));
+    FTB_TRY(run_cbhg<bf16>(h, W, xi, ldx, B, S, yo, A, s));
+    return to_f32<bf16>(yo, out, M * 2 * W.ch, s);
+  }
+  float* xi = A.take<float>(M * ldx);
+  FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small");
+  FTB_TRY(cast_rows<float>(x, xi, M, W.Cin, W.Cin, ldx, s));
+  return run_cbhg<float>(h, W, xi, ldx, B, S, out, A, s);
+}
+
+extern "C" int ftb_ft_last_launch_count(const ftb_ft_handle* h) { return h ? h->launches : -1; }

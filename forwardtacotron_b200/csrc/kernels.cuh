@@ -1,0 +1,45 @@
+// Internal launch-wrapper declarations (one per kernel family).
+#pragma once
+#include "common.cuh"
+
+namespace ftb {
+
+// conv_gemm_simt.cu / conv_gemm_tc.cu
+int conv_gemm_f32(const float* x, const float* w, const ftb_conv_desc& d, cudaStream_t s);
+int conv_gemm_bf16(const __nv_bfloat16* x, const __nv_bfloat16* w, const ftb_conv_desc& d, cudaStream_t s);
+
+// rnn_small.cu / rnn_cluster.cu
+int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
+              int out_bf16, cudaStream_t s);
+
+// attention.cu : softmax(q k^T / sqrt(hd) + key_pad_mask) v on packed qkv (B,S,3E)
+template <typename T>
+int attention(const T* qkv, const int64_t* tokens_for_mask, T* ctx, int B, int S, int E, int heads, cudaStream_t s);
+
+// elementwise.cu
+template <typename T>
+int embed(const int64_t* tok, const float* table, T* out, int64_t rows, int C, int ldo, int num_chars, cudaStream_t s);
+template <typename T>
+int maxpool_inplace(T* x, int B, int S, int C, cudaStream_t s);
+template <typename T>
+int highway_mix(const float* t12, const T* x, T* y, int64_t M, int C, cudaStream_t s);
+template <typename T>
+int cond_add(T* x, const float* pitch, const float* energy, const float* wp, const float* bp, const float* we,
+             const float* be, float ps, float es, int B, int Tn, int C, cudaStream_t s);
+int head1(const float* x, const float* w, const float* b, float alpha, float* out, int64_t rows, int C,
+          cudaStream_t s);
+template <typename T>
+int layernorm(const T* x, const T* res, const float* gamma, const float* beta, T* y, int64_t rows, int C,
+              cudaStream_t s);
+template <typename T>
+int posenc_add(T* x, const float* pe, const float* scale, int B, int S, int E, cudaStream_t s);
+int bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* shift, int C,
+            cudaStream_t s);
+int rnn_bias(const float* b_ih, const float* b_hh, float* out, int n, int fold, cudaStream_t s);
+int copy_f32(const float* in, float* out, int64_t n, cudaStream_t s);
+template <typename T>
+int cast_rows(const float* in, T* out, int64_t rows, int C, int ldi, int ldo, cudaStream_t s);
+template <typename T>
+int to_f32(const T* in, float* out, int64_t n, cudaStream_t s);
+
+}  // namespace ftb

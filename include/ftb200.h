@@ -1,0 +1,230 @@
+/*
+ * ftb200.h -- C ABI of the B200-native ForwardTacotron / FastPitch inference
+ * path and the STFT->log-mel feature extractor.
+ *
+ * The reference (tarepan/ForwardTacotron) is pure Python: it has no FFI of its
+ * own, so the drop-in boundary is its Python surface
+ *     ForwardTacotron.from_config / from_checkpoint / generate      models/forward_tacotron.py:244-268,338-350
+ *     FastPitch.from_config / from_checkpoint / generate            models/fast_pitch.py:286-303,342-354
+ *     DSP.from_config / DSP.wav_to_mel                              utils/dsp.py:59-61,71-87
+ * which forwardtacotron_b200/{models,utils}/ mirrors.  This header is the
+ * boundary UNDER that surface: what the mirrored classes bind with ctypes and
+ * what a maintainer of the reference would bind.
+ *
+ * Conventions
+ *   - every entry point returns 0 (FTB_OK) or a negative ftb_status; the text of
+ *     the last failure on the calling thread is ftb_last_error();
+ *   - all data pointers are DEVICE pointers owned by the caller unless the name
+ *     says host_; nothing is allocated behind the caller's back except the
+ *     packed weight copy held by a model handle;
+ *   - every launch goes to the cudaStream_t passed as `stream` (void*);
+ *   - activations are channel-last: (B, S, C) row-major; mel outputs are the
+ *     reference's (B, n_mels, L);
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef FTB200_H_
+#define FTB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FTB_ABI_VERSION 1
+
+typedef enum ftb_status {
+  FTB_OK = 0,
+  FTB_ERR_INVALID = -1,     /* bad argument / unsupported shape                 */
+  FTB_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed              */
+  FTB_ERR_MISSING = -3,     /* a state_dict entry is missing or has wrong shape */
+  FTB_ERR_WORKSPACE = -4,   /* caller workspace too small                       */
+  FTB_ERR_UNSUPPORTED = -5  /* config outside what the kernels are built for    */
+} ftb_status;
+
+typedef enum ftb_dtype { FTB_F32 = 0, FTB_I64 = 1, FTB_BF16 = 2, FTB_I32 = 3 } ftb_dtype;
+
+/* One state_dict entry: the name is the reference's parameter / buffer name
+ * (e.g. "prenet.conv1d_bank.3.conv.weight"), data is a device pointer in the
+ * reference's own layout and dtype. */
+typedef struct ftb_tensor {
+  const char* name;
+  const void* data;
+  int32_t dtype; /* ftb_dtype */
+  int32_t ndim;
+  int64_t shape[4];
+} ftb_tensor;
+
+const char* ftb_last_error(void);
+int ftb_abi_version(void);
+/* Number of SMs / compute capability of `device`; fails on anything but sm_100. */
+int ftb_device_check(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------- *
+ * Operator level (each replaces one torch call site of the reference)
+ * ------------------------------------------------------------------------- */
+
+/* LengthRegulator.forward, models/common_layers.py:12-19.
+ * plan: dur (B,T) f32 is clamped at 0 IN PLACE (line 13); reps = trunc(dur+0.5)
+ * (line 16); cum (B,T) int32 receives the INCLUSIVE prefix sum of reps per row,
+ * total (B) int32 the per-row frame count.  The caller reads `total` back (the
+ * one D2H of generate) to size L = max(total).
+ * expand: out (B,L,C) <- x (B,T,C) rows repeated, zero padded (line 18).
+ * elem_bytes is 2 (bf16) or 4 (f32); C*elem_bytes must be a multiple of 16. */
+int ftb_length_plan(float* dur, int32_t* cum, int32_t* total, int B, int T, void* stream);
+int ftb_length_expand(const void* x, const int32_t* cum, void* out, int B, int T, int L, int C,
+                      int elem_bytes, void* stream);
+
+/* Duration fallback, models/forward_tacotron.py:254-255: if the batch-global sum
+ * of trunc-toward-zero(dur) is <= 0, fill dur with 2.0.  scratch: 8 bytes. */
+int ftb_duration_fallback(float* dur, int64_t n, void* scratch8, void* stream);
+
+/* Conv1d (stride 1, zero padded, truncated to S) as implicit GEMM on
+ * channel-last activations, models/common_layers.py:45-52:
+ *   y[b,t,n] = sum_{j<k} sum_{c<Cin} w[n, j*Cin + c] * x[b, t + j - pad_left, c]
+ * followed by the fused epilogue, in this order:
+ *   (+bias[n]) -> (ReLU) -> (*scale[n] + shift[n]) -> (+residual[b,t,n]) -> *out_scale
+ * Outputs (any subset): out_f32 (B,S,ldo) / out_bf16 (B,S,ldo) / out_t (B,N,S) f32.
+ * A linear layer is k = 1.  Weights must be pre-packed (N, k*Cin) K-major. */
+typedef struct ftb_conv_desc {
+  int32_t B, S, Cin, N, ktaps, pad_left;
+  int32_t lda;  /* row stride of x in elements (>= Cin)               */
+  int32_t ldo;  /* row stride of out_f32 / out_bf16 (>= n_offset + N)  */
+  int32_t n_offset; /* column offset inside the output row (conv bank concat) */
+  int32_t relu;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  const float* residual_f32; /* (B,S,ldr) or NULL */
+  const void* residual_bf16; /* (B,S,ldr) or NULL */
+  int32_t ldr;
+  float out_scale;
+  float* out_f32;
+  void* out_bf16;
+  float* out_t;
+} ftb_conv_desc;
+
+/* fp32 SIMT kernel (fp32-accurate: used for the duration predictor). */
+int ftb_conv_gemm_f32(const float* x, const float* w_packed, const ftb_conv_desc* d, void* stream);
+/* tcgen05 / TMA kernel: x (B,S,lda) bf16, w bf16 (Npad, k*Cin) with Cin % 64 == 0. */
+int ftb_conv_gemm_bf16(const void* x, const void* w_packed, const ftb_conv_desc* d, void* stream);
+/* Pack a reference-layout conv weight (N, Cin, k) f32 into (Npad, k*Cin_pad) K-major
+ * f32 or bf16 (zero padded). */
+int ftb_pack_conv_weight(const float* w, void* out, int N, int Cin, int k, int Npad, int Cin_pad,
+                         int out_bf16, void* stream);
+
+/* Bidirectional single-layer GRU / LSTM recurrence (torch.nn.GRU / nn.LSTM,
+ * batch_first, zero initial state; models/common_layers.py:84, models/forward_tacotron.py:39,165).
+ * xg (B,S,2,G*H) f32 holds W_ih x + b_ih (+ b_hh for the gates where it can be
+ * folded: all LSTM gates, GRU r and z); w_hh (2,G*H,H) f32 in torch gate order;
+ * b_hn (2,H) f32 is the GRU n-gate hidden bias (NULL for LSTM).
+ * out (B,S,2H): f32 when out_bf16 == 0, else bf16.
+ * H in {64,128}: one-CTA-per-row fp32 kernel (W_hh in shared memory, exact fp32).
+ * H in {256,512}: thread-block-cluster kernel, W_hh resident in registers as
+ * bf16 MMA fragments, hidden state exchanged through distributed shared memory. */
+int ftb_rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H,
+                  int is_lstm, int out_bf16, void* stream);
+
+/* DSP.wav_to_mel, utils/dsp.py:71-87,105-107, for a batch of clips packed back to
+ * back: audio f32, clip_offsets (n_clips+1) int64 sample offsets, frame_offsets
+ * (n_clips+1) int64 with frames_i = 1 + N_i / hop.  out: (n_mels, total_frames)
+ * is written per clip as an (n_mels, frames_i) row-major block starting at
+ * out + n_mels * frame_offsets[i].  Requires n_fft == win_length == 1024. */
+typedef struct ftb_mel_config {
+  int32_t sample_rate, n_fft, hop_length, win_length, num_mels;
+  float fmin, fmax;
+} ftb_mel_config;
+typedef struct ftb_mel_handle ftb_mel_handle;
+int ftb_mel_create(const ftb_mel_config* cfg, int device, ftb_mel_handle** out);
+void ftb_mel_destroy(ftb_mel_handle* h);
+int ftb_mel_run(ftb_mel_handle* h, const float* audio, const int64_t* clip_offsets, const int64_t* frame_offsets,
+                int n_clips, int64_t total_frames, float* out, int normalize, void* stream);
+/* Copies the (num_mels, 1 + n_fft/2) f32 filterbank the handle uses to HOST memory. */
+int ftb_mel_filterbank(ftb_mel_handle* h, float* host_out);
+
+/* ------------------------------------------------------------------------- *
+ * Model level: ForwardTacotron.generate, models/forward_tacotron.py:244-330
+ * ------------------------------------------------------------------------- */
+typedef struct ftb_ft_config { /* keys of config.yaml forward_tacotron.model + num_chars, n_mels */
+  int32_t num_chars, embed_dims, series_embed_dims;
+  int32_t durpred_conv_dims, durpred_rnn_dims;
+  int32_t pitch_conv_dims, pitch_rnn_dims;
+  int32_t energy_conv_dims, energy_rnn_dims;
+  int32_t rnn_dims;
+  int32_t prenet_dims, prenet_k, prenet_num_highways;
+  int32_t postnet_dims, postnet_k, postnet_num_highways;
+  int32_t n_mels;
+  float pitch_strength, energy_strength;
+  int32_t gemm_mode; /* 0: bf16 tcgen05 GEMMs (duration predictor stays fp32); 1: all GEMMs fp32 SIMT */
+} ftb_ft_config;
+
+typedef struct ftb_ft_handle ftb_ft_handle;
+
+/* Packs the weights once (GEMM layouts, BN -> scale/shift, bias folding).
+ * `tensors` is the model's state_dict (load_state_dict contract: every name the
+ * reference's strict load expects must be present with the reference's shape). */
+int ftb_ft_create(const ftb_ft_config* cfg, const ftb_tensor* tensors, int n_tensors, int device,
+                  ftb_ft_handle** out);
+void ftb_ft_destroy(ftb_ft_handle* h);
+
+/* Bytes of caller workspace needed by predict / synthesize for these sizes. */
+int64_t ftb_ft_workspace_bytes(const ftb_ft_handle* h, int B, int T, int L);
+
+/* Stage A (generate lines 251-262): three SeriesPredictors + duration fallback.
+ * tokens (B,T) int64; dur (B,T), pitch (B,T), energy (B,T) f32 out
+ * ((B,1,T) of the reference is the same memory). */
+int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, int T, float alpha, float* dur, float* pitch,
+                   float* energy, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Between the stages the Python callbacks pitch_function / energy_function run
+ * (generate lines 259, 263), then ftb_length_plan + the D2H of `total`. */
+
+/* Stage B (_generate_mel, lines 289-330).  dur must already be clamped/planned:
+ * cum is the output of ftb_length_plan.  mel / mel_post: (B, n_mels, L) f32. */
+int ftb_ft_synthesize(ftb_ft_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
+                      const float* energy, int B, int T, int L, float* mel, float* mel_post, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* Sub-module entry points (row a3 / a4 of the scope table; used by the mirrored
+ * SeriesPredictor / CBHG modules and their parity tests).
+ * which: 0 dur_pred, 1 pitch_pred, 2 energy_pred.  out (B,T) f32 (no fallback). */
+int ftb_ft_series_predictor(ftb_ft_handle* h, int which, const int64_t* tokens, int B, int T, float alpha,
+                            float* out, void* workspace, int64_t workspace_bytes, void* stream);
+/* which: 0 prenet, 1 postnet.  x (B,S,Cin) f32 channel-last -> out (B,S,2*dims) f32. */
+int ftb_ft_cbhg(ftb_ft_handle* h, int which, const float* x, int B, int S, float* out, void* workspace,
+                int64_t workspace_bytes, void* stream);
+/* Number of kernels the last predict / synthesize call launched (bench bookkeeping). */
+int ftb_ft_last_launch_count(const ftb_ft_handle* h);
+
+/* ------------------------------------------------------------------------- *
+ * Model level: FastPitch.generate, models/fast_pitch.py:286-340
+ * ------------------------------------------------------------------------- */
+typedef struct ftb_fp_config { /* keys of config.yaml fast_pitch.model + num_chars, n_mels */
+  int32_t num_chars, n_mels;
+  int32_t durpred_d_model, durpred_n_heads, durpred_layers, durpred_d_fft;
+  int32_t pitch_d_model, pitch_n_heads, pitch_layers, pitch_d_fft;
+  int32_t energy_d_model, energy_n_heads, energy_layers, energy_d_fft;
+  int32_t d_model, conv1_kernel, conv2_kernel;
+  int32_t prenet_layers, prenet_heads, prenet_fft;
+  int32_t postnet_layers, postnet_heads, postnet_fft;
+  float pitch_strength, energy_strength;
+  int32_t gemm_mode;
+} ftb_fp_config;
+
+typedef struct ftb_fp_handle ftb_fp_handle;
+int ftb_fp_create(const ftb_fp_config* cfg, const ftb_tensor* tensors, int n_tensors, int device,
+                  ftb_fp_handle** out);
+void ftb_fp_destroy(ftb_fp_handle* h);
+int64_t ftb_fp_workspace_bytes(const ftb_fp_handle* h, int B, int T, int L);
+int ftb_fp_predict(ftb_fp_handle* h, const int64_t* tokens, int B, int T, float alpha, float* dur, float* pitch,
+                   float* energy, void* workspace, int64_t workspace_bytes, void* stream);
+/* mel (B, n_mels, L) f32; the reference returns the same tensor as 'mel' and 'mel_post'. */
+int ftb_fp_synthesize(ftb_fp_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
+                      const float* energy, int B, int T, int L, float* mel, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+int ftb_fp_last_launch_count(const ftb_fp_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FTB200_H_ */
