@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Headline benchmark: valid mel frames/s of batched ``ForwardTacotron.generate`` (BASELINE.json configs[1]:
+batch 64 x 200 synthetic phonemes, alpha 1.0, default config.yaml model) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one generate() call over one batch (stage A predictors, callbacks, length plan + its D2H, stage B).
+Utterances are independent, so N GPUs run N replicas on different batches with NO data-path collective
+(weak scaling); the only collectives are the timing barrier / max / sum.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+B, T = 64, 200                       # BASELINE.json configs[1]
+CPU_SAMPLE_B = 8                     # rows of the same batch the CPU arm times (bounded sample)
+METRIC, UNIT = 'mel_frames_per_s', 'frames/s'
+WORKLOAD = 'ForwardTacotron.generate batch 64 x 200 phonemes, alpha 1.0, config.yaml defaults, synthetic weights'
+
+
+def peaks():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {'hbm': float(d['hbm_gbs']), 'tensor': float(d.get('bf16_tflops_sustained', d['bf16_tflops'])),
+                'tensor_burst': float(d['bf16_tflops']), 'src': 'measured'}
+    return {'hbm': 6650.0, 'tensor': 1400.0, 'tensor_burst': 1590.0, 'src': 'fallback'}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_generate_rate(steps: int, warmup: int):
+    """The reference's algorithm (oracle port, torch fp32 on all host cores) on a bounded sample of the
+    same batch: the first CPU_SAMPLE_B utterances."""
+    import torch
+    from forwardtacotron_b200.utils import synth
+    from oracle import model_oracle as mo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, _ = synth.synthetic_model('forward_tacotron')
+    sd = model.state_dict()
+    x = synth.synthetic_tokens(B, T, seed=1)[:CPU_SAMPLE_B]
+    frames, times = 0, []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = mo.ft_generate(sd, x)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            frames = int((out['dur'] + 0.5).long().sum())
+    total = sum(times)
+    return {'value': frames * len(times) / total, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'first {CPU_SAMPLE_B} of the {B} utterances (T={T}), {len(times)} timed generate() calls of '
+                      f'oracle/model_oracle.py (torch {torch.__version__} fp32, {cores} threads), '
+                      f'{frames} valid frames per call'}, total / len(times) * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    cb, ms = cpu_generate_rate(steps, warmup)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'global_batch': B * args.gpus, 'phonemes': T,
+                       'note': 'CPU arm: every step is the bounded sample described in cpu_baseline.sample'},
+            'cpu_baseline': cb,
+            'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, uuid: str):
+        self.tmp = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', uuid, f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.split(',') for r in Path(self.tmp.name).read_text().strip().splitlines() if r.count(',') >= 6]
+        os.unlink(self.tmp.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                out['sm_max_mhz'] = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.strip().lower().startswith('active'):
+                    reasons.add(name)
+        if sm:
+            out['sm_mhz'] = statistics.median(sm)
+            out['samples'] = len(sm)
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def collect_profile(lib, steps):
+    import ctypes as C
+    n = lib.ftb_profile_families()
+    ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+    ln = (C.c_longlong * n)()
+    from forwardtacotron_b200 import _lib
+    _lib.check(lib.ftb_profile_collect(ms, fl, by, ln))
+    fams = []
+    for i in range(n):
+        if ln[i]:
+            fams.append({'name': lib.ftb_profile_family_name(i).decode(), 'ms_per_step': ms[i] / steps,
+                         'launches_per_step': ln[i] / steps, 'flops_per_step': fl[i] / steps,
+                         'bytes_per_step': by[i] / steps})
+    return sorted(fams, key=lambda f: -f['ms_per_step'])
+
+
+def roofline_of(fam, pk):
+    hbm_bound = fam['name'] in ('length_regulator', 'elementwise', 'stft_mel')
+    sec = fam['ms_per_step'] / 1e3
+    ncu = {}
+    p = ROOT / 'profiles' / 'ncu_traffic.json'  # per-launch DRAM bytes from the committed ncu --set full capture
+    if p.exists():
+        ncu = json.loads(p.read_text())
+    if hbm_bound:
+        ach = fam['bytes_per_step'] / sec / 1e9
+        return {'kernel': fam['name'], 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s',
+                'frac': ach / pk['hbm'], 'traffic': ncu.get(fam['name']), 'peak_source': pk['src']}
+    ach = fam['flops_per_step'] / sec / 1e12
+    return {'kernel': fam['name'], 'bound': 'tensor', 'achieved': ach, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
+            'frac': ach / pk['tensor'], 'traffic': ncu.get(fam['name']), 'peak_source': pk['src'] + ' (sustained bf16)'}
+
+
+def stft_extra(torch, dev, pk):
+    """Second headline of BASELINE.json: STFT->log-mel audio-seconds/s (clips resident in HBM, > L2)."""
+    from forwardtacotron_b200.utils import synth
+    from forwardtacotron_b200.utils.config import default_config
+    from forwardtacotron_b200.utils.dsp import DSP
+    dsp = DSP.from_config(default_config())
+    audio, offs = synth.synthetic_audio(320, seed=7)          # ~42 M samples = 169 MB of fp32 > 126 MB L2
+    a = audio.to(dev)
+    for _ in range(3):
+        out, fo = dsp.wav_to_mel_packed(a, offs)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        out, fo = dsp.wav_to_mel_packed(a, offs)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    secs = a.numel() / 22050.0
+    nbytes = a.numel() * 4 + out.numel() * 4
+    return {'metric': 'stft_mel_audio_seconds_per_s', 'value': secs / (ms / 1e3), 'unit': 'audio-s/s',
+            'ms_per_step': ms, 'clips': 320, 'audio_seconds': secs,
+            'roofline': {'kernel': 'stft_mel', 'bound': 'hbm', 'achieved': nbytes / (ms / 1e3) / 1e9,
+                         'peak': pk['hbm'], 'unit': 'GB/s', 'frac': nbytes / (ms / 1e3) / 1e9 / pk['hbm'],
+                         'note': 'includes the host-side offset upload of wav_to_mel_packed'}}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from forwardtacotron_b200 import _lib
+    from forwardtacotron_b200.utils import synth
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the ftb200 kernels have no CPU fallback')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.lib()
+    pk = peaks()
+
+    model, _ = synth.synthetic_model('forward_tacotron')
+    model = model.to(dev)
+    x_host = synth.synthetic_tokens(B, T, seed=1 + rank).pin_memory()      # a different batch per rank
+    x = x_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    out = None
+    for _ in range(max(args.warmup, 3)):
+        out = model.generate(x)
+    frames_per_step = int(out['mel_len'].sum().item())
+    L = int(out['mel'].shape[-1])
+    ws_bytes = int(lib.ftb_ft_workspace_bytes(model._handle, B, T, L))
+
+    # ---- timed region: K steps, inputs resident in HBM, CUDA events on the launching stream
+    sampler = ClockSampler('GPU-' + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
+    lib.ftb_profile_enable(1)
+    launches0 = lib.ftb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = model.generate(x)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.ftb_launch_count() - launches0
+    fams = collect_profile(lib, args.steps)
+    lib.ftb_profile_enable(0)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end through the public API with HOST buffers: pinned H2D of the tokens + D2H of the result
+    mel_host = torch.empty(out['mel_post'].shape, dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        o = model.generate(x_host.to(dev, non_blocking=True))
+        mel_host.copy_(o['mel_post'], non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o = model.generate(x_host.to(dev, non_blocking=True))
+        mel_host.copy_(o['mel_post'], non_blocking=True)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+
+    t = torch.tensor([ms_total, e2e_ms, float(frames_per_step)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, e2e_ms, frames_all = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        frames_all = float(frames_per_step)
+
+    if rank == 0:
+        value = frames_all * args.steps / (ms_total / 1e3)
+        e2e_value = frames_all * args.steps / (e2e_ms / 1e3)
+        top = fams[0]
+        kernels = [dict(f, share=f['ms_per_step'] / (ms_total / args.steps)) for f in fams]
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'global_batch': B * world, 'phonemes': T, 'mel_frames_padded_L': L,
+                       'valid_frames_per_gpu_step': frames_per_step, 'parallelism': f'utterance-sharded x{world}',
+                       'numerics': 'bf16 tcgen05 GEMMs, fp32 accumulate/state; duration predictor fp32',
+                       'l2': f'per-step working set {ws_bytes / 1e9:.2f} GB >> 126 MB L2, no explicit flush'},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 8,
+                    'd2h_bytes_per_step': mel_host.numel() * 4 + B * 4, 'ms_per_step': e2e_ms / args.steps},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': roofline_of(top, pk),
+            'kernels': kernels,
+        }
+        if world == 1:
+            try:
+                line['extra'] = {'stft_mel': stft_extra(torch, dev, pk)}
+            except Exception as e:  # the headline line must still be printed
+                line['extra'] = {'stft_mel': {'error': str(e)}}
+            cb, _ = cpu_generate_rate(3, 1)
+            line['cpu_baseline'] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,4 +1,6 @@
 // Error plumbing and device checks of the ftb200 C ABI.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ftb {
@@ -23,10 +25,101 @@ int sm_count() {
   return n;
 }
 
+// ---- launch counter + profiler --------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec {
+  int fam;
+  cudaEvent_t a, b;
+  double flops, bytes;
+  long long launches_before, launches_after;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_pool;
+
+static cudaEvent_t take_event() {
+  if (!g_pool.empty()) {
+    cudaEvent_t e = g_pool.back();
+    g_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(int family, double flops, double bytes, cudaStream_t stream) : idx(-1), s(stream) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.fam = family;
+  r.a = take_event();
+  r.b = take_event();
+  r.flops = flops;
+  r.bytes = bytes;
+  r.launches_before = g_launches.load();
+  r.launches_after = r.launches_before;
+  cudaEventRecord(r.a, s);
+  idx = (int)g_recs.size();
+  g_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  cudaEventRecord(g_recs[idx].b, s);
+  g_recs[idx].launches_after = g_launches.load();
+}
+
+static const char* kFamilyNames[FAM_COUNT] = {"conv_gemm_tcgen05", "conv_gemm_f32",   "rnn_lstm_cluster",
+                                              "rnn_gru_cluster",   "rnn_gru_small",   "length_regulator",
+                                              "attention",         "elementwise",     "stft_mel"};
+
 }  // namespace ftb
+
+extern "C" long long ftb_launch_count(void) { return ftb::g_launches.load(); }
+extern "C" int ftb_profile_families(void) { return ftb::FAM_COUNT; }
+extern "C" const char* ftb_profile_family_name(int i) {
+  return (i >= 0 && i < ftb::FAM_COUNT) ? ftb::kFamilyNames[i] : "";
+}
+extern "C" int ftb_profile_enable(int on) {
+  using namespace ftb;
+  for (ProfRec& r : g_recs) {
+    g_pool.push_back(r.a);
+    g_pool.push_back(r.b);
+  }
+  g_recs.clear();
+  g_prof_on = on != 0;
+  return FTB_OK;
+}
+// Synchronises the recorded events and accumulates per family: ms, flops, bytes, kernel launches.
+extern "C" int ftb_profile_collect(double* ms, double* flops, double* bytes, long long* launches) {
+  using namespace ftb;
+  FTB_REQUIRE(ms && flops && bytes && launches, FTB_ERR_INVALID, "ftb_profile_collect: bad arguments");
+  for (int i = 0; i < FAM_COUNT; ++i) ms[i] = flops[i] = bytes[i] = 0.0, launches[i] = 0;
+  for (ProfRec& r : g_recs) {
+    FTB_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    FTB_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.fam] += t;
+    flops[r.fam] += r.flops;
+    bytes[r.fam] += r.bytes;
+    launches[r.fam] += r.launches_after - r.launches_before;
+  }
+  return FTB_OK;
+}
 
 extern "C" const char* ftb_last_error(void) { return ftb::get_error(); }
 extern "C" int ftb_abi_version(void) { return FTB_ABI_VERSION; }
+extern "C" int ftb_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(ftb_tensor);
+    case 1: return (int)sizeof(ftb_conv_desc);
+    case 2: return (int)sizeof(ftb_mel_config);
+    case 3: return (int)sizeof(ftb_ft_config);
+    case 4: return (int)sizeof(ftb_fp_config);
+  }
+  return -1;
+}
 
 extern "C" int ftb_device_check(int device, int* sm_count, int* cc_major, int* cc_minor) {
   int n = 0;

@@ -43,8 +43,35 @@ const char* get_error();
   } while (0)
 
 // Checks the launch that was just issued (launch-config errors only; async
-// faults surface at the next synchronising call of the caller).
-#define FTB_CHECK_LAUNCH() FTB_CHECK_CUDA(cudaGetLastError())
+// faults surface at the next synchronising call of the caller) and counts it.
+#define FTB_CHECK_LAUNCH()               \
+  do {                                   \
+    FTB_CHECK_CUDA(cudaGetLastError());  \
+    ::ftb::count_launch();               \
+  } while (0)
+
+void count_launch();
+
+// ---- lightweight per-kernel-family profiler (off by default; bench.py turns it on) ----------
+enum Family {
+  FAM_GEMM_TC = 0,   // tcgen05 implicit-GEMM conv / linear
+  FAM_GEMM_F32,      // fp32 SIMT implicit-GEMM (duration predictor, validation mode)
+  FAM_RNN_LSTM,      // decoder LSTM recurrence (cluster kernel)
+  FAM_RNN_GRU,       // CBHG GRU recurrence (cluster kernel)
+  FAM_RNN_SMALL,     // predictor GRU recurrence (one CTA per row)
+  FAM_LENGTH,        // length regulator plan + expand
+  FAM_ATTENTION,
+  FAM_ELEMENTWISE,
+  FAM_STFT_MEL,
+  FAM_COUNT
+};
+// RAII: CUDA events around the launches issued inside the scope, on the launching stream.
+struct ProfScope {
+  int idx;
+  cudaStream_t s;
+  ProfScope(int family, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+};
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -81,24 +81,24 @@ __global__ void cond_add_kernel(T* __restrict__ x, const float* __restrict__ pit
 }
 
 // ---- predictor head: Linear(C -> 1) / alpha, one warp per row (forward_tacotron.py:54-55) ---
-__global__ void head1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                             float inv_alpha_is_div, float alpha, float* __restrict__ out, int64_t rows, int C) {
+template <typename T>
+__global__ void head1_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                             float alpha, float* __restrict__ out, int64_t rows, int C) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   float s = 0.f;
-  for (int c = lane; c < C; c += 32) s = fmaf(x[r * C + c], w[c], s);
+  for (int c = lane; c < C; c += 32) s = fmaf(ActIO<T>::load(x + r * C + c), w[c], s);
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) out[r] = (s + b[0]) / alpha;  // true division like `x / alpha`
-  (void)inv_alpha_is_div;
 }
 
 // ---- LayerNorm over the last dim (eps 1e-5), optional residual: y = LN(x + r) ---------------
 // one warp per row; C <= 1024.  (models/fast_pitch.py:70-71,84,91,116,128)
 template <typename T>
-__global__ void layernorm_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, T* __restrict__ y, int64_t rows, int C) {
+__global__ void layernorm_kernel(const T* x, const T* res, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, T* y, int64_t rows, int C) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -182,6 +182,7 @@ static inline int ew_blocks(int64_t n) { return (int)std::min<int64_t>(cdiv(n, 2
 template <typename T>
 int embed(const int64_t* tok, const float* table, T* out, int64_t rows, int C, int ldo, int num_chars,
           cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   embed_kernel<T><<<ew_blocks(rows * C), 256, 0, s>>>(tok, table, out, rows, C, ldo, num_chars);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
@@ -191,6 +192,7 @@ template int embed<__nv_bfloat16>(const int64_t*, const float*, __nv_bfloat16*, 
 
 template <typename T>
 int maxpool_inplace(T* x, int B, int S, int C, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   maxpool_inplace_kernel<T><<<ew_blocks((int64_t)B * C), 256, 0, s>>>(x, B, S, C);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
@@ -200,6 +202,7 @@ template int maxpool_inplace<__nv_bfloat16>(__nv_bfloat16*, int, int, int, cudaS
 
 template <typename T>
 int highway_mix(const float* t12, const T* x, T* y, int64_t M, int C, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   highway_mix_kernel<T><<<ew_blocks(M * C), 256, 0, s>>>(t12, x, y, M, C);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
@@ -211,6 +214,7 @@ template int highway_mix<__nv_bfloat16>(const float*, const __nv_bfloat16*, __nv
 template <typename T>
 int cond_add(T* x, const float* pitch, const float* energy, const float* wp, const float* bp, const float* we,
              const float* be, float ps, float es, int B, int Tn, int C, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   cond_add_kernel<T><<<ew_blocks((int64_t)B * Tn * C), 256, 0, s>>>(x, pitch, energy, wp, bp, we, be, ps, es, B, Tn, C);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
@@ -220,16 +224,21 @@ template int cond_add<float>(float*, const float*, const float*, const float*, c
 template int cond_add<__nv_bfloat16>(__nv_bfloat16*, const float*, const float*, const float*, const float*,
                                      const float*, const float*, float, float, int, int, int, cudaStream_t);
 
-int head1(const float* x, const float* w, const float* b, float alpha, float* out, int64_t rows, int C,
-          cudaStream_t s) {
-  head1_kernel<<<cdiv(rows, 8), 256, 0, s>>>(x, w, b, 0.f, alpha, out, rows, C);
+template <typename T>
+int head1(const T* x, const float* w, const float* b, float alpha, float* out, int64_t rows, int C, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
+  head1_kernel<T><<<cdiv(rows, 8), 256, 0, s>>>(x, w, b, alpha, out, rows, C);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }
+template int head1<float>(const float*, const float*, const float*, float, float*, int64_t, int, cudaStream_t);
+template int head1<__nv_bfloat16>(const __nv_bfloat16*, const float*, const float*, float, float*, int64_t, int,
+                                  cudaStream_t);
 
 template <typename T>
 int layernorm(const T* x, const T* res, const float* gamma, const float* beta, T* y, int64_t rows, int C,
               cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   FTB_REQUIRE(C <= 1024, FTB_ERR_UNSUPPORTED, "layernorm: C=%d > 1024", C);
   layernorm_kernel<T><<<cdiv(rows, 8), 256, 0, s>>>(x, res, gamma, beta, y, rows, C);
   FTB_CHECK_LAUNCH();
@@ -242,6 +251,7 @@ template int layernorm<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*
 
 template <typename T>
 int posenc_add(T* x, const float* pe, const float* scale, int B, int S, int E, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   posenc_add_kernel<T><<<ew_blocks((int64_t)B * S * E), 256, 0, s>>>(x, pe, scale, B, S, E);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
@@ -251,22 +261,26 @@ template int posenc_add<__nv_bfloat16>(__nv_bfloat16*, const float*, const float
 
 int bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* shift, int C,
             cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   bn_fold_kernel<<<cdiv(C, 128), 128, 0, s>>>(w, b, mean, var, scale, shift, C);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }
 int rnn_bias(const float* b_ih, const float* b_hh, float* out, int n, int fold, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   rnn_bias_kernel<<<cdiv(n, 128), 128, 0, s>>>(b_ih, b_hh, out, n, fold);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }
 int copy_f32(const float* in, float* out, int64_t n, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   copy_f32_kernel<<<ew_blocks(n), 256, 0, s>>>(in, out, n);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }
 template <typename T>
 int cast_rows(const float* in, T* out, int64_t rows, int C, int ldi, int ldo, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   cast_kernel<T><<<ew_blocks(rows * ldo), 256, 0, s>>>(in, out, rows, C, ldi, ldo);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
@@ -276,6 +290,7 @@ template int cast_rows<__nv_bfloat16>(const float*, __nv_bfloat16*, int64_t, int
 
 template <typename T>
 int to_f32(const T* in, float* out, int64_t n, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   to_f32_kernel<T><<<ew_blocks(n), 256, 0, s>>>(in, out, n);
   FTB_CHECK_LAUNCH();
   return FTB_OK;

@@ -1,0 +1,287 @@
+// FastPitch.generate (models/fast_pitch.py:286-340) as a native runtime.
+//   stage A  ftb_fp_predict    : three transformer SeriesPredictors (no padding mask) + duration fallback
+//   stage B  ftb_fp_synthesize : embedding -> prenet transformer (key mask x == 0) -> conditioning ->
+//                                LengthRegulator -> postnet transformer (no mask) -> lin
+// FFT block (post-LN, :76-92): x = LN1(x + out_proj(attn(qkv(x)))); x = LN2(x + conv2(relu(conv1(x)))).
+// GEMM-shaped work (qkv / out projections, k9 and k1 convs, lin) goes through the shared implicit-GEMM
+// kernels with bias / ReLU / residual fused in the epilogue; attention is attention.cu.
+#include "model_common.cuh"
+
+namespace ftb {
+
+struct FftBlockW {
+  Layer qkv, out_proj, conv1, conv2;
+  const float *n1w, *n1b, *n2w, *n2b;
+};
+struct TransformerW {  // ForwardTransformer, models/fast_pitch.py:95-130
+  int E = 0, dfft = 0, heads = 0;
+  const float* pe = nullptr;     // (max_len, 1, E) buffer, read in place
+  const float* scale = nullptr;  // (1)
+  int max_len = 0;
+  std::vector<FftBlockW> layers;
+  const float *nw = nullptr, *nb = nullptr;
+  bool f32_only = false;
+};
+struct FpSeriesW {  // SeriesPredictor, models/fast_pitch.py:133-160
+  const float* emb = nullptr;
+  TransformerW tr;
+  const float *lin_w = nullptr, *lin_b = nullptr;
+};
+
+}  // namespace ftb
+
+struct ftb_fp_handle : ftb::ModelBase {
+  ftb_fp_config cfg;
+  ftb::FpSeriesW series[3];
+  const float* embedding = nullptr;
+  ftb::TransformerW prenet, postnet;
+  const float *pitch_w = nullptr, *pitch_b = nullptr, *energy_w = nullptr, *energy_b = nullptr;
+  ftb::Layer lin;
+  bool bf16_mode() const { return cfg.gemm_mode == 0; }
+};
+
+namespace ftb {
+
+static int build_transformer(ftb_fp_handle* h, TransformerW& W, const std::string& p, int E, int dfft, int layers,
+                             int heads, int k1, int k2, bool f32_only) {
+  W.E = E;
+  W.dfft = dfft;
+  W.heads = heads;
+  W.f32_only = f32_only;
+  const bool w16 = h->bf16_mode() && !f32_only, w32 = !w16;
+  FTB_REQUIRE(heads > 0 && E % heads == 0 && (E / heads == 64 || E / heads == 128), FTB_ERR_UNSUPPORTED,
+              "%s: head dim %d not built (64, 128)", p.c_str(), heads ? E / heads : 0);
+  FTB_REQUIRE(E % 64 == 0 && dfft % 64 == 0 && E <= 1024, FTB_ERR_UNSUPPORTED, "%s: d_model/d_fft must be multiples of 64",
+              p.c_str());
+  FTB_REQUIRE(h->has(p + ".pos_encoder.pe"), FTB_ERR_MISSING, "state_dict entry '%s.pos_encoder.pe' is missing", p.c_str());
+  const ftb_tensor& pe = h->sd[p + ".pos_encoder.pe"];
+  FTB_REQUIRE(pe.dtype == FTB_F32 && pe.ndim == 3 && pe.shape[1] == 1 && pe.shape[2] == E, FTB_ERR_MISSING,
+              "'%s.pos_encoder.pe' must be float32 (max_len, 1, %d)", p.c_str(), E);
+  W.pe = (const float*)pe.data;
+  W.max_len = (int)pe.shape[0];
+  FTB_TRY(h->get(p + ".pos_encoder.scale", {1}, &W.scale));
+  W.layers.resize(layers);
+  for (int i = 0; i < layers; ++i) {
+    const std::string q = p + ".layers." + std::to_string(i);
+    FftBlockW& L = W.layers[i];
+    FTB_TRY(h->make_conv(L.qkv, q + ".self_attn.in_proj_weight", 3 * E, E, 1, 0, false, "", q + ".self_attn.in_proj_bias",
+                         w32, w16));
+    FTB_TRY(h->make_conv(L.out_proj, q + ".self_attn.out_proj.weight", E, E, 1, 0, false, "",
+                         q + ".self_attn.out_proj.bias", w32, w16));
+    FTB_TRY(h->make_conv(L.conv1, q + ".conv1.weight", dfft, E, k1, k1 / 2, true, "", q + ".conv1.bias", w32, w16));
+    FTB_TRY(h->make_conv(L.conv2, q + ".conv2.weight", E, dfft, k2, k2 / 2, false, "", q + ".conv2.bias", w32, w16));
+    FTB_TRY(h->get(q + ".norm1.weight", {E}, &L.n1w));
+    FTB_TRY(h->get(q + ".norm1.bias", {E}, &L.n1b));
+    FTB_TRY(h->get(q + ".norm2.weight", {E}, &L.n2w));
+    FTB_TRY(h->get(q + ".norm2.bias", {E}, &L.n2b));
+  }
+  FTB_TRY(h->get(p + ".norm.weight", {E}, &W.nw));
+  FTB_TRY(h->get(p + ".norm.bias", {E}, &W.nb));
+  return FTB_OK;
+}
+
+template <typename T>
+struct TrBufs {
+  T *qkv, *ctx, *a, *f1;
+};
+template <typename T>
+static TrBufs<T> plan_tr(Arena& A, const TransformerW& W, int B, int S) {
+  TrBufs<T> w;
+  const int64_t M = (int64_t)B * S;
+  w.qkv = A.take<T>(M * 3 * W.E);
+  w.ctx = A.take<T>(M * W.E);
+  w.a = A.take<T>(M * W.E);
+  w.f1 = A.take<T>(M * W.dfft);
+  return w;
+}
+
+// x (B,S,E) is transformed in place.  mask_tokens: (B,S) ids, keys with id 0 are ignored; or nullptr.
+template <typename T>
+static int run_transformer(ftb_fp_handle* h, TransformerW& W, T* x, const int64_t* mask_tokens, int B, int S, Arena& A,
+                           cudaStream_t s) {
+  FTB_REQUIRE(S <= W.max_len, FTB_ERR_INVALID, "The size of tensor a (%d) must match the size of tensor b (%d) at "
+              "non-singleton dimension 0", S, W.max_len);
+  const int64_t mark = A.mark();
+  TrBufs<T> w = plan_tr<T>(A, W, B, S);
+  FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for ForwardTransformer");
+  const int64_t M = (int64_t)B * S;
+  const int E = W.E;
+  FTB_TRY(posenc_add<T>(x, W.pe, W.scale, B, S, E, s));
+  for (FftBlockW& L : W.layers) {
+    FTB_TRY(h->gemm<T>(L.qkv, x, E, B, S, act_out(w.qkv, 3 * E), nullptr, 0, 1.f, s));
+    FTB_TRY(attention<T>(w.qkv, mask_tokens, w.ctx, B, S, E, W.heads, s));
+    FTB_TRY(h->gemm<T>(L.out_proj, w.ctx, E, B, S, act_out(w.a, E), x, E, 1.f, s));  // + residual
+    FTB_TRY(layernorm<T>(w.a, nullptr, L.n1w, L.n1b, x, M, E, s));
+    FTB_TRY(h->gemm<T>(L.conv1, x, E, B, S, act_out(w.f1, W.dfft), nullptr, 0, 1.f, s));  // + bias, ReLU
+    FTB_TRY(h->gemm<T>(L.conv2, w.f1, W.dfft, B, S, act_out(w.a, E), x, E, 1.f, s));      // + bias + residual
+    FTB_TRY(layernorm<T>(w.a, nullptr, L.n2w, L.n2b, x, M, E, s));
+    h->launches += 3;
+  }
+  FTB_TRY(layernorm<T>(x, nullptr, W.nw, W.nb, x, M, E, s));
+  h->launches += 2;
+  A.reset(mark);
+  return FTB_OK;
+}
+
+template <typename T>
+static int run_fp_series(ftb_fp_handle* h, FpSeriesW& P, const int64_t* tok, int B, int Tn, float alpha, float* out,
+                         Arena& A, cudaStream_t s) {
+  const int64_t mark = A.mark();
+  const int64_t M = (int64_t)B * Tn;
+  T* x = A.take<T>(M * P.tr.E);
+  FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for SeriesPredictor");
+  FTB_TRY(embed<T>(tok, P.emb, x, M, P.tr.E, P.tr.E, h->cfg.num_chars, s));
+  FTB_TRY(run_transformer<T>(h, P.tr, x, nullptr, B, Tn, A, s));
+  FTB_TRY(head1<T>(x, P.lin_w, P.lin_b, alpha, out, M, P.tr.E, s));
+  h->launches += 2;
+  A.reset(mark);
+  return FTB_OK;
+}
+
+template <typename T>
+static int run_fp_synthesize(ftb_fp_handle* h, const int64_t* tok, const int32_t* cum, const float* pitch,
+                             const float* energy, int B, int Tn, int L, float* mel, Arena& A, cudaStream_t s) {
+  const ftb_fp_config& c = h->cfg;
+  const int E = c.d_model;
+  const int64_t MT = (int64_t)B * Tn, ML = (int64_t)B * L;
+  T* x = A.take<T>(MT * E);
+  T* up = A.take<T>(ML * E);
+  FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for synthesize");
+  FTB_TRY(embed<T>(tok, h->embedding, x, MT, E, E, c.num_chars, s));
+  FTB_TRY(run_transformer<T>(h, h->prenet, x, tok, B, Tn, A, s));
+  FTB_TRY(cond_add<T>(x, pitch, energy, h->pitch_w, h->pitch_b, h->energy_w, h->energy_b, c.pitch_strength,
+                      c.energy_strength, B, Tn, E, s));
+  FTB_TRY(ftb_length_expand(x, cum, up, B, Tn, L, E, (int)sizeof(T), s));
+  FTB_TRY(run_transformer<T>(h, h->postnet, up, nullptr, B, L, A, s));
+  Out o;
+  o.t = mel;
+  FTB_TRY(h->gemm<T>(h->lin, up, E, B, L, o, nullptr, 0, 1.f, s));
+  h->launches += 3;
+  return FTB_OK;
+}
+
+template <typename T>
+static int64_t fp_bytes(const ftb_fp_handle* h, int B, int Tn, int L) {
+  int64_t best = 0;
+  for (int i = 0; i < 3; ++i) {
+    Arena A(nullptr, 0);
+    A.take<char>(256);
+    if (h->series[i].tr.f32_only || !h->bf16_mode()) {
+      A.take<float>((int64_t)B * Tn * h->series[i].tr.E);
+      plan_tr<float>(A, h->series[i].tr, B, Tn);
+    } else {
+      A.take<T>((int64_t)B * Tn * h->series[i].tr.E);
+      plan_tr<T>(A, h->series[i].tr, B, Tn);
+    }
+    best = std::max(best, A.mark());
+  }
+  if (L > 0) {
+    Arena A(nullptr, 0);
+    A.take<T>((int64_t)B * Tn * h->cfg.d_model);
+    A.take<T>((int64_t)B * L * h->cfg.d_model);
+    const int64_t base = A.mark();
+    plan_tr<T>(A, h->prenet, B, Tn);
+    const int64_t pre = A.mark();
+    A.reset(base);
+    plan_tr<T>(A, h->postnet, B, L);
+    best = std::max(best, std::max(pre, A.mark()));
+  }
+  return best + 4096;
+}
+
+}  // namespace ftb
+
+using namespace ftb;
+
+extern "C" int ftb_fp_create(const ftb_fp_config* cfg, const ftb_tensor* tensors, int n_tensors, int device,
+                             ftb_fp_handle** out) {
+  FTB_REQUIRE(cfg && tensors && out && n_tensors > 0, FTB_ERR_INVALID, "ftb_fp_create: bad arguments");
+  FTB_TRY(ftb_device_check(device, nullptr, nullptr, nullptr));
+  FTB_CHECK_CUDA(cudaSetDevice(device));
+  ftb_fp_handle* h = new ftb_fp_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  for (int i = 0; i < n_tensors; ++i) h->sd[tensors[i].name] = tensors[i];
+  const ftb_fp_config& c = h->cfg;
+  auto build_series = [&](FpSeriesW& P, const std::string& p, int E, int heads, int layers, int dfft, bool f32) -> int {
+    FTB_TRY(h->get(p + ".embedding.weight", {c.num_chars, E}, &P.emb));
+    FTB_TRY(build_transformer(h, P.tr, p + ".transformer", E, dfft, layers, heads, c.conv1_kernel, c.conv2_kernel, f32));
+    FTB_TRY(h->get(p + ".lin.weight", {1, E}, &P.lin_w));
+    FTB_TRY(h->get(p + ".lin.bias", {1}, &P.lin_b));
+    return FTB_OK;
+  };
+  auto build = [&]() -> int {
+    FTB_TRY(build_series(h->series[0], "dur_pred", c.durpred_d_model, c.durpred_n_heads, c.durpred_layers,
+                         c.durpred_d_fft, true));
+    FTB_TRY(build_series(h->series[1], "pitch_pred", c.pitch_d_model, c.pitch_n_heads, c.pitch_layers, c.pitch_d_fft,
+                         false));
+    FTB_TRY(build_series(h->series[2], "energy_pred", c.energy_d_model, c.energy_n_heads, c.energy_layers,
+                         c.energy_d_fft, false));
+    FTB_TRY(h->get("embedding.weight", {c.num_chars, c.d_model}, &h->embedding));
+    FTB_TRY(build_transformer(h, h->prenet, "prenet", c.d_model, c.prenet_fft, c.prenet_layers, c.prenet_heads,
+                              c.conv1_kernel, c.conv2_kernel, false));
+    FTB_TRY(build_transformer(h, h->postnet, "postnet", c.d_model, c.postnet_fft, c.postnet_layers, c.postnet_heads,
+                              c.conv1_kernel, c.conv2_kernel, false));
+    FTB_TRY(h->get("pitch_proj.weight", {c.d_model, 1, 3}, &h->pitch_w));
+    FTB_TRY(h->get("pitch_proj.bias", {c.d_model}, &h->pitch_b));
+    FTB_TRY(h->get("energy_proj.weight", {c.d_model, 1, 3}, &h->energy_w));
+    FTB_TRY(h->get("energy_proj.bias", {c.d_model}, &h->energy_b));
+    const bool w16 = h->bf16_mode(), w32 = !w16;
+    FTB_TRY(h->make_conv(h->lin, "lin.weight", c.n_mels, c.d_model, 1, 0, false, "", "lin.bias", w32, w16));
+    FTB_CHECK_CUDA(cudaStreamSynchronize(h->prep));
+    return FTB_OK;
+  };
+  const int st = build();
+  if (st != FTB_OK) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return FTB_OK;
+}
+
+extern "C" void ftb_fp_destroy(ftb_fp_handle* h) { delete h; }
+
+extern "C" int64_t ftb_fp_workspace_bytes(const ftb_fp_handle* h, int B, int T, int L) {
+  if (!h || B <= 0 || T <= 0) return -1;
+  return h->bf16_mode() ? fp_bytes<bf16>(h, B, T, L) : fp_bytes<float>(h, B, T, L);
+}
+
+extern "C" int ftb_fp_predict(ftb_fp_handle* h, const int64_t* tokens, int B, int T, float alpha, float* dur,
+                              float* pitch, float* energy, void* workspace, int64_t workspace_bytes, void* stream) {
+  FTB_REQUIRE(h && tokens && dur && pitch && energy && workspace && B > 0 && T > 0, FTB_ERR_INVALID,
+              "ftb_fp_predict: bad arguments");
+  FTB_REQUIRE(alpha != 0.f, FTB_ERR_INVALID, "alpha must be non-zero");
+  FTB_REQUIRE(workspace_bytes >= 256, FTB_ERR_WORKSPACE, "workspace too small");
+  h->launches = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* outs[3] = {dur, pitch, energy};
+  for (int i = 0; i < 3; ++i) {
+    Arena A(ws + 256, workspace_bytes - 256);
+    const float a = i == 0 ? alpha : 1.f;
+    if (h->series[i].tr.f32_only || !h->bf16_mode())
+      FTB_TRY(run_fp_series<float>(h, h->series[i], tokens, B, T, a, outs[i], A, s));
+    else
+      FTB_TRY(run_fp_series<bf16>(h, h->series[i], tokens, B, T, a, outs[i], A, s));
+    if (i == 0) {
+      FTB_TRY(ftb_duration_fallback(dur, (int64_t)B * T, ws, s));
+      h->launches += 2;
+    }
+  }
+  return FTB_OK;
+}
+
+extern "C" int ftb_fp_synthesize(ftb_fp_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
+                                 const float* energy, int B, int T, int L, float* mel, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  FTB_REQUIRE(h && tokens && cum && pitch && energy && mel && workspace, FTB_ERR_INVALID,
+              "ftb_fp_synthesize: bad arguments");
+  FTB_REQUIRE(B > 0 && T > 0 && L > 0, FTB_ERR_INVALID, "ftb_fp_synthesize: bad sizes B=%d T=%d L=%d", B, T, L);
+  h->launches = 0;
+  Arena A(workspace, workspace_bytes);
+  if (h->bf16_mode()) return run_fp_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, A, (cudaStream_t)stream);
+  return run_fp_synthesize<float>(h, tokens, cum, pitch, energy, B, T, L, mel, A, (cudaStream_t)stream);
+}
+
+extern "C" int ftb_fp_last_launch_count(const ftb_fp_handle* h) { return h ? h->launches : -1; }

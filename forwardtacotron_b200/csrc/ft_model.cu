@@ -170,7 +170,7 @@ static int run_series(ftb_ft_handle* h, SeriesW& P, const int64_t* tok, int B, i
   FTB_TRY(h->gemm<T>(P.conv[2], w.b, P.C, B, Tn, act_out(w.a, P.C), nullptr, 0, 1.f, s));
   FTB_TRY(h->gemm<T>(P.rnn.in, w.a, P.C, B, Tn, act_out(w.xg, 6 * P.H), nullptr, 0, 1.f, s));
   FTB_TRY(rnn_bidir(w.xg, P.rnn.w_hh, P.rnn.b_hn, w.ro, B, Tn, P.H, 0, 0, s));
-  FTB_TRY(head1(w.ro, P.lin_w, P.lin_b, alpha, out, M, 2 * P.H, s));
+  FTB_TRY(head1<float>(w.ro, P.lin_w, P.lin_b, alpha, out, M, 2 * P.H, s));
   h->launches += 3;
   A.reset(mark);
   return FTB_OK;

@@ -26,8 +26,8 @@ int highway_mix(const float* t12, const T* x, T* y, int64_t M, int C, cudaStream
 template <typename T>
 int cond_add(T* x, const float* pitch, const float* energy, const float* wp, const float* bp, const float* we,
              const float* be, float ps, float es, int B, int Tn, int C, cudaStream_t s);
-int head1(const float* x, const float* w, const float* b, float alpha, float* out, int64_t rows, int C,
-          cudaStream_t s);
+template <typename T>
+int head1(const T* x, const float* w, const float* b, float alpha, float* out, int64_t rows, int C, cudaStream_t s);
 template <typename T>
 int layernorm(const T* x, const T* res, const float* gamma, const float* beta, T* y, int64_t rows, int C,
               cudaStream_t s);

@@ -120,6 +120,7 @@ using namespace ftb;
 
 extern "C" int ftb_length_plan(float* dur, int32_t* cum, int32_t* total, int B, int T, void* stream) {
   FTB_REQUIRE(dur && cum && total && B > 0 && T > 0, FTB_ERR_INVALID, "ftb_length_plan: bad arguments");
+  ProfScope prof(FAM_LENGTH, 0.0, (double)B * T * 12, (cudaStream_t)stream);
   length_plan_kernel<<<B, kPlanThreads, 0, (cudaStream_t)stream>>>(dur, cum, total, T);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
@@ -135,6 +136,7 @@ extern "C" int ftb_length_expand(const void* x, const int32_t* cum, void* out, i
   const int64_t warps = (int64_t)B * (T + kZeroWarpsPerRow);
   const int blocks = cdiv(warps, kExpandWarps);
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof(FAM_LENGTH, 0.0, ((double)B * T + (double)B * L) * row_bytes + (double)B * T * 4, s);
   const uint4* xs = (const uint4*)x;
   uint4* os = (uint4*)out;
   const int nv = cdiv(chunks, 32);

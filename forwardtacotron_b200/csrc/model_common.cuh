@@ -183,6 +183,8 @@ struct ModelBase {
     d.out_bf16 = o.b16;
     d.out_t = o.t;
     ++launches;
+    ProfScope prof(std::is_same<T, float>::value ? FAM_GEMM_F32 : FAM_GEMM_TC,
+                   2.0 * B * S * (double)L.N * L.k * L.Cin, 0.0, s);
     if (std::is_same<T, float>::value) {
       d.residual_f32 = (const float*)residual;
       FTB_REQUIRE(L.w32, FTB_ERR_INVALID, "layer has no fp32 weights packed");

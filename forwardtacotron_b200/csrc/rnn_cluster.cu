@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
                        const float* __restrict__ b_hn,  // (2,H) GRU only
                        void* __restrict__ out, int B, int S, int out_bf16) {
   using C = RnnCfg<G, H, CL, BC>;
-  constexpr int HC = C::HC, R = C::R, NT = C::NT, KT = C::KT, HP = C::HP, PPT = C::PPT, PRE_LD = C::PRE_LD;
+  constexpr int HC = C::HC, NT = C::NT, KT = C::KT, HP = C::HP, PPT = C::PPT, PRE_LD = C::PRE_LD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [2][BC][HP]
   __nv_bfloat16* hstage = hbuf + 2 * BC * HP;                        // [BC][HC]
@@ -257,6 +257,7 @@ static int launch_rnn_cluster(const float* xg, const float* w_hh, const float* b
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16));
+  count_launch();
   return FTB_OK;
 }
 

@@ -96,6 +96,9 @@ int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out
 int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
               int out_bf16, cudaStream_t s) {
   FTB_REQUIRE(xg && w_hh && out && B > 0 && S > 0, FTB_ERR_INVALID, "rnn_bidir: bad arguments");
+  const int G = is_lstm ? 4 : 3;
+  ProfScope prof(is_lstm ? FAM_RNN_LSTM : (H >= 256 ? FAM_RNN_GRU : FAM_RNN_SMALL), 2.0 * 2 * B * S * (double)G * H * H,
+                 (double)B * S * 2 * G * H * 4 + (double)B * S * 2 * H * (out_bf16 ? 2 : 4), s);
   if (!is_lstm && H == 64) return launch_gru_small<64>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
   if (!is_lstm && H == 128) return launch_gru_small<128>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
   return rnn_cluster(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, s);

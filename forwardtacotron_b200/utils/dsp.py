@@ -1,0 +1,145 @@
+"""Drop-in ``DSP`` for the STFT -> log-mel path (reference: utils/dsp.py).
+
+Same constructor (all 19 ``dsp:`` keys of config.yaml:9-34 are kwargs, utils/dsp.py:14-57) and the
+same ``wav_to_mel(y, normalize=True) -> (n_mels, 1 + len(y)//hop) float32`` (utils/dsp.py:71-87).
+The arithmetic of the reference lives in librosa 0.7.2 on the CPU; here one fused sm_100a kernel does
+framing, Hann window, 1024-point real FFT, magnitude, Slaney mel filterbank and log-clamp.
+
+Beyond the reference surface, ``wav_to_mel_batch`` featurises many clips in ONE launch (the reference
+reaches the same thing with a multiprocessing pool over files, preprocess.py:129-139) and
+``wav_to_mel`` also accepts CUDA tensors so audio already resident in HBM is not copied back and forth.
+The file I/O, silence trimming, VAD, mu-law and Griffin-Lim helpers of the reference class are outside
+the hot path and are not re-implemented here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, List, Sequence, Union
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+class DSP:
+
+    def __init__(self, num_mels: int, sample_rate: int, hop_length: int, win_length: int, n_fft: int, fmin: float,
+                 fmax: float, peak_norm: bool, trim_start_end_silence: bool, trim_silence_top_db: int,
+                 pitch_max_freq: int, trim_long_silences: bool, vad_sample_rate: int, vad_window_length: float,
+                 vad_moving_average_width: float, vad_max_silence_length: int, bits: int, mu_law: bool,
+                 voc_mode: str, device: Union[str, torch.device, None] = None) -> None:
+        self.n_mels = num_mels
+        self.sample_rate = sample_rate
+        self.hop_length = hop_length
+        self.win_length = win_length
+        self.n_fft = n_fft
+        self.fmin = fmin
+        self.fmax = fmax
+        self.should_peak_norm = peak_norm
+        self.should_trim_start_end_silence = trim_start_end_silence
+        self.should_trim_long_silences = trim_long_silences
+        self.trim_silence_top_db = trim_silence_top_db
+        self.pitch_max_freq = pitch_max_freq
+        self.vad_sample_rate = vad_sample_rate
+        self.vad_window_length = vad_window_length
+        self.vad_moving_average_width = vad_moving_average_width
+        self.vad_max_silence_length = vad_max_silence_length
+        self.bits = bits
+        self.mu_law = mu_law
+        self.voc_mode = voc_mode
+        self._device = torch.device(device) if device is not None else None
+        self._handles: Dict[int, C.c_void_p] = {}
+
+    @classmethod
+    def from_config(cls, config: Dict[str, Any]) -> 'DSP':
+        return DSP(**config['dsp'])
+
+    # ------------------------------------------------------------------ native plumbing
+    def _handle(self, device: torch.device) -> C.c_void_p:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
+            cfg = _lib.MelConfig(int(self.sample_rate), int(self.n_fft), int(self.hop_length), int(self.win_length),
+                                 int(self.n_mels), float(self.fmin), float(self.fmax))
+            h = C.c_void_p()
+            _lib.check(_lib.lib().ftb_mel_create(C.byref(cfg), idx, C.byref(h)))
+            self._handles[idx] = h
+        return h
+
+    def __del__(self):
+        try:
+            for h in self._handles.values():
+                _lib.lib().ftb_mel_destroy(h)
+        except Exception:
+            pass
+
+    def _default_device(self) -> torch.device:
+        if self._device is not None:
+            return self._device
+        if not torch.cuda.is_available():
+            raise RuntimeError('DSP.wav_to_mel runs on sm_100a GPUs only and no CUDA device is available '
+                               '(there is no CPU fallback)')
+        return torch.device('cuda', torch.cuda.current_device())
+
+    def mel_filterbank(self) -> np.ndarray:
+        """The (n_mels, 1 + n_fft//2) float32 Slaney filterbank the kernel uses."""
+        h = self._handle(self._default_device())
+        fb = np.empty((self.n_mels, 1 + self.n_fft // 2), dtype=np.float32)
+        _lib.check(_lib.lib().ftb_mel_filterbank(h, fb.ctypes.data_as(C.c_void_p)))
+        return fb
+
+    # ------------------------------------------------------------------ the hot path
+    def wav_to_mel_packed(self, audio: torch.Tensor, clip_offsets: torch.Tensor, normalize: bool = True):
+        """audio: flat float32 CUDA tensor holding all clips back to back; clip_offsets: (n+1) int64 (CPU or
+        CUDA).  Returns (flat output, frame_offsets): clip i is ``out[80*fo[i]:80*fo[i+1]].view(80, -1)``."""
+        if not audio.is_cuda:
+            raise RuntimeError('wav_to_mel_packed expects audio resident on the GPU')
+        dev = audio.device
+        audio = audio.to(torch.float32).contiguous()
+        offs_cpu = clip_offsets.detach().to('cpu', torch.int64)
+        lens = offs_cpu[1:] - offs_cpu[:-1]
+        if int(lens.min()) < 1:
+            raise ValueError('empty clip')
+        frames = 1 + lens // self.hop_length  # librosa.stft with center=True
+        fo_cpu = torch.zeros(len(lens) + 1, dtype=torch.int64)
+        fo_cpu[1:] = torch.cumsum(frames, 0)
+        total = int(fo_cpu[-1])
+        offs = offs_cpu.to(dev, non_blocking=True)
+        fo = fo_cpu.to(dev, non_blocking=True)
+        out = torch.empty(self.n_mels * total, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ftb_mel_run(self._handle(dev), _lib.ptr(audio), _lib.ptr(offs), _lib.ptr(fo),
+                                              len(lens), total, _lib.ptr(out), int(bool(normalize)),
+                                              _lib.current_stream(dev)))
+        return out, fo_cpu
+
+    def wav_to_mel_batch(self, clips: Sequence[Union[np.ndarray, torch.Tensor]], normalize: bool = True) -> List:
+        """Many clips, one launch.  Returns a list of (n_mels, frames_i) arrays / tensors (numpy in -> numpy out)."""
+        dev = self._default_device()
+        as_numpy = not isinstance(clips[0], torch.Tensor)
+        ts = [torch.as_tensor(np.ascontiguousarray(c), dtype=torch.float32) if not isinstance(c, torch.Tensor)
+              else c.to(torch.float32) for c in clips]
+        dev = ts[0].device if ts[0].is_cuda else dev
+        offs = torch.zeros(len(ts) + 1, dtype=torch.int64)
+        offs[1:] = torch.cumsum(torch.tensor([t.numel() for t in ts]), 0)
+        flat = torch.cat([t.reshape(-1) for t in ts])
+        if not flat.is_cuda:
+            flat = flat.pin_memory().to(dev, non_blocking=True)
+        out, fo = self.wav_to_mel_packed(flat, offs, normalize)
+        res = []
+        host = out.cpu().numpy() if as_numpy else None
+        for i in range(len(ts)):
+            a, b = self.n_mels * int(fo[i]), self.n_mels * int(fo[i + 1])
+            res.append(host[a:b].reshape(self.n_mels, -1) if as_numpy else out[a:b].view(self.n_mels, -1))
+        return res
+
+    def wav_to_mel(self, y: Union[np.ndarray, torch.Tensor], normalize=True) -> Union[np.ndarray, torch.Tensor]:
+        return self.wav_to_mel_batch([y], normalize)[0]
+
+    def normalize(self, mel: np.ndarray) -> np.ndarray:
+        mel = np.clip(mel, a_min=1.e-5, a_max=None)
+        return np.log(mel)
+
+    def denormalize(self, mel: np.ndarray) -> np.ndarray:
+        return np.exp(mel)

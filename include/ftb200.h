@@ -57,6 +57,18 @@ typedef struct ftb_tensor {
 
 const char* ftb_last_error(void);
 int ftb_abi_version(void);
+/* sizeof() of the ABI structs as compiled (0 ftb_tensor, 1 ftb_conv_desc, 2 ftb_mel_config,
+ * 3 ftb_ft_config, 4 ftb_fp_config); bindings use it to verify their struct layout. */
+int ftb_struct_size(int which);
+/* Kernel launches issued by this library since it was loaded (bench bookkeeping). */
+long long ftb_launch_count(void);
+/* Optional per-kernel-family timing: CUDA events recorded on the launching stream around every launch
+ * while enabled (enable(1) also clears earlier records).  collect() synchronises the events and fills
+ * arrays of ftb_profile_families() entries: milliseconds, algorithmic FLOPs, algorithmic bytes, launches. */
+int ftb_profile_families(void);
+const char* ftb_profile_family_name(int family);
+int ftb_profile_enable(int on);
+int ftb_profile_collect(double* ms, double* flops, double* bytes, long long* launches);
 /* Number of SMs / compute capability of `device`; fails on anything but sm_100. */
 int ftb_device_check(int device, int* sm_count, int* cc_major, int* cc_minor);
 
@@ -106,8 +118,11 @@ typedef struct ftb_conv_desc {
 
 /* fp32 SIMT kernel (fp32-accurate: used for the duration predictor). */
 int ftb_conv_gemm_f32(const float* x, const float* w_packed, const ftb_conv_desc* d, void* stream);
-/* tcgen05 / TMA kernel: x (B,S,lda) bf16, w bf16 (Npad, k*Cin) with Cin % 64 == 0. */
+/* tcgen05 / TMA kernel: x (B,S,lda) bf16, w bf16 (N, k*Cin) with Cin % 64 == 0. */
 int ftb_conv_gemm_bf16(const void* x, const void* w_packed, const ftb_conv_desc* d, void* stream);
+/* Every mbarrier wait in the tcgen05 kernel is bounded so a protocol bug cannot hang the GPU;
+ * this returns how many waits gave up since the library was loaded (0 in a healthy run). */
+int ftb_tc_timeout_count(void);
 /* Pack a reference-layout conv weight (N, Cin, k) f32 into (Npad, k*Cin_pad) K-major
  * f32 or bf16 (zero padded). */
 int ftb_pack_conv_weight(const float* w, void* out, int N, int Cin, int k, int Npad, int Cin_pad,

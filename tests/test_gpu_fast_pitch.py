@@ -1,0 +1,51 @@
+"""FastPitch.generate on the GPU against the reference fixtures and the oracle (rows a10-a12)."""
+import pytest
+import torch
+
+from oracle import model_oracle as mo
+
+from util import assert_close, cpu_state_dict, cuda_model, load, near_tie_mask, rounded
+from forwardtacotron_b200.utils import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def check_against(model, x, want, alpha=1.0, pf=None, ef=None):
+    pf = pf or (lambda p: p)
+    ef = ef or (lambda e: e)
+    out = model.generate(x.cuda(), alpha=alpha, pitch_function=pf, energy_function=ef)
+    assert_close(out['dur'], want['dur'], 1e-3, 1e-4, 'dur')
+    assert_close(out['pitch'], want['pitch'], what='pitch')
+    assert_close(out['energy'], want['energy'], what='energy')
+    flips = rounded(out['dur']) != rounded(want['dur'])
+    if flips.any():
+        assert bool((near_tie_mask(want['dur']) | ~flips).all()), 'a duration differs that is not a rounding near-tie'
+        out = model.synthesize(x.cuda(), want['dur'].clone().cuda(), pf(out['pitch']), ef(out['energy']))
+    assert out['mel_post'] is out['mel']                       # same tensor, as in the reference (:339)
+    return out, assert_close(out['mel'], want['mel'], what='mel')
+
+
+@pytest.mark.parametrize('gemm_mode', [1, 0])
+@pytest.mark.parametrize('name,alpha,cb', [('fp_b2_t24', 1.0, True), ('fp_b3_t40_ragged', 0.9, False)])
+def test_reference_fixtures(name, alpha, cb, gemm_mode):
+    g = load(name)
+    model, _ = cuda_model('fast_pitch', gemm_mode)
+    pf = (lambda p: p * 1.2) if cb else None
+    ef = (lambda e: e + 0.1) if cb else None
+    out, res = check_against(model, g['x'], g, alpha, pf, ef)
+    print(name, 'gemm_mode', gemm_mode, res)
+
+
+@pytest.mark.parametrize('gemm_mode', [1, 0])
+def test_batch_against_oracle(gemm_mode):
+    model, _ = cuda_model('fast_pitch', gemm_mode)
+    x = synth.synthetic_tokens(6, 150, seed=3, ragged=True)
+    want = mo.fp_generate(cpu_state_dict(model), x, pitch_function=lambda p: p * 1.2, energy_function=lambda e: e + 0.1)
+    out, res = check_against(model, x, want, pf=lambda p: p * 1.2, ef=lambda e: e + 0.1)
+    print('fp B6xT150 gemm_mode', gemm_mode, res, 'L', out['mel'].shape[-1])
+
+
+def test_positional_table_limit_raises():
+    model, _ = cuda_model('fast_pitch', 0)
+    with pytest.raises(RuntimeError, match='must match the size'):
+        model.generate(torch.ones(1, 5001, dtype=torch.long, device='cuda'))

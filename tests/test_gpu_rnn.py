@@ -1,0 +1,72 @@
+"""GRU / LSTM recurrence kernels against the oracle's step-by-step restatement and ATen."""
+import pytest
+import torch
+
+from forwardtacotron_b200 import _lib
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+def make_sd(H, I, lstm, seed):
+    g = torch.Generator().manual_seed(seed)
+    G = 4 if lstm else 3
+    sd = {}
+    for sfx in ('', '_reverse'):
+        sd[f'rnn.weight_ih_l0{sfx}'] = (torch.rand(G * H, I, generator=g) * 2 - 1) / H ** 0.5
+        sd[f'rnn.weight_hh_l0{sfx}'] = (torch.rand(G * H, H, generator=g) * 2 - 1) / H ** 0.5
+        sd[f'rnn.bias_ih_l0{sfx}'] = (torch.rand(G * H, generator=g) * 2 - 1) / H ** 0.5
+        sd[f'rnn.bias_hh_l0{sfx}'] = (torch.rand(G * H, generator=g) * 2 - 1) / H ** 0.5
+    return sd
+
+
+def run_kernel(sd, x, H, lstm, out_bf16=False):
+    """Host does the input projection in fp32 (what the GEMM epilogue produces), the kernel the recurrence."""
+    B, S, _ = x.shape
+    G = 4 if lstm else 3
+    xg, whh, bhn = [], [], []
+    for sfx in ('', '_reverse'):
+        b = sd[f'rnn.bias_ih_l0{sfx}'].clone()
+        fold = G * H if lstm else 2 * H
+        b[:fold] += sd[f'rnn.bias_hh_l0{sfx}'][:fold]
+        xg.append(x @ sd[f'rnn.weight_ih_l0{sfx}'].T + b)
+        whh.append(sd[f'rnn.weight_hh_l0{sfx}'])
+        bhn.append(sd[f'rnn.bias_hh_l0{sfx}'][2 * H:3 * H])
+    xg = torch.stack(xg, dim=2).contiguous().cuda()                  # (B,S,2,G*H)
+    whh = torch.stack(whh).contiguous().cuda()
+    bhn = torch.stack(bhn).contiguous().cuda()
+    out = torch.empty(B, S, 2 * H, dtype=torch.bfloat16 if out_bf16 else torch.float32, device='cuda')
+    _lib.check(_lib.lib().ftb_rnn_bidir(_lib.ptr(xg), _lib.ptr(whh), None if lstm else _lib.ptr(bhn), _lib.ptr(out),
+                                        B, S, H, int(lstm), int(out_bf16), _lib.current_stream(out.device)))
+    torch.cuda.synchronize()
+    return out.float().cpu()
+
+
+@pytest.mark.parametrize('H,B,S', [(64, 3, 40), (128, 2, 57), (64, 70, 9)])
+def test_small_gru_is_fp32_exact(H, B, S):
+    sd = make_sd(H, 256, False, H + B)
+    x = torch.randn(B, S, 256, generator=torch.Generator().manual_seed(1))
+    want = mo.rnn_explicit(sd, 'rnn', x, 'gru')
+    got = run_kernel(sd, x, H, False)
+    assert float((got - want).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize('H,lstm,B,S', [(256, False, 5, 33), (256, False, 64, 120), (512, True, 3, 21),
+                                       (512, True, 64, 150), (512, True, 17, 40)])
+def test_cluster_rnn(H, lstm, B, S):
+    sd = make_sd(H, H if not lstm else 512, lstm, H + B + S)
+    x = torch.randn(B, S, H if not lstm else 512, generator=torch.Generator().manual_seed(2)) * 0.5
+    want = mo.rnn(sd, 'rnn', x, 'lstm' if lstm else 'gru')
+    got = run_kernel(sd, x, H, lstm)
+    # W_hh and the h operand of the recurrent matmul are bf16 (fp32 accumulate, fp32 state)
+    mx = float((got - want).abs().max())
+    mn = float((got - want).abs().mean())
+    assert mx < 1e-2 and mn < 1e-3, (mx, mn)
+    got16 = run_kernel(sd, x, H, lstm, out_bf16=True)
+    assert float((got16 - got).abs().max()) < 8e-3
+
+
+def test_unsupported_size_is_an_error():
+    with pytest.raises(_lib.FtbError, match='no kernel'):
+        z = torch.zeros(8, device='cuda')
+        _lib.check(_lib.lib().ftb_rnn_bidir(_lib.ptr(z), _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), 1, 1, 96, 0, 0, None))
