@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(tc::THREADS, 2)
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t0 = blockIdx.x * BM, b = blockIdx.y, n0 = blockIdx.z * BN;
+  // n tiles vary fastest: the CTAs that share one activation tile run together, so it is read from HBM once
+  const int t0 = blockIdx.y * BM, b = blockIdx.z, n0 = blockIdx.x * BN;
   const int cblocks = a.Cin / BK;
   const int nkb = a.ktaps * cblocks;
 
@@ -286,8 +287,8 @@ int conv_gemm_bf16(const __nv_bfloat16* x, const __nv_bfloat16* w, const ftb_con
   a.pad_left = d.pad_left;
   a.box_rows = box_rows;
   a.epi = make_epi(d);
-  dim3 grid(cdiv(d.S, BM), d.B, npad / BN);
-  FTB_REQUIRE(d.B <= 65535 && npad / BN <= 65535, FTB_ERR_INVALID, "conv_gemm_bf16: grid too large");
+  dim3 grid(npad / BN, cdiv(d.S, BM), d.B);
+  FTB_REQUIRE(d.B <= 65535 && cdiv(d.S, BM) <= 65535, FTB_ERR_INVALID, "conv_gemm_bf16: grid too large");
   conv_gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_w, a);
   FTB_CHECK_LAUNCH();
   return FTB_OK;

@@ -94,37 +94,45 @@ __global__ void head1_kernel(const T* __restrict__ x, const float* __restrict__ 
   if (lane == 0) out[r] = (s + b[0]) / alpha;  // true division like `x / alpha`
 }
 
-// ---- LayerNorm over the last dim (eps 1e-5), optional residual: y = LN(x + r) ---------------
-// one warp per row; C <= 1024.  (models/fast_pitch.py:70-71,84,91,116,128)
-template <typename T>
-__global__ void layernorm_kernel(const T* x, const T* res, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, T* y, int64_t rows, int C) {
+// ---- LayerNorm over the last dim (eps 1e-5) of an fp32 stream -----------------------------------
+// y32 = LN(x) kept in fp32 (the residual stream of the FFT blocks stays fp32), y16 = optional bf16
+// copy that feeds the next tensor-core GEMM.  One warp per row; C <= 1024.  In place (y32 == x) is
+// fine: a row is fully read before it is written.  (models/fast_pitch.py:70-71,84,91,116,128)
+__global__ void layernorm_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float* y32, __nv_bfloat16* y16, int64_t rows, int C) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   constexpr int MAXV = 32;  // C <= 1024
   float v[MAXV];
   float s = 0.f;
-  int n = 0;
-  for (int c = lane; c < C; c += 32, ++n) {
-    float a = ActIO<T>::load(x + r * C + c);
-    if (res) a += ActIO<T>::load(res + r * C + c);
-    v[n] = a;
-    s += a;
+#pragma unroll
+  for (int n = 0; n < MAXV; ++n) {
+    const int c = lane + 32 * n;
+    v[n] = c < C ? x[r * C + c] : 0.f;
+    s += v[n];
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / C;
   float q = 0.f;
-  for (int i = 0; i < n; ++i) {
-    const float d = v[i] - mean;
+#pragma unroll
+  for (int n = 0; n < MAXV; ++n) {
+    const float d = (lane + 32 * n < C) ? v[n] - mean : 0.f;
     q += d * d;
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / C + 1e-5f);
-  n = 0;
-  for (int c = lane; c < C; c += 32, ++n) ActIO<T>::store(y + r * C + c, (v[n] - mean) * rstd * gamma[c] + beta[c]);
+  const float rstd = 1.f / sqrtf(q / C + 1e-5f);
+#pragma unroll
+  for (int n = 0; n < MAXV; ++n) {
+    const int c = lane + 32 * n;
+    if (c < C) {
+      const float o = (v[n] - mean) * rstd * gamma[c] + beta[c];
+      if (y32) y32[r * C + c] = o;
+      if (y16) y16[r * C + c] = __float2bfloat16_rn(o);
+    }
+  }
 }
 
 // ---- x + scale * pe[:S]  (models/fast_pitch.py:32-34); pe: (max_len, E) ---------------------
@@ -235,19 +243,14 @@ template int head1<float>(const float*, const float*, const float*, float, float
 template int head1<__nv_bfloat16>(const __nv_bfloat16*, const float*, const float*, float, float*, int64_t, int,
                                   cudaStream_t);
 
-template <typename T>
-int layernorm(const T* x, const T* res, const float* gamma, const float* beta, T* y, int64_t rows, int C,
-              cudaStream_t s) {
+int layernorm(const float* x, const float* gamma, const float* beta, float* y32, __nv_bfloat16* y16, int64_t rows,
+              int C, cudaStream_t s) {
   ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   FTB_REQUIRE(C <= 1024, FTB_ERR_UNSUPPORTED, "layernorm: C=%d > 1024", C);
-  layernorm_kernel<T><<<cdiv(rows, 8), 256, 0, s>>>(x, res, gamma, beta, y, rows, C);
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, s>>>(x, gamma, beta, y32, y16, rows, C);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }
-template int layernorm<float>(const float*, const float*, const float*, const float*, float*, int64_t, int,
-                              cudaStream_t);
-template int layernorm<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*, const float*, const float*,
-                                      __nv_bfloat16*, int64_t, int, cudaStream_t);
 
 template <typename T>
 int posenc_add(T* x, const float* pe, const float* scale, int B, int S, int E, cudaStream_t s) {

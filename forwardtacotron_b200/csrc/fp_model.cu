@@ -82,7 +82,8 @@ static int build_transformer(ftb_fp_handle* h, TransformerW& W, const std::strin
 
 template <typename T>
 struct TrBufs {
-  T *qkv, *ctx, *a, *f1;
+  T *qkv, *ctx, *f1;
+  float* a32;
 };
 template <typename T>
 static TrBufs<T> plan_tr(Arena& A, const TransformerW& W, int B, int S) {
@@ -90,15 +91,17 @@ static TrBufs<T> plan_tr(Arena& A, const TransformerW& W, int B, int S) {
   const int64_t M = (int64_t)B * S;
   w.qkv = A.take<T>(M * 3 * W.E);
   w.ctx = A.take<T>(M * W.E);
-  w.a = A.take<T>(M * W.E);
   w.f1 = A.take<T>(M * W.dfft);
+  w.a32 = A.take<float>(M * W.E);
   return w;
 }
 
 // x (B,S,E) is transformed in place.  mask_tokens: (B,S) ids, keys with id 0 are ignored; or nullptr.
+// The residual stream lives in fp32 (x32); in bf16 mode `x` is only the bf16 copy that feeds the
+// tensor-core GEMMs, rewritten by every LayerNorm.
 template <typename T>
-static int run_transformer(ftb_fp_handle* h, TransformerW& W, T* x, const int64_t* mask_tokens, int B, int S, Arena& A,
-                           cudaStream_t s) {
+static int run_transformer(ftb_fp_handle* h, TransformerW& W, T* x, float* x32_buf, const int64_t* mask_tokens, int B,
+                           int S, Arena& A, cudaStream_t s) {
   FTB_REQUIRE(S <= W.max_len, FTB_ERR_INVALID, "The size of tensor a (%d) must match the size of tensor b (%d) at "
               "non-singleton dimension 0", S, W.max_len);
   const int64_t mark = A.mark();
@@ -106,19 +109,27 @@ static int run_transformer(ftb_fp_handle* h, TransformerW& W, T* x, const int64_
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for ForwardTransformer");
   const int64_t M = (int64_t)B * S;
   const int E = W.E;
-  FTB_TRY(posenc_add<T>(x, W.pe, W.scale, B, S, E, s));
+  constexpr bool kF32 = std::is_same<T, float>::value;
+  float* x32 = kF32 ? (float*)x : x32_buf;  // caller-owned fp32 stream (B,S,E) in bf16 mode
+  bf16* x16 = kF32 ? nullptr : (bf16*)x;
+  if (!kF32) FTB_TRY(to_f32<T>(x, x32, M * E, s));
+  FTB_TRY(posenc_add<float>(x32, W.pe, W.scale, B, S, E, s));
+  if (!kF32) FTB_TRY(cast_rows<T>(x32, x, M, E, E, E, s));
+  Out a32;
+  a32.f32 = w.a32;
+  a32.ldo = E;
   for (FftBlockW& L : W.layers) {
     FTB_TRY(h->gemm<T>(L.qkv, x, E, B, S, act_out(w.qkv, 3 * E), nullptr, 0, 1.f, s));
     FTB_TRY(attention<T>(w.qkv, mask_tokens, w.ctx, B, S, E, W.heads, s));
-    FTB_TRY(h->gemm<T>(L.out_proj, w.ctx, E, B, S, act_out(w.a, E), x, E, 1.f, s));  // + residual
-    FTB_TRY(layernorm<T>(w.a, nullptr, L.n1w, L.n1b, x, M, E, s));
+    FTB_TRY(h->gemm<T>(L.out_proj, w.ctx, E, B, S, a32, nullptr, E, 1.f, s, x32));  // + bias + residual (fp32)
+    FTB_TRY(layernorm(w.a32, L.n1w, L.n1b, x32, x16, M, E, s));
     FTB_TRY(h->gemm<T>(L.conv1, x, E, B, S, act_out(w.f1, W.dfft), nullptr, 0, 1.f, s));  // + bias, ReLU
-    FTB_TRY(h->gemm<T>(L.conv2, w.f1, W.dfft, B, S, act_out(w.a, E), x, E, 1.f, s));      // + bias + residual
-    FTB_TRY(layernorm<T>(w.a, nullptr, L.n2w, L.n2b, x, M, E, s));
+    FTB_TRY(h->gemm<T>(L.conv2, w.f1, W.dfft, B, S, a32, nullptr, E, 1.f, s, x32));       // + bias + residual
+    FTB_TRY(layernorm(w.a32, L.n2w, L.n2b, x32, x16, M, E, s));
     h->launches += 3;
   }
-  FTB_TRY(layernorm<T>(x, nullptr, W.nw, W.nb, x, M, E, s));
-  h->launches += 2;
+  FTB_TRY(layernorm(x32, W.nw, W.nb, x32, x16, M, E, s));
+  h->launches += 4;
   A.reset(mark);
   return FTB_OK;
 }
@@ -129,10 +140,11 @@ static int run_fp_series(ftb_fp_handle* h, FpSeriesW& P, const int64_t* tok, int
   const int64_t mark = A.mark();
   const int64_t M = (int64_t)B * Tn;
   T* x = A.take<T>(M * P.tr.E);
+  float* x32 = std::is_same<T, float>::value ? (float*)x : A.take<float>(M * P.tr.E);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for SeriesPredictor");
   FTB_TRY(embed<T>(tok, P.emb, x, M, P.tr.E, P.tr.E, h->cfg.num_chars, s));
-  FTB_TRY(run_transformer<T>(h, P.tr, x, nullptr, B, Tn, A, s));
-  FTB_TRY(head1<T>(x, P.lin_w, P.lin_b, alpha, out, M, P.tr.E, s));
+  FTB_TRY(run_transformer<T>(h, P.tr, x, x32, nullptr, B, Tn, A, s));
+  FTB_TRY(head1<float>(x32, P.lin_w, P.lin_b, alpha, out, M, P.tr.E, s));  // head reads the fp32 stream
   h->launches += 2;
   A.reset(mark);
   return FTB_OK;
@@ -146,13 +158,14 @@ static int run_fp_synthesize(ftb_fp_handle* h, const int64_t* tok, const int32_t
   const int64_t MT = (int64_t)B * Tn, ML = (int64_t)B * L;
   T* x = A.take<T>(MT * E);
   T* up = A.take<T>(ML * E);
+  float* x32 = std::is_same<T, float>::value ? nullptr : A.take<float>(std::max(MT, ML) * E);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for synthesize");
   FTB_TRY(embed<T>(tok, h->embedding, x, MT, E, E, c.num_chars, s));
-  FTB_TRY(run_transformer<T>(h, h->prenet, x, tok, B, Tn, A, s));
+  FTB_TRY(run_transformer<T>(h, h->prenet, x, x32, tok, B, Tn, A, s));
   FTB_TRY(cond_add<T>(x, pitch, energy, h->pitch_w, h->pitch_b, h->energy_w, h->energy_b, c.pitch_strength,
                       c.energy_strength, B, Tn, E, s));
   FTB_TRY(ftb_length_expand(x, cum, up, B, Tn, L, E, (int)sizeof(T), s));
-  FTB_TRY(run_transformer<T>(h, h->postnet, up, nullptr, B, L, A, s));
+  FTB_TRY(run_transformer<T>(h, h->postnet, up, x32, nullptr, B, L, A, s));
   Out o;
   o.t = mel;
   FTB_TRY(h->gemm<T>(h->lin, up, E, B, L, o, nullptr, 0, 1.f, s));
@@ -171,6 +184,7 @@ static int64_t fp_bytes(const ftb_fp_handle* h, int B, int Tn, int L) {
       plan_tr<float>(A, h->series[i].tr, B, Tn);
     } else {
       A.take<T>((int64_t)B * Tn * h->series[i].tr.E);
+      A.take<float>((int64_t)B * Tn * h->series[i].tr.E);
       plan_tr<T>(A, h->series[i].tr, B, Tn);
     }
     best = std::max(best, A.mark());
@@ -179,6 +193,7 @@ static int64_t fp_bytes(const ftb_fp_handle* h, int B, int Tn, int L) {
     Arena A(nullptr, 0);
     A.take<T>((int64_t)B * Tn * h->cfg.d_model);
     A.take<T>((int64_t)B * L * h->cfg.d_model);
+    A.take<float>((int64_t)B * std::max(Tn, L) * h->cfg.d_model);
     const int64_t base = A.mark();
     plan_tr<T>(A, h->prenet, B, Tn);
     const int64_t pre = A.mark();
@@ -213,10 +228,12 @@ extern "C" int ftb_fp_create(const ftb_fp_config* cfg, const ftb_tensor* tensors
   auto build = [&]() -> int {
     FTB_TRY(build_series(h->series[0], "dur_pred", c.durpred_d_model, c.durpred_n_heads, c.durpred_layers,
                          c.durpred_d_fft, true));
+    // The three predictors are small (d_model 128, phoneme rate) and their post-LN stacks amplify bf16
+    // operand rounding past the 1e-3 mean-abs budget (measured 2.9e-3 on pitch), so all of them run fp32.
     FTB_TRY(build_series(h->series[1], "pitch_pred", c.pitch_d_model, c.pitch_n_heads, c.pitch_layers, c.pitch_d_fft,
-                         false));
+                         true));
     FTB_TRY(build_series(h->series[2], "energy_pred", c.energy_d_model, c.energy_n_heads, c.energy_layers,
-                         c.energy_d_fft, false));
+                         c.energy_d_fft, true));
     FTB_TRY(h->get("embedding.weight", {c.num_chars, c.d_model}, &h->embedding));
     FTB_TRY(build_transformer(h, h->prenet, "prenet", c.d_model, c.prenet_fft, c.prenet_layers, c.prenet_heads,
                               c.conv1_kernel, c.conv2_kernel, false));

@@ -28,9 +28,8 @@ int cond_add(T* x, const float* pitch, const float* energy, const float* wp, con
              const float* be, float ps, float es, int B, int Tn, int C, cudaStream_t s);
 template <typename T>
 int head1(const T* x, const float* w, const float* b, float alpha, float* out, int64_t rows, int C, cudaStream_t s);
-template <typename T>
-int layernorm(const T* x, const T* res, const float* gamma, const float* beta, T* y, int64_t rows, int C,
-              cudaStream_t s);
+int layernorm(const float* x, const float* gamma, const float* beta, float* y32, __nv_bfloat16* y16, int64_t rows,
+              int C, cudaStream_t s);
 template <typename T>
 int posenc_add(T* x, const float* pe, const float* scale, int B, int S, int E, cudaStream_t s);
 int bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* shift, int C,

@@ -161,7 +161,7 @@ struct ModelBase {
   // y = epilogue(conv(x)) with the kernel matching T: float -> fp32 SIMT, bf16 -> tcgen05
   template <typename T>
   int gemm(const Layer& L, const T* x, int lda, int B, int S, Out o, const T* residual, int ldr, float out_scale,
-           cudaStream_t s) {
+           cudaStream_t s, const float* residual32 = nullptr) {
     ftb_conv_desc d;
     memset(&d, 0, sizeof(d));
     d.B = B;
@@ -186,11 +186,12 @@ struct ModelBase {
     ProfScope prof(std::is_same<T, float>::value ? FAM_GEMM_F32 : FAM_GEMM_TC,
                    2.0 * B * S * (double)L.N * L.k * L.Cin, 0.0, s);
     if (std::is_same<T, float>::value) {
-      d.residual_f32 = (const float*)residual;
+      d.residual_f32 = residual32 ? residual32 : (const float*)residual;
       FTB_REQUIRE(L.w32, FTB_ERR_INVALID, "layer has no fp32 weights packed");
       return conv_gemm_f32((const float*)x, L.w32, d, s);
     }
     d.residual_bf16 = residual;
+    d.residual_f32 = residual32;
     FTB_REQUIRE(L.w16, FTB_ERR_INVALID, "layer has no bf16 weights packed");
     return conv_gemm_bf16((const bf16*)x, L.w16, d, s);
   }
