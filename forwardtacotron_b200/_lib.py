@@ -79,6 +79,7 @@ SIGNATURES = {
     'ftb_duration_fallback': (_I, [_P, _L, _P, _P]),
     'ftb_conv_gemm_f32': (_I, [_P, _P, C.POINTER(ConvDesc), _P]),
     'ftb_conv_gemm_bf16': (_I, [_P, _P, C.POINTER(ConvDesc), _P]),
+    'ftb_conv_bank_bf16': (_I, [_P, C.POINTER(_P), C.POINTER(ConvDesc), _I, _I, _P]),
     'ftb_tc_timeout_count': (_I, []),
     'ftb_pack_conv_weight': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'ftb_rnn_bidir': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

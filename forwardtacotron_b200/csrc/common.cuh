@@ -106,6 +106,13 @@ __device__ __forceinline__ float tanhf_(float x) {
   float e = __expf(2.f * x);
   return 1.f - 2.f / (e + 1.f);
 }
+// MUFU-only variants for the recurrence kernels (2 MUFU + 2-3 FP32 ops, no division subroutine);
+// relative error ~1e-6, far below the bf16 rounding of the recurrent operand they feed.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  // 2^126 < e + 1 makes __fdividef return 0, which is the right limit (tanh -> 1)
+  return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -1,18 +1,28 @@
-// bf16 implicit-GEMM conv1d on the 5th-generation tensor cores (sm_100a):
-//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory -> tcgen05.mma (accumulator in
-//   TMEM, fp32) -> tcgen05.ld -> fused epilogue (epilogue.cuh) -> global.
+// bf16 implicit-GEMM conv1d on the 5th-generation tensor cores (sm_100a), version 2:
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> 4-stage shared-memory ring -> tcgen05.mma with the
+//   fp32 accumulator in TMEM (double buffered: 2 x 256 columns) -> tcgen05.ld -> fused epilogue.
 //
-// Convolution as GEMM without im2col: the activation tensor (B,S,C) is described by a 3-D
-// tensor map (C, S, B).  Tap j of a CTA tile [t0, t0+128) of utterance b is the SAME box shifted
-// to row t0 + j - pad_left; rows outside [0,S) are zero-filled by the TMA unit, which is exactly
-// the conv zero padding (and keeps utterances from leaking into each other).  K loop = taps x
-// 64-channel blocks.  One CTA = one 128(t) x 128(n) output tile:
-//   warp 0    : TMA producer (one elected lane), 3-stage mbarrier ring
-//   warp 1    : TMEM allocation + tcgen05.mma issue (one elected lane), commit -> stage release
-//   warps 2-5 : epilogue: TMEM -> registers -> shared staging tile -> coalesced global stores
-// Two CTAs fit per SM (96 KB smem, 128 TMEM columns each), so one CTA's epilogue overlaps the
-// other's main loop.
+// Convolution as GEMM without im2col: the activation tensor (B,S,C) is described by a 3-D tensor
+// map (C, S, B).  Tap j of the tile [t0, t0+128) of utterance b is the SAME box shifted to row
+// t0 + j - pad_left; rows outside [0,S) are zero-filled by the TMA unit, which is exactly the conv
+// zero padding (and keeps utterances from leaking into each other).  K loop = taps x 64-channel blocks.
+//
+// One PERSISTENT CTA per SM walks a static round-robin schedule of 128(t) x BN(n) output tiles
+// (BN = 256 for the wide layers).  A launch can carry up to 16 "problems" that read the same
+// activation tensor with different weights / taps / output column offset: the whole CBHG conv bank
+// (models/common_layers.py:92-97) is ONE launch, ordered heaviest-first so the tail is short.
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocation + tcgen05.mma issue (one elected lane); commit -> stage release
+//   warps 2..9  : epilogue.  TMEM lane quarter = warp % 4, the two warps of a quarter split the
+//                 32-column chunks.  TMEM -> registers -> per-warp smem transpose -> lanes walk n, so
+//                 per-column parameters sit in registers and every global access is coalesced.
+// The epilogue of tile i overlaps the main loop of tile i+1 through the second TMEM buffer.
+// Optional fused MaxPool1d(2,1,1)[:S] (common_layers.py:100): tiles advance by 127 rows and carry one
+// halo row, so out[t] = max(v[t-1], v[t]) needs no second pass over the bank output.
 #include <cuda.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "epilogue.cuh"
 #include "kernels.cuh"
@@ -20,17 +30,20 @@
 namespace ftb {
 
 namespace tc {
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int STAGING_LD = BN + 1;
-constexpr int SMEM_TILES = STAGES * STAGE_BYTES;                 // 98304
-static_assert(BM * STAGING_LD * 4 <= SMEM_TILES, "staging tile must fit in the pipeline buffers");
-constexpr int SMEM_BYTES = SMEM_TILES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 192;
-constexpr uint32_t TMEM_COLS = 128;
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N=128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr int BM = 128, BK = 64, STAGES = 4, BN_MAX = 256, MAXP = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN_MAX * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;  // 16K + 32K
+constexpr int EPI_WARPS = 8, STG_LD = 33;
+constexpr int SMEM_TILES = STAGES * STAGE_BYTES;                  // 196608
+constexpr int SMEM_STAGING = EPI_WARPS * 32 * STG_LD * 4;         // 33792
+constexpr int SMEM_BYTES = SMEM_TILES + SMEM_STAGING + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 32 * (2 + EPI_WARPS);                     // 320
+constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // bounded wait: a protocol bug must not hang the GPU
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 }  // namespace tc
 
 __device__ int g_tc_timeouts = 0;  // a barrier wait that gave up (never expected; prevents hangs)
@@ -41,6 +54,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
@@ -99,37 +115,73 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 
-struct TcConvArgs {
-  int S, Cin, ktaps, pad_left, box_rows;
-  EpiParams epi;
+// One conv / linear of a launch; all problems of a launch share the activation tensor and outputs.
+struct alignas(64) TcProb {
+  CUtensorMap map_w;  // (ktaps*Cin, N) bf16, box 64 x bn
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  int N, ktaps, pad_left, n_offset, relu;
+  int n_tiles, nkb, tile_begin;
+  uint32_t idesc;
 };
+static_assert(sizeof(TcProb) == 192, "TcProb layout");
+struct alignas(64) TcArgs {
+  CUtensorMap map_a;  // (Cin, S, B) bf16, box 64 x box_rows x 1
+  TcProb prob[tc::MAXP];
+  int nprob, B, S, Cin, cblocks;
+  int m_tiles, m_stride, box_rows, bn, total_tiles, pool;
+  int ldo, ldr, n_total;  // n_total: N of the (B,N,S) transposed output
+  float out_scale;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  float* out_t;
+  const float* res_f32;
+  const __nv_bfloat16* res_bf16;
+};
+static_assert(sizeof(TcArgs) <= 4000, "kernel parameter space");
 
-__global__ void __launch_bounds__(tc::THREADS, 2)
-    conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                        const TcConvArgs a) {
+struct TileCoord {
+  int p, b, t0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile) {
+  int p = 0;
+  while (p + 1 < a.nprob && tile >= a.prob[p + 1].tile_begin) ++p;
+  const int local = tile - a.prob[p].tile_begin;
+  const int nt = local % a.prob[p].n_tiles, rest = local / a.prob[p].n_tiles;
+  TileCoord c;
+  c.p = p;
+  c.b = rest / a.m_tiles;
+  c.t0 = (rest % a.m_tiles) * a.m_stride - a.pool;
+  c.n0 = nt * a.bn;
+  return c;
+}
+
+__global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcArgs a) {
   using namespace tc;
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + SMEM_TILES);  // full[STAGES], empty[STAGES], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* staging_all = reinterpret_cast<float*>(tiles + SMEM_TILES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + SMEM_TILES + SMEM_STAGING);
+  // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const uint32_t tiles_u32 = smem_u32(tiles);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
+                 tempty0 = smem_u32(bars + 2 * STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // n tiles vary fastest: the CTAs that share one activation tile run together, so it is read from HBM once
-  const int t0 = blockIdx.y * BM, b = blockIdx.z, n0 = blockIdx.x * BN;
-  const int cblocks = a.Cin / BK;
-  const int nkb = a.ktaps * cblocks;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map_a) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(full0 + 8 * i, 1);
       mbar_init(empty0 + 8 * i, 1);
     }
-    mbar_init(tfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // one full warp allocates (and later frees) the accumulator columns
@@ -145,71 +197,142 @@ __global__ void __launch_bounds__(tc::THREADS, 2)
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      const uint32_t tx = (uint32_t)(a.box_rows * BK * 2 + B_BYTES);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % STAGES;
-        if (kb >= STAGES) mbar_wait(empty0 + 8 * st, ((kb / STAGES) - 1) & 1);
-        const int j = kb / cblocks, cb = kb % cblocks;
-        const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
-        mbar_expect_tx(full0 + 8 * st, tx);
-        tma_load_3d(sa, &map_a, full0 + 8 * st, cb * BK, t0 + j - a.pad_left, b);
-        tma_load_2d(sb, &map_w, full0 + 8 * st, j * a.Cin + cb * BK, n0);
+      const uint32_t tx = (uint32_t)(a.box_rows * BK * 2 + a.bn * BK * 2);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile(a, tile);
+        const TcProb& P = a.prob[c.p];
+        int j = 0, cb = 0;
+        for (int kb = 0; kb < P.nkb; ++kb, ++it) {
+          const uint32_t st = it % STAGES;
+          if (it >= STAGES) mbar_wait(empty0 + 8 * st, ((it / STAGES) - 1) & 1);
+          const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
+          mbar_expect_tx(full0 + 8 * st, tx);
+          tma_load_3d(sa, &a.map_a, full0 + 8 * st, cb * BK, c.t0 + j - P.pad_left, c.b);
+          tma_load_2d(sb, &P.map_w, full0 + 8 * st, j * a.Cin + cb * BK, c.n0);
+          if (++cb == a.cblocks) cb = 0, ++j;
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % STAGES;
-        mbar_wait(full0 + 8 * st, (kb / STAGES) & 1);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tl) {
+        const TileCoord c = decode_tile(a, tile);
+        const TcProb& P = a.prob[c.p];
+        const uint32_t buf = tl & 1;
+        if (tl >= 2) mbar_wait(tempty0 + 8 * buf, ((tl >> 1) - 1) & 1);  // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
+        const uint32_t d_tmem = tmem_base + buf * BN_MAX;
+        const uint32_t idesc = P.idesc;
+        for (int kb = 0; kb < P.nkb; ++kb, ++it) {
+          const uint32_t st = it % STAGES;
+          mbar_wait(full0 + 8 * st, (it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          umma_bf16(tmem_base, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), IDESC,
-                    (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty0 + 8 * st);  // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty0 + 8 * st);  // frees the smem stage when these MMAs retire
+        umma_commit(tfull0 + 8 * buf);  // accumulator complete
       }
-      umma_commit(tfull);  // accumulator complete
     }
-  } else {  // ===== epilogue warps 2..5 =====
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
-    float* staging = reinterpret_cast<float*>(tiles);
-    mbar_wait(tfull, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = quarter * 32 + lane;
+  } else {  // ===== epilogue warps 2..9 =====
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;  // TMEM lane quarter, column half
+    float* stg = staging_all + (half * 4 + q) * 32 * STG_LD;
+    const float* stg_prev = staging_all + (half * 4 + (q > 0 ? q - 1 : 0)) * 32 * STG_LD;  // pool halo row
+    const bool row_major = a.out_f32 || a.out_bf16;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tl) {
+      const TileCoord c = decode_tile(a, tile);
+      const TcProb& P = a.prob[c.p];
+      const uint32_t buf = tl & 1;
+      const int ncols = min(a.bn, P.N - c.n0);
+      const int nchunks = (ncols + 31) >> 5;
+      mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t mbase = (int64_t)c.b * a.S;
+      bool released = false;
+      for (int ch = half; ch < nchunks; ch += 2) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX + ch * 32, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ch + 2 >= nchunks) {  // last TMEM read of this warp for this tile: hand the buffer back
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+          released = true;
+        }
+        const int nb = c.n0 + ch * 32;  // first output column of the chunk
+        if (a.out_t) {                  // (B,N,S) output: lanes walk t (coalesced along the time axis)
+          const int t = c.t0 + q * 32 + lane;
+          if (t < a.S) {
+            EpiParams e;
+            e.bias = P.bias, e.scale = P.scale, e.shift = P.shift, e.res_f32 = a.res_f32, e.res_bf16 = a.res_bf16;
+            e.relu = P.relu, e.ldr = a.ldr, e.out_scale = a.out_scale;
 #pragma unroll
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 32, r);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int i = 0; i < 32; ++i) staging[row * STAGING_LD + c * 32 + i] = __uint_as_float(r[i]);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-    const EpiParams& e = a.epi;
-    const int64_t mbase = (int64_t)b * a.S;
-    if (e.out_f32 || e.out_bf16) {  // row-major outputs: lanes walk n (coalesced)
-      for (int rr = 0; rr < 32; ++rr) {
-        const int r_ = quarter * 32 + rr, t = t0 + r_;
-        if (t >= a.S) break;
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          const int n = n0 + c * 32 + lane;
-          if (n < e.N) {
-            const float v = epi_value(e, mbase + t, n, staging[r_ * STAGING_LD + c * 32 + lane]);
-            if (e.out_f32) e.out_f32[(mbase + t) * e.ldo + e.n_offset + n] = v;
-            if (e.out_bf16) e.out_bf16[(mbase + t) * e.ldo + e.n_offset + n] = __float2bfloat16_rn(v);
+            for (int i = 0; i < 32; ++i) {
+              const int n = nb + i;
+              if (n < P.N) a.out_t[((int64_t)c.b * a.n_total + n) * a.S + t] = epi_value(e, mbase + t, n, __uint_as_float(r[i]));
+            }
           }
         }
+        if (row_major) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = __uint_as_float(r[i]);
+          if (a.pool)
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // the 4 quarters of this column half
+          else
+            __syncwarp();
+          const int n = nb + lane;
+          const bool nok = n < P.N;
+          const float bias = (nok && P.bias) ? __ldg(P.bias + n) : 0.f;
+          const float scale = (nok && P.scale) ? __ldg(P.scale + n) : 1.f;
+          const float shift = (nok && P.shift) ? __ldg(P.shift + n) : 0.f;
+          const bool relu = P.relu != 0;
+          auto affine = [&](float v) {
+            v += bias;
+            if (relu) v = fmaxf(v, 0.f);
+            return fmaf(v, scale, shift);
+          };
+          const int col = P.n_offset + n;
+          if (!a.pool) {
+            for (int rr = 0; rr < 32; ++rr) {
+              const int t = c.t0 + q * 32 + rr;
+              if (t >= a.S) break;
+              const int64_t m = mbase + t;
+              float v = affine(stg[rr * STG_LD + lane]);
+              if (nok) {
+                if (a.res_f32) v += a.res_f32[m * a.ldr + n];
+                if (a.res_bf16) v += __bfloat162float(a.res_bf16[m * a.ldr + n]);
+                v *= a.out_scale;
+                if (a.out_f32) a.out_f32[m * a.ldo + col] = v;
+                if (a.out_bf16) a.out_bf16[m * a.ldo + col] = __float2bfloat16_rn(v);
+              }
+            }
+          } else {  // out[t] = max(v[t-1], v[t]); tile row 0 is the halo row t0 = first output row - 1
+            float prev = -INFINITY;
+            if (q > 0) prev = affine(stg_prev[31 * STG_LD + lane]);
+            for (int rr = 0; rr < 32; ++rr) {
+              const int i = q * 32 + rr, t = c.t0 + i;
+              if (t >= a.S) break;
+              const float cur = affine(stg[rr * STG_LD + lane]);
+              if (i >= 1 && nok) {
+                const int64_t m = mbase + t;
+                const float v = fmaxf(prev, cur) * a.out_scale;
+                if (a.out_f32) a.out_f32[m * a.ldo + col] = v;
+                if (a.out_bf16) a.out_bf16[m * a.ldo + col] = __float2bfloat16_rn(v);
+              }
+              prev = t >= 0 ? cur : -INFINITY;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // neighbours finished with my row 31
+          }
+          __syncwarp();
+        }
       }
-    }
-    if (e.out_t) {  // (B,N,S) output: lanes walk t (coalesced along the time axis)
-      const int t = t0 + row;
-      for (int c = 0; c < BN; ++c) {
-        const int n = n0 + c;
-        if (n >= e.N) break;
-        if (t < a.S) e.out_t[((int64_t)b * e.N + n) * a.S + t] = epi_value(e, mbase + t, n, staging[row * STAGING_LD + c]);
+      if (!released) {  // no chunk for this warp in this tile
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
       }
     }
   }
@@ -250,48 +373,116 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   return FTB_OK;
 }
 
-int conv_gemm_bf16(const __nv_bfloat16* x, const __nv_bfloat16* w, const ftb_conv_desc& d, cudaStream_t s) {
-  using namespace tc;
-  FTB_REQUIRE(x && w, FTB_ERR_INVALID, "conv_gemm_bf16: null operand");
-  FTB_REQUIRE(d.B > 0 && d.S > 0 && d.N > 0 && d.ktaps > 0, FTB_ERR_INVALID, "conv_gemm_bf16: bad shape");
-  FTB_REQUIRE(d.Cin % BK == 0 && d.lda % 8 == 0 && d.lda >= d.Cin, FTB_ERR_INVALID,
-              "conv_gemm_bf16: Cin=%d must be a multiple of 64 and lda=%d a multiple of 8", d.Cin, d.lda);
-  FTB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, FTB_ERR_INVALID, "conv_gemm_bf16: unaligned operand");
-  FTB_REQUIRE(d.out_f32 || d.out_bf16 || d.out_t, FTB_ERR_INVALID, "conv_gemm_bf16: no output");
-  const int npad = (int)align_up(d.N, BN);
-  const int ktot = d.ktaps * d.Cin;
+int tc_tile_n(int N) { return N % 256 == 0 ? 256 : (N > 64 ? 128 : 64); }
 
-  CUtensorMap map_a, map_w;
-  const int box_rows = d.S < BM ? d.S : BM;
+// x (B,S,lda) bf16; items[i] is one conv over x.  All items must agree on the tile width tc_tile_n(N).
+int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, const TcItem* items, int n_items,
+                    const TcOut& o, cudaStream_t s) {
+  using namespace tc;
+  FTB_REQUIRE(x && items && n_items > 0 && n_items <= MAXP, FTB_ERR_INVALID, "conv_gemm_group: bad arguments");
+  FTB_REQUIRE(B > 0 && S > 0, FTB_ERR_INVALID, "conv_gemm_group: bad shape");
+  FTB_REQUIRE(Cin % BK == 0 && lda % 8 == 0 && lda >= Cin, FTB_ERR_INVALID,
+              "conv_gemm_bf16: Cin=%d must be a multiple of 64 and lda=%d a multiple of 8", Cin, lda);
+  FTB_REQUIRE(((uintptr_t)x & 15) == 0, FTB_ERR_INVALID, "conv_gemm_bf16: unaligned operand");
+  FTB_REQUIRE(o.out_f32 || o.out_bf16 || o.out_t, FTB_ERR_INVALID, "conv_gemm_bf16: no output");
+  FTB_REQUIRE(!o.pool || (!o.out_t && !o.res_f32 && !o.res_bf16), FTB_ERR_INVALID,
+              "conv_gemm_bf16: the fused max-pool supports row-major outputs without residual only");
+  FTB_REQUIRE(B <= 65535, FTB_ERR_INVALID, "conv_gemm_bf16: batch too large");
+
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nprob = n_items;
+  a.B = B;
+  a.S = S;
+  a.Cin = Cin;
+  a.cblocks = Cin / BK;
+  a.pool = o.pool ? 1 : 0;
+  a.m_stride = o.pool ? BM - 1 : BM;
+  a.m_tiles = cdiv(S, a.m_stride);
+  a.box_rows = BM;  // the box may exceed the tensor: rows outside [0,S) are zero-filled (conv padding, pool halo)
+  a.bn = tc_tile_n(items[0].N);
+  a.ldo = o.ldo;
+  a.ldr = o.ldr;
+  a.out_scale = o.out_scale == 0.f ? 1.f : o.out_scale;
+  a.out_f32 = o.out_f32;
+  a.out_bf16 = o.out_bf16;
+  a.out_t = o.out_t;
+  a.res_f32 = o.res_f32;
+  a.res_bf16 = o.res_bf16;
+  a.n_total = items[0].N;
+  FTB_REQUIRE(!o.out_t || n_items == 1, FTB_ERR_INVALID, "conv_gemm_bf16: transposed output needs a single problem");
   {
-    cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)d.S, (cuuint64_t)d.B};
-    cuuint64_t strides[2] = {(cuuint64_t)d.lda * 2, (cuuint64_t)d.S * d.lda * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
-    FTB_TRY(make_map(&map_a, x, 3, dims, strides, box));
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)S, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)lda * 2, (cuuint64_t)S * lda * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)a.box_rows, 1};
+    FTB_TRY(make_map(&a.map_a, x, 3, dims, strides, box));
   }
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d.N};  // rows >= N of the last tile are zero-filled by TMA
+  // heaviest problems first: with the static round-robin schedule this is longest-processing-time-first
+  int order[MAXP];
+  for (int i = 0; i < n_items; ++i) order[i] = i;
+  std::stable_sort(order, order + n_items, [&](int l, int r) { return items[l].ktaps > items[r].ktaps; });
+  int tiles = 0;
+  for (int i = 0; i < n_items; ++i) {
+    const TcItem& it = items[order[i]];
+    TcProb& P = a.prob[i];
+    FTB_REQUIRE(it.w && it.N > 0 && it.ktaps > 0 && ((uintptr_t)it.w & 15) == 0, FTB_ERR_INVALID, "conv_gemm_bf16: bad problem");
+    FTB_REQUIRE(tc_tile_n(it.N) == a.bn, FTB_ERR_INVALID, "conv_gemm_group: mixed tile widths");
+    const int ktot = it.ktaps * Cin;
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)it.N};  // rows >= N of the last tile are zero-filled by TMA
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
-    FTB_TRY(make_map(&map_w, w, 2, dims, strides, box));
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)a.bn};
+    FTB_TRY(make_map(&P.map_w, it.w, 2, dims, strides, box));
+    P.bias = it.bias;
+    P.scale = it.scale;
+    P.shift = it.shift;
+    FTB_REQUIRE(!it.scale == !it.shift, FTB_ERR_INVALID, "conv_gemm_bf16: scale and shift come together");
+    P.N = it.N;
+    P.ktaps = it.ktaps;
+    P.pad_left = it.pad_left;
+    P.n_offset = it.n_offset;
+    P.relu = it.relu;
+    P.n_tiles = cdiv(it.N, a.bn);
+    P.nkb = it.ktaps * a.cblocks;
+    P.tile_begin = tiles;
+    P.idesc = idesc_bf16(it.N >= a.bn ? a.bn : (int)align_up(it.N, 16));
+    tiles += P.n_tiles * a.m_tiles * B;
   }
+  a.total_tiles = tiles;
   static bool configured = false;
   if (!configured) {
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  TcConvArgs a;
-  a.S = d.S;
-  a.Cin = d.Cin;
-  a.ktaps = d.ktaps;
-  a.pad_left = d.pad_left;
-  a.box_rows = box_rows;
-  a.epi = make_epi(d);
-  dim3 grid(npad / BN, cdiv(d.S, BM), d.B);
-  FTB_REQUIRE(d.B <= 65535 && cdiv(d.S, BM) <= 65535, FTB_ERR_INVALID, "conv_gemm_bf16: grid too large");
-  conv_gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_w, a);
+  const int grid = std::min(tiles, sm_count());
+  conv_gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(a);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
+}
+
+int conv_gemm_bf16(const __nv_bfloat16* x, const __nv_bfloat16* w, const ftb_conv_desc& d, cudaStream_t s) {
+  FTB_REQUIRE(x && w, FTB_ERR_INVALID, "conv_gemm_bf16: null operand");
+  FTB_REQUIRE(d.B > 0 && d.S > 0 && d.N > 0 && d.ktaps > 0, FTB_ERR_INVALID, "conv_gemm_bf16: bad shape");
+  TcItem it;
+  it.w = w;
+  it.N = d.N;
+  it.ktaps = d.ktaps;
+  it.pad_left = d.pad_left;
+  it.n_offset = d.n_offset;
+  it.relu = d.relu;
+  it.bias = d.bias;
+  it.scale = d.scale;
+  it.shift = d.shift;
+  TcOut o;
+  o.out_f32 = d.out_f32;
+  o.out_bf16 = (__nv_bfloat16*)d.out_bf16;
+  o.out_t = d.out_t;
+  o.res_f32 = d.residual_f32;
+  o.res_bf16 = (const __nv_bfloat16*)d.residual_bf16;
+  o.ldo = d.ldo;
+  o.ldr = d.ldr;
+  o.out_scale = d.out_scale;
+  o.pool = false;
+  return conv_gemm_group(x, d.lda, d.B, d.S, d.Cin, &it, 1, o, s);
 }
 
 }  // namespace ftb
@@ -301,6 +492,36 @@ using namespace ftb;
 extern "C" int ftb_conv_gemm_bf16(const void* x, const void* w_packed, const ftb_conv_desc* d, void* stream) {
   FTB_REQUIRE(d, FTB_ERR_INVALID, "ftb_conv_gemm_bf16: null desc");
   return conv_gemm_bf16((const __nv_bfloat16*)x, (const __nv_bfloat16*)w_packed, *d, (cudaStream_t)stream);
+}
+
+extern "C" int ftb_conv_bank_bf16(const void* x, const void* const* w_packed, const ftb_conv_desc* descs, int n_convs,
+                                  int maxpool, void* stream) {
+  FTB_REQUIRE(x && w_packed && descs && n_convs > 0 && n_convs <= tc::MAXP, FTB_ERR_INVALID,
+              "ftb_conv_bank_bf16: bad arguments (1..%d convs)", tc::MAXP);
+  const ftb_conv_desc& d0 = descs[0];
+  std::vector<TcItem> items(n_convs);
+  for (int i = 0; i < n_convs; ++i) {
+    const ftb_conv_desc& d = descs[i];
+    FTB_REQUIRE(d.B == d0.B && d.S == d0.S && d.Cin == d0.Cin && d.lda == d0.lda && d.ldo == d0.ldo &&
+                    d.out_f32 == d0.out_f32 && d.out_bf16 == d0.out_bf16 && !d.out_t && !d.residual_f32 && !d.residual_bf16,
+                FTB_ERR_INVALID, "ftb_conv_bank_bf16: the convs of a bank share input, shape and output tensor");
+    items[i].w = (const __nv_bfloat16*)w_packed[i];
+    items[i].N = d.N;
+    items[i].ktaps = d.ktaps;
+    items[i].pad_left = d.pad_left;
+    items[i].n_offset = d.n_offset;
+    items[i].relu = d.relu;
+    items[i].bias = d.bias;
+    items[i].scale = d.scale;
+    items[i].shift = d.shift;
+  }
+  TcOut o;
+  o.out_f32 = d0.out_f32;
+  o.out_bf16 = (__nv_bfloat16*)d0.out_bf16;
+  o.ldo = d0.ldo;
+  o.out_scale = d0.out_scale;
+  o.pool = maxpool != 0;
+  return conv_gemm_group((const __nv_bfloat16*)x, d0.lda, d0.B, d0.S, d0.Cin, items.data(), n_convs, o, (cudaStream_t)stream);
 }
 
 extern "C" int ftb_tc_timeout_count(void) {

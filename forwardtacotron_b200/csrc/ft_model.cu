@@ -184,9 +184,7 @@ static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int 
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for CBHG");
   const int64_t M = (int64_t)B * S;
   const int bank_c = W.K * W.ch;
-  for (int i = 0; i < W.K; ++i)
-    FTB_TRY(h->gemm<T>(W.bank[i], x, ldx, B, S, act_out(w.bank, bank_c, i * W.ch), nullptr, 0, 1.f, s));
-  FTB_TRY(maxpool_inplace<T>(w.bank, B, S, bank_c, s));
+  FTB_TRY(h->conv_bank<T>(W.bank, x, ldx, B, S, w.bank, W.ch, s));
   FTB_TRY(h->gemm<T>(W.proj1, w.bank, bank_c, B, S, act_out(w.p1, W.p0), nullptr, 0, 1.f, s));
   if (w.ld2 != W.p1) FTB_CHECK_CUDA(cudaMemsetAsync(w.p2, 0, (size_t)M * w.ld2 * sizeof(T), s));
   FTB_TRY(h->gemm<T>(W.proj2, w.p1, W.p0, B, S, act_out(w.p2, w.ld2), x, ldx, 1.f, s));  // + residual
@@ -199,7 +197,7 @@ static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int 
   }
   FTB_TRY(h->gemm<T>(W.rnn.in, cur, W.ch, B, S, act_out(w.xg, 6 * W.ch), nullptr, 0, 1.f, s));
   FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, std::is_same<T, bf16>::value, s));
-  h->launches += 2 + W.nhw;
+  h->launches += 1 + W.nhw;
   A.reset(mark);
   return FTB_OK;
 }

@@ -7,6 +7,28 @@ namespace ftb {
 // conv_gemm_simt.cu / conv_gemm_tc.cu
 int conv_gemm_f32(const float* x, const float* w, const ftb_conv_desc& d, cudaStream_t s);
 int conv_gemm_bf16(const __nv_bfloat16* x, const __nv_bfloat16* w, const ftb_conv_desc& d, cudaStream_t s);
+// Grouped tcgen05 launch: up to 16 convs over the same activation tensor (the CBHG conv bank) in one
+// persistent kernel, optionally with MaxPool1d(2,1,1)[:S] fused into the epilogue.
+struct TcItem {
+  const __nv_bfloat16* w = nullptr;  // packed (N, ktaps*Cin) K-major
+  int N = 0, ktaps = 1, pad_left = 0, n_offset = 0, relu = 0;
+  const float* bias = nullptr;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+};
+struct TcOut {
+  float* out_f32 = nullptr;
+  __nv_bfloat16* out_bf16 = nullptr;
+  float* out_t = nullptr;
+  const float* res_f32 = nullptr;
+  const __nv_bfloat16* res_bf16 = nullptr;
+  int ldo = 0, ldr = 0;
+  float out_scale = 1.f;
+  bool pool = false;
+};
+int tc_tile_n(int N);
+int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, const TcItem* items, int n_items,
+                    const TcOut& o, cudaStream_t s);
 
 // rnn_small.cu / rnn_cluster.cu
 int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,

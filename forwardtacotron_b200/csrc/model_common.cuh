@@ -195,6 +195,42 @@ struct ModelBase {
     FTB_REQUIRE(L.w16, FTB_ERR_INVALID, "layer has no bf16 weights packed");
     return conv_gemm_bf16((const bf16*)x, L.w16, d, s);
   }
+
+  // CBHG conv bank (models/common_layers.py:92-100): K convs of x, concatenated along the channel axis,
+  // then MaxPool1d(2,1,1)[:S].  bf16: ONE grouped tcgen05 launch with the pool fused into the epilogue.
+  // fp32 validation mode: one SIMT launch per conv + the stand-alone pool kernel.
+  template <typename T>
+  int conv_bank(const std::vector<Layer>& bank, const T* x, int lda, int B, int S, T* out, int ch, cudaStream_t s) {
+    const int K = (int)bank.size(), bank_c = K * ch;
+    if (std::is_same<T, float>::value) {
+      for (int i = 0; i < K; ++i) FTB_TRY(gemm<T>(bank[i], x, lda, B, S, act_out(out, bank_c, i * ch), nullptr, 0, 1.f, s));
+      ++launches;
+      return maxpool_inplace<T>(out, B, S, bank_c, s);
+    }
+    double flops = 0;
+    std::vector<TcItem> items(K);
+    for (int i = 0; i < K; ++i) {
+      const Layer& L = bank[i];
+      FTB_REQUIRE(L.w16 && L.N == ch, FTB_ERR_INVALID, "conv bank layer %d is not packed for tcgen05", i);
+      items[i].w = L.w16;
+      items[i].N = L.N;
+      items[i].ktaps = L.k;
+      items[i].pad_left = L.pad;
+      items[i].n_offset = i * ch;
+      items[i].relu = L.relu;
+      items[i].bias = L.bias;
+      items[i].scale = L.scale;
+      items[i].shift = L.shift;
+      flops += 2.0 * B * S * (double)L.N * L.k * L.Cin;
+    }
+    TcOut o;
+    o.out_bf16 = (bf16*)out;
+    o.ldo = bank_c;
+    o.pool = true;
+    ++launches;
+    ProfScope prof(FAM_GEMM_TC, flops, 0.0, s);
+    return conv_gemm_group((const bf16*)x, lda, B, S, bank[0].CinP, items.data(), K, o, s);
+  }
 };
 
 }  // namespace ftb

@@ -42,7 +42,7 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
 }
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta) {
   uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
   return r;
 }
 // 16-byte store into a peer CTA's shared memory that signals the peer's mbarrier when it lands
@@ -64,8 +64,8 @@ __device__ __forceinline__ void rnn_mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 24)) break;  // bounded: a protocol bug must not hang the GPU
   }
 }
-__device__ __forceinline__ void cp_async_4(uint32_t dst, const float* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
 template <int G, int H, int CL, int BC>
@@ -80,6 +80,14 @@ struct RnnCfg {
   static constexpr int PAIRS = HC * BC;  // (hidden unit, utterance) pairs per CTA
   static constexpr int PPT = (PAIRS + NT - 1) / NT;
   static constexpr int PRE_LD = BC + 1;
+  static constexpr int XCH = G * PAIRS / 4;            // 16-byte chunks of one step's input pre-activations
+  static constexpr int XPT = (XCH + NT - 1) / NT;      // ... per thread
+  static constexpr int CH = HC / 8;                    // 16-byte chunks per utterance row of the h slice
+  static constexpr int PER_DST = BC * CH;              // chunks pushed to one peer per step
+  static constexpr int PUSH_GROUPS = (NT / PER_DST >= CL) ? CL : (NT / PER_DST >= CL / 2) ? CL / 2
+                                   : (NT / PER_DST >= CL / 4) ? CL / 4 : (NT / PER_DST >= CL / 8) ? CL / 8 : 1;
+  static constexpr int DST_PER_GROUP = CL / PUSH_GROUPS;
+  static_assert(PER_DST <= NT && PUSH_GROUPS >= 1 && CL % PUSH_GROUPS == 0, "push mapping");
   static constexpr uint32_t TX_BYTES = CL * BC * HC * 2;  // one full h_t (all slices) per phase
   static constexpr size_t OFF_STAGE = sizeof(__nv_bfloat16) * 2 * BC * HP;
   static constexpr size_t OFF_PRE = OFF_STAGE + sizeof(__nv_bfloat16) * BC * HC;
@@ -141,7 +149,6 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
 
   // ---- per-thread (unit, utterance) pairs ------------------------------------------
   float cstate[PPT], hprev[PPT], bhn[PPT];
-  const float* xptr[PPT];
   int64_t optr[PPT];
   bool pvalid[PPT];
 #pragma unroll
@@ -153,20 +160,28 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
     hprev[p] = 0.f;
     const int hu = rank * HC + u;
     bhn[p] = (G == 3 && pvalid[p]) ? b_hn[dir * H + hu] : 0.f;
-    xptr[p] = xg + (((int64_t)(b0 + n) * S) * 2 + dir) * (G * H) + hu;
     optr[p] = ((int64_t)(b0 + n) * S) * (2 * H) + dir * H + hu;
   }
   __syncthreads();  // xs zero-fill done before the first cp.async lands on it
-  auto prefetch_x = [&](int step) {  // input pre-activations of `step` -> xs[step & 1]
+  // input pre-activations of `step` -> xs[step & 1], layout [g][n][u] (same index as the pair id),
+  // moved as 16-byte chunks: chunk c = (g, n, 4 consecutive units)
+  const float* xsrc[C::XPT];
+  uint32_t xdst[C::XPT];
+#pragma unroll
+  for (int i = 0; i < C::XPT; ++i) {
+    const int c = tid + i * NT;
+    const int g = c / (PAIRS / 4), rem = c % (PAIRS / 4);
+    const int n = rem / (HC / 4), u4 = rem % (HC / 4);
+    const bool ok = c < C::XCH && (b0 + n) < B;
+    xsrc[i] = ok ? xg + (((int64_t)(b0 + n) * S) * 2 + dir) * (G * H) + g * H + rank * HC + u4 * 4 : nullptr;
+    xdst[i] = smem_u32(xs + g * PAIRS + n * HC + u4 * 4);
+  }
+  auto prefetch_x = [&](int step) {
     const int tt = dir ? S - 1 - step : step;
-    const uint32_t dst = smem_u32(xs + (step & 1) * G * PAIRS);
+    const uint32_t boff = (uint32_t)((step & 1) * G * PAIRS * 4);
 #pragma unroll
-    for (int p = 0; p < PPT; ++p)
-      if (pvalid[p]) {
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-          cp_async_4(dst + 4 * (g * PAIRS + tid + p * NT), xptr[p] + (int64_t)tt * 2 * G * H + g * H);
-      }
+    for (int i = 0; i < C::XPT; ++i)
+      if (xsrc[i]) cp_async_16(xdst[i] + boff, xsrc[i] + (int64_t)tt * 2 * G * H);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   prefetch_x(0);
@@ -177,6 +192,13 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
   const int lm4_n = (NTL == 1) ? i8 : (q >> 1) * 8 + i8;  // x4: two n tiles (or two k tiles when BC == 8)
   const int lm4_k = (NTL == 1) ? q * 8 : (q & 1) * 8;
   const int lm2_n = i8, lm2_k = (q & 1) * 8;              // x2: one n tile
+
+  // push mapping: thread -> (peer group, utterance row, 16-byte chunk); peer CTA `d` sees this CTA's shared
+  // window at local address + dsm_base + d * dsm_stride (shared::cluster addresses are linear in the rank)
+  const int push_grp = tid / C::PER_DST, push_n = (tid % C::PER_DST) / C::CH, push_ch = tid % C::CH;
+  const uint32_t hbuf_u32 = smem_u32(hbuf);
+  const uint32_t dsm_base = map_to_cta(hbuf_u32, 0) - hbuf_u32;
+  const uint32_t dsm_stride = map_to_cta(hbuf_u32, 1) - map_to_cta(hbuf_u32, 0);
 
   for (int s = 0; s < S; ++s) {
     const int cur = s & 1;
@@ -256,16 +278,16 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
         const int u = idx % HC, n = idx / HC;
         float hn;
         if (G == 4) {  // LSTM, gate order i, f, g, o; biases folded into xg
-          const float gi = sigmoidf_(xc[0 * PAIRS + idx] + pre[(0 * HC + u) * PRE_LD + n]);
-          const float gf = sigmoidf_(xc[1 * PAIRS + idx] + pre[(1 * HC + u) * PRE_LD + n]);
-          const float gg = tanhf_(xc[2 * PAIRS + idx] + pre[(2 * HC + u) * PRE_LD + n]);
-          const float go = sigmoidf_(xc[(3 % G) * PAIRS + idx] + pre[((3 % G) * HC + u) * PRE_LD + n]);
+          const float gi = sigmoid_fast(xc[0 * PAIRS + idx] + pre[(0 * HC + u) * PRE_LD + n]);
+          const float gf = sigmoid_fast(xc[1 * PAIRS + idx] + pre[(1 * HC + u) * PRE_LD + n]);
+          const float gg = tanh_fast(xc[2 * PAIRS + idx] + pre[(2 * HC + u) * PRE_LD + n]);
+          const float go = sigmoid_fast(xc[(3 % G) * PAIRS + idx] + pre[((3 % G) * HC + u) * PRE_LD + n]);
           cstate[p] = gf * cstate[p] + gi * gg;
-          hn = go * tanhf_(cstate[p]);
+          hn = go * tanh_fast(cstate[p]);
         } else {  // GRU, gate order r, z, n; b_hn stays inside r * (.)
-          const float gr = sigmoidf_(xc[0 * PAIRS + idx] + pre[(0 * HC + u) * PRE_LD + n]);
-          const float gz = sigmoidf_(xc[1 * PAIRS + idx] + pre[(1 * HC + u) * PRE_LD + n]);
-          const float gn = tanhf_(xc[2 * PAIRS + idx] + gr * (pre[(2 * HC + u) * PRE_LD + n] + bhn[p]));
+          const float gr = sigmoid_fast(xc[0 * PAIRS + idx] + pre[(0 * HC + u) * PRE_LD + n]);
+          const float gz = sigmoid_fast(xc[1 * PAIRS + idx] + pre[(1 * HC + u) * PRE_LD + n]);
+          const float gn = tanh_fast(xc[2 * PAIRS + idx] + gr * (pre[(2 * HC + u) * PRE_LD + n] + bhn[p]));
           hn = (1.f - gz) * gn + gz * hprev[p];
         }
         hprev[p] = hn;
@@ -282,16 +304,16 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
     __syncthreads();
     // 5. push this CTA's slice of h_t into every CTA's next-step buffer; each 16-byte st.async
     //    completes bytes on the destination CTA's mbarrier for that buffer
-    if (s + 1 < S) {
-      constexpr int CH = HC / 8;  // 16B chunks per utterance row of the slice
-      constexpr int PER_DST = BC * CH;
-      const uint32_t dst_local = smem_u32(hbuf + ((cur ^ 1) * BC) * HP + rank * HC);
-      const uint32_t bar_local = bar0 + 8 * (cur ^ 1);
-      for (int i = tid; i < CL * PER_DST; i += NT) {
-        const int d = (i / PER_DST + rank) % CL, rem = i % PER_DST;
-        const int n = rem / CH, ch = rem % CH;
-        const uint4 v = *reinterpret_cast<const uint4*>(hstage + n * HC + ch * 8);
-        st_async_16(map_to_cta(dst_local + 2 * (n * HP + ch * 8), d), v, map_to_cta(bar_local, d));
+    if (s + 1 < S && tid < C::PUSH_GROUPS * C::PER_DST) {
+      const uint32_t off = (uint32_t)(((cur ^ 1) * BC + push_n) * HP + rank * HC + push_ch * 8) * 2;
+      const uint4 v = *reinterpret_cast<const uint4*>(hstage + push_n * HC + push_ch * 8);
+      const uint32_t bar_off = 8 * (cur ^ 1);
+#pragma unroll
+      for (int j = 0; j < C::DST_PER_GROUP; ++j) {
+        // peer order is rotated by the own rank so the 16 CTAs do not all hit the same peer at once
+        const uint32_t d = (uint32_t)((push_grp * C::DST_PER_GROUP + j + rank) % CL);
+        const uint32_t rb = dsm_base + d * dsm_stride;
+        st_async_16(hbuf_u32 + rb + off, v, bar0 + rb + bar_off);
       }
     }
   }

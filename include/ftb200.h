@@ -120,6 +120,13 @@ typedef struct ftb_conv_desc {
 int ftb_conv_gemm_f32(const float* x, const float* w_packed, const ftb_conv_desc* d, void* stream);
 /* tcgen05 / TMA kernel: x (B,S,lda) bf16, w bf16 (N, k*Cin) with Cin % 64 == 0. */
 int ftb_conv_gemm_bf16(const void* x, const void* w_packed, const ftb_conv_desc* d, void* stream);
+/* CBHG conv bank, models/common_layers.py:92-100: n_convs (<= 16) convs of the SAME input, written side by
+ * side into one (B,S,ldo) tensor at their n_offset (the reference's torch.cat), optionally followed by
+ * MaxPool1d(kernel 2, stride 1, padding 1)[:S] along t -- out[t] = max(y[t-1], y[t]), out[0] = y[0] -- fused
+ * into the epilogue.  One persistent tcgen05 launch.  descs[i] share B, S, Cin, lda, ldo and the output
+ * pointers; no residual / transposed output.  All N must select the same tile width (equal N is enough). */
+int ftb_conv_bank_bf16(const void* x, const void* const* w_packed, const ftb_conv_desc* descs, int n_convs,
+                       int maxpool, void* stream);
 /* Every mbarrier wait in the tcgen05 kernel is bounded so a protocol bug cannot hang the GPU;
  * this returns how many waits gave up since the library was loaded (0 in a healthy run). */
 int ftb_tc_timeout_count(void);

@@ -107,3 +107,46 @@ def test_tc_large_k_and_batch():
     got, _ = run_kernel(x, w, 3, True, None, None, None, None, 1.0, True)
     assert float((got - want).abs().max()) < 5e-3
     assert _lib.lib().ftb_tc_timeout_count() == 0
+
+
+@pytest.mark.parametrize('B,S,Cin,ch,K', [(2, 50, 256, 256, 16), (3, 300, 80, 256, 8), (1, 127, 64, 256, 3),
+                                          (2, 128, 64, 128, 4), (1, 255, 128, 256, 5)])
+@pytest.mark.parametrize('pool', [True, False])
+def test_conv_bank_grouped(B, S, Cin, ch, K, pool):
+    """The whole CBHG bank (k = 1..K, ReLU -> BN, concat) + MaxPool1d(2,1,1)[:S] in one grouped launch."""
+    lib = _lib.lib()
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(S + K)
+    x = torch.randn(B, S, Cin, generator=g).bfloat16().float()
+    cin_pad = (Cin + 63) // 64 * 64
+    xd = torch.zeros(B, S, cin_pad, dtype=torch.bfloat16, device=dev)
+    xd[:, :, :Cin] = x.to(dev)
+    out = torch.full((B, S, K * ch + 8), 7.0, dtype=torch.float32, device=dev)
+    descs = (_lib.ConvDesc * K)()
+    wptrs = (C.c_void_p * K)()
+    keep, wants = [], []
+    for i in range(K):
+        k = i + 1
+        w = (torch.randn(ch, Cin, k, generator=g) / (Cin * k) ** 0.5).bfloat16().float()
+        scale = torch.rand(ch, generator=g) - 0.3          # negative scales: BN does not commute with the pool
+        shift = torch.randn(ch, generator=g) * 0.1
+        wants.append(reference(x, w, k, True, scale, shift, None, None, 1.0))
+        wp = torch.empty(ch * k * cin_pad, dtype=torch.bfloat16, device=dev)
+        wdev = w.to(dev).contiguous()
+        _lib.check(lib.ftb_pack_conv_weight(_lib.ptr(wdev), _lib.ptr(wp), ch, Cin, k, ch, cin_pad, 1, None))
+        sd, hd = scale.to(dev), shift.to(dev)
+        keep += [wp, wdev, sd, hd]
+        d = descs[i]
+        d.B, d.S, d.Cin, d.N, d.ktaps, d.pad_left = B, S, cin_pad, ch, k, k // 2
+        d.lda, d.ldo, d.n_offset, d.relu = cin_pad, K * ch + 8, i * ch, 1
+        d.scale, d.shift, d.out_scale, d.out_f32 = sd.data_ptr(), hd.data_ptr(), 1.0, out.data_ptr()
+        wptrs[i] = wp.data_ptr()
+    _lib.check(lib.ftb_conv_bank_bf16(_lib.ptr(xd), wptrs, descs, K, int(pool), _lib.current_stream(dev)))
+    torch.cuda.synchronize()
+    want = torch.cat(wants, dim=2)
+    if pool:
+        want = F.max_pool1d(want.transpose(1, 2), kernel_size=2, stride=1, padding=1)[:, :, :S].transpose(1, 2)
+    got = out.cpu()
+    assert float((got[:, :, :K * ch] - want).abs().max()) < 3e-3
+    assert torch.all(got[:, :, K * ch:] == 7.0)
+    assert lib.ftb_tc_timeout_count() == 0
