@@ -160,8 +160,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile) {
 __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcArgs a) {
   using namespace tc;
   extern __shared__ unsigned char smem_dyn[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
-  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  // SWIZZLE_128B tiles need 1024-byte alignment (offset arithmetic keeps the pointer in the shared space)
+  unsigned char* tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   float* staging_all = reinterpret_cast<float*>(tiles + SMEM_TILES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + SMEM_TILES + SMEM_STAGING);
   // full[STAGES], empty[STAGES], tfull[2], tempty[2]
@@ -242,17 +242,26 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
     const int ew = warp - 2, q = warp & 3, half = ew >> 2;  // TMEM lane quarter, column half
     float* stg = staging_all + (half * 4 + q) * 32 * STG_LD;
     const float* stg_prev = staging_all + (half * 4 + (q > 0 ? q - 1 : 0)) * 32 * STG_LD;  // pool halo row
-    const bool row_major = a.out_f32 || a.out_bf16;
+    const bool has_o32 = a.out_f32 != nullptr, has_o16 = a.out_bf16 != nullptr, has_ot = a.out_t != nullptr;
+    const bool has_r32 = a.res_f32 != nullptr, has_r16 = a.res_bf16 != nullptr;
+    const bool row_major = has_o32 || has_o16, pool = a.pool != 0;
+    const int64_t ldo = a.ldo, ldr = a.ldr;
+    const float out_scale = a.out_scale;
+    const int S = a.S;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tl) {
       const TileCoord c = decode_tile(a, tile);
       const TcProb& P = a.prob[c.p];
       const uint32_t buf = tl & 1;
-      const int ncols = min(a.bn, P.N - c.n0);
+      const int pN = P.N;
+      const int ncols = min(a.bn, pN - c.n0);
       const int nchunks = (ncols + 31) >> 5;
+      const float relu_lo = P.relu ? 0.f : -INFINITY;
+      const int trow0 = c.t0 + q * 32;                 // time index of this warp's first accumulator row
+      const int nrows = max(0, min(32, S - trow0));    // rows of this quarter inside the utterance
+      const int64_t mrow0 = (int64_t)c.b * S + trow0;  // flattened (b, t) row of accumulator row 0 of the quarter
       mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t mbase = (int64_t)c.b * a.S;
       bool released = false;
       for (int ch = half; ch < nchunks; ch += 2) {
         uint32_t r[32];
@@ -264,66 +273,62 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
           released = true;
         }
         const int nb = c.n0 + ch * 32;  // first output column of the chunk
-        if (a.out_t) {                  // (B,N,S) output: lanes walk t (coalesced along the time axis)
-          const int t = c.t0 + q * 32 + lane;
-          if (t < a.S) {
+        if (has_ot) {                   // (B,N,S) output: lanes walk t (coalesced along the time axis)
+          const int t = trow0 + lane;
+          if (t < S) {
             EpiParams e;
             e.bias = P.bias, e.scale = P.scale, e.shift = P.shift, e.res_f32 = a.res_f32, e.res_bf16 = a.res_bf16;
-            e.relu = P.relu, e.ldr = a.ldr, e.out_scale = a.out_scale;
+            e.relu = P.relu, e.ldr = a.ldr, e.out_scale = out_scale;
+            float* ot = a.out_t + ((int64_t)c.b * a.n_total + nb) * S + t;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int n = nb + i;
-              if (n < P.N) a.out_t[((int64_t)c.b * a.n_total + n) * a.S + t] = epi_value(e, mbase + t, n, __uint_as_float(r[i]));
-            }
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < pN) ot[(int64_t)i * S] = epi_value(e, mrow0 + lane, nb + i, __uint_as_float(r[i]));
           }
         }
         if (row_major) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = __uint_as_float(r[i]);
-          if (a.pool)
+          if (pool)
             asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // the 4 quarters of this column half
           else
             __syncwarp();
           const int n = nb + lane;
-          const bool nok = n < P.N;
+          const bool nok = n < pN;
           const float bias = (nok && P.bias) ? __ldg(P.bias + n) : 0.f;
           const float scale = (nok && P.scale) ? __ldg(P.scale + n) : 1.f;
           const float shift = (nok && P.shift) ? __ldg(P.shift + n) : 0.f;
-          const bool relu = P.relu != 0;
-          auto affine = [&](float v) {
-            v += bias;
-            if (relu) v = fmaxf(v, 0.f);
-            return fmaf(v, scale, shift);
-          };
-          const int col = P.n_offset + n;
-          if (!a.pool) {
-            for (int rr = 0; rr < 32; ++rr) {
-              const int t = c.t0 + q * 32 + rr;
-              if (t >= a.S) break;
-              const int64_t m = mbase + t;
-              float v = affine(stg[rr * STG_LD + lane]);
-              if (nok) {
-                if (a.res_f32) v += a.res_f32[m * a.ldr + n];
-                if (a.res_bf16) v += __bfloat162float(a.res_bf16[m * a.ldr + n]);
-                v *= a.out_scale;
-                if (a.out_f32) a.out_f32[m * a.ldo + col] = v;
-                if (a.out_bf16) a.out_bf16[m * a.ldo + col] = __float2bfloat16_rn(v);
+          const int64_t ooff = mrow0 * ldo + P.n_offset + n;
+          float* o32 = a.out_f32 + ooff;
+          __nv_bfloat16* o16 = a.out_bf16 + ooff;
+          const float* sp = stg + lane;
+          if (!pool) {
+            const float* r32 = a.res_f32 + mrow0 * ldr + n;
+            const __nv_bfloat16* r16 = a.res_bf16 + mrow0 * ldr + n;
+            if (nok) {
+#pragma unroll 4
+              for (int rr = 0; rr < nrows; ++rr) {
+                float v = fmaf(fmaxf(sp[rr * STG_LD] + bias, relu_lo), scale, shift);
+                if (has_r32) v += r32[rr * ldr];
+                if (has_r16) v += __bfloat162float(r16[rr * ldr]);
+                v *= out_scale;
+                if (has_o32) o32[rr * ldo] = v;
+                if (has_o16) o16[rr * ldo] = __float2bfloat16_rn(v);
               }
             }
           } else {  // out[t] = max(v[t-1], v[t]); tile row 0 is the halo row t0 = first output row - 1
             float prev = -INFINITY;
-            if (q > 0) prev = affine(stg_prev[31 * STG_LD + lane]);
-            for (int rr = 0; rr < 32; ++rr) {
-              const int i = q * 32 + rr, t = c.t0 + i;
-              if (t >= a.S) break;
-              const float cur = affine(stg[rr * STG_LD + lane]);
-              if (i >= 1 && nok) {
-                const int64_t m = mbase + t;
-                const float v = fmaxf(prev, cur) * a.out_scale;
-                if (a.out_f32) a.out_f32[m * a.ldo + col] = v;
-                if (a.out_bf16) a.out_bf16[m * a.ldo + col] = __float2bfloat16_rn(v);
+            if (q > 0) prev = fmaf(fmaxf(stg_prev[31 * STG_LD + lane] + bias, relu_lo), scale, shift);
+            if (nok) {
+#pragma unroll 4
+              for (int rr = 0; rr < nrows; ++rr) {
+                const float cur = fmaf(fmaxf(sp[rr * STG_LD] + bias, relu_lo), scale, shift);
+                if (q + rr > 0) {  // not the halo row
+                  const float v = fmaxf(prev, cur) * out_scale;
+                  if (has_o32) o32[rr * ldo] = v;
+                  if (has_o16) o16[rr * ldo] = __float2bfloat16_rn(v);
+                }
+                prev = trow0 + rr >= 0 ? cur : -INFINITY;
               }
-              prev = t >= 0 ? cur : -INFINITY;
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // neighbours finished with my row 31
           }
