@@ -157,6 +157,43 @@ __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile) {
   return c;
 }
 
+// Epilogue phase 2 for one 32x32 chunk: lane = output column, rows walk the time axis.  Specialised on
+// which outputs / residuals exist so the row loop is branch-free: LDS, 3-4 FP ops, coalesced LDG/STG.
+struct EpiCol {
+  float bias, relu_lo, scale, shift, out_scale;
+};
+__device__ __forceinline__ float epi_affine(const EpiCol& e, float acc) {
+  return fmaf(fmaxf(acc + e.bias, e.relu_lo), e.scale, e.shift);
+}
+template <int OUT /*1 f32, 2 bf16, 3 both*/, int RES /*0 none, 1 f32, 2 bf16*/>
+__device__ __forceinline__ void epi_rows(const float* sp, int nrows, const EpiCol& e, float* o32, __nv_bfloat16* o16,
+                                         int64_t ldo, const float* r32, const __nv_bfloat16* r16, int64_t ldr) {
+#pragma unroll 8
+  for (int rr = 0; rr < nrows; ++rr) {
+    float v = epi_affine(e, sp[rr * tc::STG_LD]);
+    if (RES == 1) v += *r32, r32 += ldr;
+    if (RES == 2) v += __bfloat162float(*r16), r16 += ldr;
+    v *= e.out_scale;
+    if (OUT & 1) *o32 = v, o32 += ldo;
+    if (OUT & 2) *o16 = __float2bfloat16_rn(v), o16 += ldo;
+  }
+}
+template <int OUT>
+__device__ __forceinline__ void epi_rows_pool(const float* sp, int nrows, const EpiCol& e, float prev, bool first_is_halo,
+                                              int trow0, float* o32, __nv_bfloat16* o16, int64_t ldo) {
+#pragma unroll 8
+  for (int rr = 0; rr < nrows; ++rr) {
+    const float cur = epi_affine(e, sp[rr * tc::STG_LD]);
+    if (!(first_is_halo && rr == 0)) {
+      const float v = fmaxf(prev, cur) * e.out_scale;
+      if (OUT & 1) *o32 = v;
+      if (OUT & 2) *o16 = __float2bfloat16_rn(v);
+    }
+    o32 += ldo, o16 += ldo;
+    prev = trow0 + rr >= 0 ? cur : -INFINITY;
+  }
+}
+
 __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcArgs a) {
   using namespace tc;
   extern __shared__ unsigned char smem_dyn[];
@@ -294,42 +331,38 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
             __syncwarp();
           const int n = nb + lane;
           const bool nok = n < pN;
-          const float bias = (nok && P.bias) ? __ldg(P.bias + n) : 0.f;
-          const float scale = (nok && P.scale) ? __ldg(P.scale + n) : 1.f;
-          const float shift = (nok && P.shift) ? __ldg(P.shift + n) : 0.f;
+          EpiCol e;
+          e.bias = (nok && P.bias) ? __ldg(P.bias + n) : 0.f;
+          e.scale = (nok && P.scale) ? __ldg(P.scale + n) : 1.f;
+          e.shift = (nok && P.shift) ? __ldg(P.shift + n) : 0.f;
+          e.relu_lo = relu_lo;
+          e.out_scale = out_scale;
           const int64_t ooff = mrow0 * ldo + P.n_offset + n;
           float* o32 = a.out_f32 + ooff;
           __nv_bfloat16* o16 = a.out_bf16 + ooff;
           const float* sp = stg + lane;
+          const int nr = nok ? nrows : 0;
           if (!pool) {
             const float* r32 = a.res_f32 + mrow0 * ldr + n;
             const __nv_bfloat16* r16 = a.res_bf16 + mrow0 * ldr + n;
-            if (nok) {
-#pragma unroll 4
-              for (int rr = 0; rr < nrows; ++rr) {
-                float v = fmaf(fmaxf(sp[rr * STG_LD] + bias, relu_lo), scale, shift);
-                if (has_r32) v += r32[rr * ldr];
-                if (has_r16) v += __bfloat162float(r16[rr * ldr]);
-                v *= out_scale;
-                if (has_o32) o32[rr * ldo] = v;
-                if (has_o16) o16[rr * ldo] = __float2bfloat16_rn(v);
-              }
+            if (has_o16 && !has_o32) {
+              if (has_r16) epi_rows<2, 2>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
+              else if (has_r32) epi_rows<2, 1>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
+              else epi_rows<2, 0>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
+            } else if (has_o32 && !has_o16) {
+              if (has_r32) epi_rows<1, 1>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
+              else if (has_r16) epi_rows<1, 2>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
+              else epi_rows<1, 0>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
+            } else {
+              if (has_r32) epi_rows<3, 1>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
+              else if (has_r16) epi_rows<3, 2>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
+              else epi_rows<3, 0>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
             }
           } else {  // out[t] = max(v[t-1], v[t]); tile row 0 is the halo row t0 = first output row - 1
-            float prev = -INFINITY;
-            if (q > 0) prev = fmaf(fmaxf(stg_prev[31 * STG_LD + lane] + bias, relu_lo), scale, shift);
-            if (nok) {
-#pragma unroll 4
-              for (int rr = 0; rr < nrows; ++rr) {
-                const float cur = fmaf(fmaxf(sp[rr * STG_LD] + bias, relu_lo), scale, shift);
-                if (q + rr > 0) {  // not the halo row
-                  const float v = fmaxf(prev, cur) * out_scale;
-                  if (has_o32) o32[rr * ldo] = v;
-                  if (has_o16) o16[rr * ldo] = __float2bfloat16_rn(v);
-                }
-                prev = trow0 + rr >= 0 ? cur : -INFINITY;
-              }
-            }
+            const float prev = q > 0 ? epi_affine(e, stg_prev[31 * STG_LD + lane]) : -INFINITY;
+            if (has_o16 && !has_o32) epi_rows_pool<2>(sp, nr, e, prev, q == 0, trow0, o32, o16, ldo);
+            else if (has_o32 && !has_o16) epi_rows_pool<1>(sp, nr, e, prev, q == 0, trow0, o32, o16, ldo);
+            else epi_rows_pool<3>(sp, nr, e, prev, q == 0, trow0, o32, o16, ldo);
             asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // neighbours finished with my row 31
           }
           __syncwarp();
