@@ -113,6 +113,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
   // 2^126 < e + 1 makes __fdividef return 0, which is the right limit (tanh -> 1)
   return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);
 }
+// One-MUFU variants (tanh.approx.f32, max relative error 2^-11): the recurrence kernels are bound by the SFU pipe
+// (16 lanes/clk/SM) once the matmul is off the critical path; the error is 4x below the bf16 rounding of the
+// recurrent operand h that the same kernels already apply.
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(tanh_mufu(0.5f * x), 0.5f, 0.5f); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

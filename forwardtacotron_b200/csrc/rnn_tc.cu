@@ -27,9 +27,6 @@ namespace cg = cooperative_groups;
 namespace ftb {
 
 namespace rt {
-constexpr int GATE_WARPS = 8, THREADS = 32 * (1 + GATE_WARPS);
-constexpr int NCOL = 16;       // utterances per sub-chunk = N of the MMA
-constexpr int PRE_LD = 12;     // floats per row of the per-warp regroup buffer (48 B: float4 / float2 aligned)
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
 __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t cta) {
@@ -66,12 +63,29 @@ __device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, u
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// K-major SWIZZLE_128B descriptor: SBO = 8 rows * 128 B = 1024, version 1, layout type 2
+__device__ __forceinline__ uint64_t adesc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// D[tmem] (+)= A[smem] . B[smem]
+__device__ __forceinline__ void umma_ss_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -87,41 +101,71 @@ __device__ __forceinline__ void bulk_push(uint32_t dst_cluster, uint32_t src_cta
 }
 }  // namespace rt
 
-template <int G, int H, int CL, int NSUB>
+// Optional step-phase timing (developer tool, scripts/rnn_phase_timing.py): when set, thread 0 of CTA (0,0,0) records
+// SM clock stamps of the first 64 steps.  Slots per step: 2 accumulator ready, 3 TMEM read, 4 gate maths + stores done,
+// 5 after fences + barrier, 6 pushes issued, 7 own slices landed and next step's MMAs issued.
+__device__ long long* g_rnn_dbg = nullptr;
+#define RNN_STAMP(slot)                                                                  \
+  do {                                                                                   \
+    if (dbg && s < 64) dbg[s * 8 + (slot)] = clock64();                                   \
+  } while (0)
+
+template <int G, int H, int CL, int NCOLS, int CW, int UC>
 struct RtCfg {
   static constexpr int HC = H / CL;                  // hidden units per CTA
-  static constexpr int KSTEPS = H / 16;              // MMAs per step and sub-chunk
-  static constexpr int WCOLS = H / 2;                // TMEM columns holding the W slice (2 bf16 per column)
-  static constexpr int DCOL0 = WCOLS;                // accumulators follow
-  static constexpr uint32_t TMEM_COLS = (WCOLS + NSUB * rt::NCOL <= 256) ? 256 : 512;
-  static constexpr uint32_t HB_BYTES = rt::NCOL * H * 2;    // one B-operand buffer
-  static constexpr uint32_t SBO = (H / 8) * 128;            // bytes between 8-utterance groups
-  static constexpr uint32_t SLICE = (HC / 8) * 128;         // this CTA's units for one 8-utterance group
-  static constexpr size_t OFF_PRE = (size_t)NSUB * 2 * HB_BYTES;
-  static constexpr size_t OFF_BAR = OFF_PRE + sizeof(float) * rt::GATE_WARPS * 32 * rt::PRE_LD;
-  static constexpr size_t SMEM_USED = OFF_BAR + 8 * (NSUB * 2 + NSUB) + 16;
+  static constexpr int KSPLIT = 2;                   // accumulators (slice r adds into accumulator r % KSPLIT)
+  static constexpr uint32_t TMEM_COLS = (KSPLIT * NCOLS <= 32) ? 32 : (KSPLIT * NCOLS <= 64) ? 64 : 128;
+  // W slice = A operand in shared memory, K-major SWIZZLE_128B (the layout TMA produces for the GEMM kernel):
+  // k-block kb (64 units) is a 128-row x 128-byte tile at kb*16 KB; row m at m*128; the 16-byte chunk c of a row
+  // (8 units) sits at chunk position c ^ (m % 8).
+  static constexpr uint32_t W_BYTES = 128 * H * 2;
+  static constexpr int NCG = UC / CW;                // column groups (of the UC columns that can carry data) = warps per TMEM lane quarter
+  static constexpr int WARPS = 4 * NCG, THREADS = 32 * WARPS;
+  static constexpr int PPT = CW / 4;                 // (unit, utterance) pairs per thread
+  static constexpr uint32_t SL = (NCOLS / 8) * 512;  // bytes of one CTA's slice (32 units x NCOLS utterances)
+  static constexpr uint32_t HB_BYTES = CL * SL;      // one B-operand buffer = NCOLS x H bf16
+  static constexpr int PRE_LD = CW + 4;              // floats per row of the per-warp regroup buffer
+  static constexpr size_t OFF_W = (size_t)2 * HB_BYTES;
+  static constexpr size_t OFF_PRE = OFF_W + W_BYTES;
+  static constexpr size_t OFF_BAR = OFF_PRE + sizeof(float) * WARPS * 32 * PRE_LD;
+  static constexpr int NBAR = 2 * CL + 1;            // h_full[buf][slice] + d_full
+  static constexpr size_t SMEM_USED = OFF_BAR + 8 * NBAR + 16;
   // one CTA per SM: the occupancy calculator does not know about TMEM, and a second resident CTA would block in
   // tcgen05.alloc behind the first one's columns
   static constexpr size_t SMEM = SMEM_USED > 120 * 1024 ? SMEM_USED : 120 * 1024;
-  // D=f32, A=B=bf16, K-major, M=128, N=16
-  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(rt::NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // D=f32, A=B=bf16, K-major, M=128, N=NCOLS
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static_assert(HC == 32 && G <= 4 && H % 64 == 0, "unsupported RNN tiling: 32 hidden units x 4 gate rows per CTA");
+  static_assert(NCOLS % 16 == 0 && UC <= NCOLS && UC % CW == 0 && (CW == 4 || CW == 8) && WARPS <= 16, "unsupported column tiling");
 };
 
-template <int G, int H, int CL, int NSUB>
-__global__ void __launch_bounds__(rt::THREADS, 1)
+// B operand of one step: NCOLS x H bf16, K-major, no swizzle, stored slice-major so that the 32 hidden units a
+// CTA produces are ONE contiguous block (one bulk copy per peer):
+//   byte offset of (utterance n, unit k) = (k/32)*SL + (n/8)*512 + ((k%32)/8)*128 + (n%8)*16 + (k%8)*2
+// A 16-wide MMA k-step never straddles a slice, so inside one instruction LBO (next 8 units) = 128 B and
+// SBO (next 8 utterances) = 512 B are uniform.
+//
+// Every warp is gate warp AND MMA issuer.  Issuing one tcgen05.mma costs the issuing thread ~60-90 cycles however
+// small N is (measured, scripts/rnn_phase_timing.py), so the 2*CL MMAs of a step are issued by up to 16 threads in
+// parallel: warp w owns slices w, w + WARPS, ... (ring order from the own slice), waits for exactly those slices
+// to land and issues their two MMAs into accumulator (slice % KSPLIT).  All MMAs accumulate; the accumulators are
+// cleared by the warps right after they read them.
+template <int G, int H, int CL, int NCOLS, int CW, int UC>
+__global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
     rnn_tc_kernel(const float* __restrict__ xg,    // (B,S,2,G*H)
                   const float* __restrict__ w_hh,  // (2,G*H,H)
                   const float* __restrict__ b_hn,  // (2,H) GRU only
                   void* __restrict__ out, int B, int S, int out_bf16, int bc) {
-  using C = RtCfg<G, H, CL, NSUB>;
+  using C = RtCfg<G, H, CL, NCOLS, CW, UC>;
   using namespace rt;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int THREADS = C::THREADS, WARPS = C::WARPS, PRE_LD = C::PRE_LD, PPT = C::PPT, KSPLIT = C::KSPLIT;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* pre_all = reinterpret_cast<float*>(smem_raw + C::OFF_PRE);
-  const uint32_t hb0 = smem_u32(smem_raw);                   // hB[c][buf] at hb0 + (c*2 + buf) * HB_BYTES
-  const uint32_t bar0 = smem_u32(smem_raw + C::OFF_BAR);     // h_full[c][buf] at bar0 + 8*(c*2+buf); d_full[c] after
-  const uint32_t dfull0 = bar0 + 8 * NSUB * 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + C::OFF_BAR + 8 * (NSUB * 2 + NSUB));
+  const uint32_t hb0 = smem_u32(smem_raw);                // hB[buf] at hb0 + buf * HB_BYTES
+  const uint32_t bar0 = smem_u32(smem_raw + C::OFF_BAR);  // h_full[buf][slice] at bar0 + 8*(buf*CL + slice); then d_full
+  const uint32_t dfull = bar0 + 8 * 2 * CL;
+  const uint32_t wa0 = smem_u32(smem_raw + C::OFF_W);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + C::OFF_BAR + 8 * C::NBAR);
 
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
@@ -129,9 +173,10 @@ __global__ void __launch_bounds__(rt::THREADS, 1)
   const int nvalid = min(bc, B - b0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < (int)(C::OFF_PRE / 16); i += THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (int)(C::OFF_W / 16); i += THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    for (int i = 0; i < NSUB * 2 + NSUB; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+    for (int i = 0; i < C::NBAR; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(i == C::NBAR - 1 ? WARPS : 1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -145,26 +190,33 @@ __global__ void __launch_bounds__(rt::THREADS, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  // gate-warp geometry: TMEM lane quarter q, accumulator row 32q + lane = (unit 8q + lane/4, gate lane%4)
-  const int q = warp & 3, half = warp >= 1 ? (warp - 1) >> 2 : 0;
+  // warp geometry: TMEM lane quarter q, accumulator row 32q + lane = (unit 8q + lane/4, gate lane%4);
+  // column group cgp = the CW utterances this warp handles
+  const int q = warp & 3, cgp = warp >> 2;
   const int u_local = 8 * q + (lane >> 2), sub = lane & 3;
   const int hu = (int)rank * C::HC + u_local;  // hidden unit of the gate maths this thread does
+  const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + cgp * CW;  // this warp's window of accumulator 0
 
-  if (warp >= 1) {  // ---- W_hh slice -> TMEM (bf16 pairs); the two warps of a quarter split the columns
-    const int g = sub;
+  {  // ---- W_hh slice -> shared memory (bf16, UMMA K-major cells); the warps of a quarter split K
+    const int g = sub, m = 32 * q + lane;
     const float* wrow = w_hh + ((int64_t)(dir * G + (g < G ? g : 0)) * H + hu) * H;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c8 = half * (C::WCOLS / 16); c8 < (half + 1) * (C::WCOLS / 16); ++c8) {
-      uint32_t r[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < G) v = *reinterpret_cast<const float4*>(wrow + c8 * 16 + i * 4);
-        r[2 * i] = pack_bf16x2(v.x, v.y);
-        r[2 * i + 1] = pack_bf16x2(v.z, v.w);
+    unsigned char* wdst = smem_raw + C::OFF_W + m * 128;
+    constexpr int PER = H / 8 / C::NCG;  // 8-unit chunks per warp
+    for (int kc = cgp * PER; kc < (cgp + 1) * PER; ++kc) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (g < G) {
+        const float4 a = *reinterpret_cast<const float4*>(wrow + kc * 8), b = *reinterpret_cast<const float4*>(wrow + kc * 8 + 4);
+        v = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
       }
-      tmem_st8(trow + c8 * 8, r);
+      *reinterpret_cast<uint4*>(wdst + (kc >> 3) * 16384 + (((kc & 7) ^ (m & 7)) << 4)) = v;
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the UMMA reads
+    // clear the accumulators (step 0 reads them without any MMA: h_{-1} = 0)
+    const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < KSPLIT; ++a)
+#pragma unroll
+      for (int i = 0; i < CW; i += 4) tmem_st4(tacc + a * NCOLS + i, z);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -172,129 +224,175 @@ __global__ void __launch_bounds__(rt::THREADS, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   cluster.sync();  // every CTA of the cluster is resident, its barriers initialised and h buffers zeroed
 
-  if (warp == 0) {
-    if (lane == 0) {  // ===== MMA issuer =====
-      for (int s = 0; s < S; ++s) {
-        const uint32_t buf = s & 1;
+  long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) ? g_rnn_dbg : nullptr;
+  float* pre = pre_all + warp * 32 * PRE_LD;
+  float cst[PPT], hprev[PPT], xcur[PPT][G];
+  const float* xp[PPT];  // input pre-activations of the NEXT step to fetch
+  int64_t op[PPT];       // output element of the CURRENT step
+  bool ok[PPT];
+  const int64_t xstep = (dir ? -1 : 1) * (int64_t)(2 * G * H), ostep = (dir ? -1 : 1) * (int64_t)(2 * H);
+  const float bhn = (G == 3) ? b_hn[dir * H + hu] : 0.f;
+  const int t_first = dir ? S - 1 : 0;
+  const int ng8 = (nvalid + 7) >> 3;  // 8-utterance groups that carry data
 #pragma unroll
-        for (int c = 0; c < NSUB; ++c) {
-          if (s > 0) mbar_wait(bar0 + 8 * (c * 2 + buf), ((uint32_t)(s - 1) >> 1) & 1);  // h_{t-1} complete
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t hb = hb0 + (c * 2 + buf) * C::HB_BYTES;
-          const uint32_t d = tmem_base + C::DCOL0 + c * NCOL;
-#pragma unroll 8
-          for (int ks = 0; ks < C::KSTEPS; ++ks)
-            umma_ts_bf16(d, tmem_base + ks * 8, bdesc_kmajor(hb + ks * 256, C::SBO), C::IDESC, ks > 0 ? 1u : 0u);
-          umma_commit(dfull0 + 8 * c);
-        }
-      }
-    }
-  } else {  // ===== gate warps =====
-    float* pre = pre_all + (warp - 1) * 32 * PRE_LD;
-    float cst[NSUB][2], hprev[NSUB][2], xcur[NSUB][2][G];
-    const float* xb[NSUB][2];
-    int64_t ob[NSUB][2];
-    bool ok[NSUB][2];
-    int ng8[NSUB];
-    const float bhn = (G == 3) ? b_hn[dir * H + hu] : 0.f;
-    const int t_first = dir ? S - 1 : 0;
+  for (int e = 0; e < PPT; ++e) {
+    const int n = cgp * CW + sub * PPT + e;  // utterance of the chunk
+    ok[e] = n < nvalid;
+    cst[e] = 0.f;
+    hprev[e] = 0.f;
+    const int64_t b = b0 + (ok[e] ? n : 0);
+    xp[e] = xg + ((b * S + t_first) * 2 + dir) * (int64_t)(G * H) + hu;
+    op[e] = (b * S + t_first) * (2 * H) + dir * H + hu;
 #pragma unroll
-    for (int c = 0; c < NSUB; ++c) {
-      ng8[c] = max(0, min(2, (nvalid - c * NCOL + 7) >> 3));
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int n = c * NCOL + half * 8 + sub * 2 + e;  // utterance of the chunk
-        ok[c][e] = n < nvalid;
-        cst[c][e] = 0.f;
-        hprev[c][e] = 0.f;
-        const int64_t b = b0 + (ok[c][e] ? n : 0);
-        xb[c][e] = xg + ((b * S) * 2 + dir) * (int64_t)(G * H) + hu;
-        ob[c][e] = (b * S) * (2 * H) + dir * H + hu;
-#pragma unroll
-        for (int g = 0; g < G; ++g) xcur[c][e][g] = ok[c][e] ? __ldg(xb[c][e] + (int64_t)t_first * 2 * G * H + g * H) : 0.f;
-      }
-    }
-    // this thread's bulk copies: peer (rank + 1 + j) % CL, 8-utterance group grp
-    const int gt = tid - 32;
+    for (int g = 0; g < G; ++g) xcur[e][g] = ok[e] ? __ldg(xp[e] + g * H) : 0.f;
+    xp[e] += xstep;
+  }
+  // own slice cell of utterance n: rank*SL + (n/8)*512 + q*128 + (n%8)*16 + (unit%8)*2
+  const int n0 = cgp * CW + sub * PPT;
+  const uint32_t cell0 = rank * C::SL + (uint32_t)(n0 >> 3) * 512u + (uint32_t)q * 128u + (uint32_t)(n0 & 7) * 16u + (lane >> 2) * 2u;
 
-    for (int s = 0; s < S; ++s) {
-      const int t = dir ? S - 1 - s : s;
-      const uint32_t nbuf = (s & 1) ^ 1;
-#pragma unroll
-      for (int c = 0; c < NSUB; ++c) {
-        // next step's input pre-activations: in flight while this step computes
-        float xnext[2][G];
-        if (s + 1 < S) {
-          const int tn = dir ? t - 1 : t + 1;
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-#pragma unroll
-            for (int g = 0; g < G; ++g) xnext[e][g] = ok[c][e] ? __ldg(xb[c][e] + (int64_t)tn * 2 * G * H + g * H) : 0.f;
-        }
-        mbar_wait(dfull0 + 8 * c, s & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t r[8];
-        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + C::DCOL0 + c * NCOL + half * 8, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // regroup: row (unit, gate) x 8 utterances  ->  thread (unit, 2 utterances) x 4 gates
-        *reinterpret_cast<float4*>(pre + lane * PRE_LD) =
-            make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
-        *reinterpret_cast<float4*>(pre + lane * PRE_LD + 4) =
-            make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
-        __syncwarp();
-        float2 p[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) p[g] = *reinterpret_cast<const float2*>(pre + ((lane & ~3) + g) * PRE_LD + sub * 2);
-        __syncwarp();
-        float hn[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float pe0 = e ? p[0].y : p[0].x, pe1 = e ? p[1].y : p[1].x, pe2 = e ? p[2].y : p[2].x;
-          if (G == 4) {  // LSTM, gate order i, f, g, o; biases folded into xg
-            const float pe3 = e ? p[G - 1].y : p[G - 1].x;
-            const float gi = sigmoid_fast(xcur[c][e][0] + pe0);
-            const float gf = sigmoid_fast(xcur[c][e][1] + pe1);
-            const float gg = tanh_fast(xcur[c][e][2] + pe2);
-            const float go = sigmoid_fast(xcur[c][e][G - 1] + pe3);
-            cst[c][e] = gf * cst[c][e] + gi * gg;
-            hn[e] = go * tanh_fast(cst[c][e]);
-          } else {  // GRU, gate order r, z, n; b_hn stays inside r * (.)
-            const float gr = sigmoid_fast(xcur[c][e][0] + pe0);
-            const float gz = sigmoid_fast(xcur[c][e][1] + pe1);
-            const float gn = tanh_fast(xcur[c][e][2] + gr * (pe2 + bhn));
-            hn[e] = (1.f - gz) * gn + gz * hprev[c][e];
-          }
-          hprev[c][e] = hn[e];
-          if (ok[c][e]) {
-            const int64_t o = ob[c][e] + (int64_t)t * 2 * H;
-            if (out_bf16)
-              reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(hn[e]);
-            else
-              reinterpret_cast<float*>(out)[o] = hn[e];
-          }
-#pragma unroll
-          for (int g = 0; g < G; ++g) xcur[c][e][g] = xnext[e][g];
-        }
-        if (s + 1 < S) {
-          // own slice of h_t (bf16) -> next step's B buffer of THIS CTA: cell (n = half*8 + 2*sub + e, kc = 4*rank + q)
-          const uint32_t cell = (uint32_t)half * (C::SBO) + (4u * rank + q) * 128u + (uint32_t)(sub * 2) * 16u + (lane >> 2) * 2u;
-          unsigned char* hb_next = smem_raw + (c * 2 + nbuf) * C::HB_BYTES;
-          if (ok[c][0]) *reinterpret_cast<__nv_bfloat16*>(hb_next + cell) = __float2bfloat16_rn(hn[0]);
-          if (ok[c][1]) *reinterpret_cast<__nv_bfloat16*>(hb_next + cell + 16) = __float2bfloat16_rn(hn[1]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to UMMA / bulk copy
-          asm volatile("bar.sync 1, %0;" ::"r"(GATE_WARPS * 32) : "memory");
-          const uint32_t hbn = hb0 + (c * 2 + nbuf) * C::HB_BYTES, barn = bar0 + 8 * (c * 2 + nbuf);
-          if (gt < (CL - 1) * ng8[c]) {
-            const uint32_t peer = (rank + 1 + gt / ng8[c]) % CL, grp = gt % ng8[c];
-            const uint32_t src = hbn + grp * C::SBO + 4u * rank * 128u;
-            bulk_push(mapa(src, peer), src, C::SLICE, mapa(barn, peer));
-          }
-          if (gt == GATE_WARPS * 32 - 1)  // own slice is in place; the peers' bytes complete the phase
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barn),
-                         "r"((uint32_t)((CL - 1) * ng8[c]) * C::SLICE)
+  if (lane == 0) {  // arm the first use of both buffers' slice barriers (the slices this warp will wait for)
+    for (int i = warp; i < CL; i += WARPS)
+      if (i > 0)
+        for (int bf = 0; bf < 2; ++bf)
+          if (S > 1 + (bf ^ 1))  // buffer 1 is first used for h_0 (step 1), buffer 0 for h_1 (step 2)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * (bf * CL + (rank + i) % CL)),
+                         "r"((uint32_t)ng8 * 512u)
                          : "memory");
-        }
+  }
+  cluster.sync();  // all barriers armed before any peer can push
+
+  for (int s = 0; s < S; ++s) {
+    const uint32_t nbuf = (s & 1) ^ 1;
+    // next step's input pre-activations: in flight while this step computes
+    float xnext[PPT][G];
+    if (s + 1 < S) {
+#pragma unroll
+      for (int e = 0; e < PPT; ++e) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) xnext[e][g] = ok[e] ? __ldg(xp[e] + g * H) : 0.f;
+        xp[e] += xstep;
       }
+    }
+    if (s > 0) mbar_wait(dfull, (s - 1) & 1);  // all MMAs of this step have retired
+    RNN_STAMP(2);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float acc[CW];
+    {
+      uint32_t r[KSPLIT][CW];
+#pragma unroll
+      for (int a = 0; a < KSPLIT; ++a)
+#pragma unroll
+        for (int i = 0; i < CW; i += 4)
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(r[a][i]), "=r"(r[a][i + 1]), "=r"(r[a][i + 2]), "=r"(r[a][i + 3])
+                       : "r"(tacc + a * NCOLS + i));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int a = 0; a < KSPLIT; ++a)
+#pragma unroll
+        for (int i = 0; i < CW; i += 4) tmem_st4(tacc + a * NCOLS + i, z);  // cleared for the next step's MMAs
+#pragma unroll
+      for (int i = 0; i < CW; ++i) {
+        float v = __uint_as_float(r[0][i]);
+#pragma unroll
+        for (int a = 1; a < KSPLIT; ++a) v += __uint_as_float(r[a][i]);
+        acc[i] = v;
+      }
+    }
+    RNN_STAMP(3);
+    // regroup: row (unit, gate) x CW utterances  ->  thread (unit, PPT utterances) x 4 gates
+#pragma unroll
+    for (int i = 0; i < CW; i += 4)
+      *reinterpret_cast<float4*>(pre + lane * PRE_LD + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+    __syncwarp();
+    float p[G][PPT];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float* src = pre + ((lane & ~3) + g) * PRE_LD + sub * PPT;
+      if (PPT == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(src);
+        p[g][0] = v.x, p[g][PPT - 1] = v.y;
+      } else {
+        p[g][0] = *src;
+      }
+    }
+    __syncwarp();
+    float hn[PPT];
+#pragma unroll
+    for (int e = 0; e < PPT; ++e) {
+      if (G == 4) {  // LSTM, gate order i, f, g, o; biases folded into xg
+        const float gi = sigmoid_mufu(xcur[e][0] + p[0][e]);
+        const float gf = sigmoid_mufu(xcur[e][1] + p[1][e]);
+        const float gg = tanh_mufu(xcur[e][2] + p[2][e]);
+        const float go = sigmoid_mufu(xcur[e][G - 1] + p[G - 1][e]);
+        cst[e] = gf * cst[e] + gi * gg;
+        hn[e] = go * tanh_mufu(cst[e]);
+      } else {  // GRU, gate order r, z, n; b_hn stays inside r * (.)
+        const float gr = sigmoid_mufu(xcur[e][0] + p[0][e]);
+        const float gz = sigmoid_mufu(xcur[e][1] + p[1][e]);
+        const float gn = tanh_mufu(xcur[e][2] + gr * (p[2][e] + bhn));
+        hn[e] = (1.f - gz) * gn + gz * hprev[e];
+      }
+      hprev[e] = hn[e];
+      if (ok[e]) {
+        if (out_bf16)
+          reinterpret_cast<__nv_bfloat16*>(out)[op[e]] = __float2bfloat16_rn(hn[e]);
+        else
+          reinterpret_cast<float*>(out)[op[e]] = hn[e];
+      }
+      op[e] += ostep;
+#pragma unroll
+      for (int g = 0; g < G; ++g) xcur[e][g] = xnext[e][g];
+    }
+    if (s + 1 < S) {
+      // own slice of h_t (bf16) -> next step's B buffer of THIS CTA
+      unsigned char* hb_next = smem_raw + nbuf * C::HB_BYTES;
+#pragma unroll
+      for (int e = 0; e < PPT; ++e)
+        if (ok[e]) *reinterpret_cast<__nv_bfloat16*>(hb_next + cell0 + e * 16) = __float2bfloat16_rn(hn[e]);
+      RNN_STAMP(4);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");       // accumulator clear has landed
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic writes -> visible to UMMA / bulk copy
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
+      RNN_STAMP(5);
+      if (lane == 0) {
+        // barrier [nbuf][rank] of every PEER tracks this CTA's slice: the consumer arms it (arrive + expect_tx, below)
+        // and this bulk copy completes the bytes
+        const uint32_t hbn = hb0 + nbuf * C::HB_BYTES, barn = bar0 + 8 * (nbuf * CL + rank);
+        const uint32_t src = hbn + rank * C::SL, bytes = (uint32_t)ng8 * 512u;
+        for (int j = warp; j < CL - 1; j += WARPS) {  // one bulk copy per peer, spread over the warps
+          const uint32_t peer = (rank + 1 + j) % CL;
+          bulk_push(mapa(src, peer), src, bytes, mapa(barn, peer));
+        }
+        RNN_STAMP(6);
+        // issue the next step's MMAs of the slices this warp owns as soon as each has landed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int i = warp; i < CL; i += WARPS) {
+          const uint32_t r = (rank + i) % CL;
+          if (i > 0) {  // the own slice (i == 0) is complete since the barrier above
+            const uint32_t hbar = bar0 + 8 * (nbuf * CL + r);
+            mbar_wait(hbar, ((uint32_t)s >> 1) & 1);
+            // re-arm for the next use of this buffer (h_{t+2}); that slice cannot be sent before this CTA has
+            // sent h_{t+1}, so the expect_tx is always in place first
+            if (s + 3 < S)
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hbar), "r"(bytes) : "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const uint32_t d_acc = tmem_base + (r % KSPLIT) * NCOLS;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t ks = 2 * r + j;
+            umma_ss_bf16(d_acc, adesc_sw128(wa0 + (ks >> 2) * 16384 + (ks & 3) * 32), bdesc_kmajor(hbn + r * C::SL + j * 256, 512),
+                         C::IDESC, 1u);
+          }
+        }
+        umma_commit(dfull);
+        RNN_STAMP(7);
+      }
+      __syncwarp();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -306,16 +404,16 @@ __global__ void __launch_bounds__(rt::THREADS, 1)
   cluster.sync();  // no CTA exits while a peer may still address its shared memory
 }
 
-template <int G, int H, int CL, int NSUB>
+template <int G, int H, int CL, int NCOLS, int CW, int UC>
 static int launch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
                          int bc, cudaStream_t s, int* max_clusters) {
-  using C = RtCfg<G, H, CL, NSUB>;
-  auto kern = rnn_tc_kernel<G, H, CL, NSUB>;
+  using C = RtCfg<G, H, CL, NCOLS, CW, UC>;
+  auto kern = rnn_tc_kernel<G, H, CL, NCOLS, CW, UC>;
   static bool configured = false;
   static int max_active = 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL, max_clusters ? 1 : cdiv(B, bc), 2);
-  cfg.blockDim = dim3(rt::THREADS);
+  cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -342,29 +440,36 @@ static int launch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, 
 }
 
 // Utterances per cluster: the smallest chunk whose cluster count still fits on the GPU in ONE wave (the
-// clusters are independent, so a second wave would double the latency of the whole recurrence).  The bytes
-// every CTA receives per step grow with the chunk, so smaller is faster as long as it is one wave.
+// clusters are independent, so a second wave would double the latency of the whole recurrence).  Fewer
+// utterances per cluster = fewer gate-maths pairs per thread and fewer bytes per hand-off.
 template <int G, int H, int CL>
 static int dispatch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
                            cudaStream_t s) {
-  int m1 = 0, m2 = 0;
-  FTB_TRY((launch_rnn_tc<G, H, CL, 1>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 16, s, &m1)));
-  FTB_TRY((launch_rnn_tc<G, H, CL, 2>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 32, s, &m2)));
-  if (2 * cdiv(B, 8) <= m1) return launch_rnn_tc<G, H, CL, 1>(xg, w_hh, b_hn, out, B, S, out_bf16, 8, s, nullptr);
-  if (2 * cdiv(B, 16) <= m1) return launch_rnn_tc<G, H, CL, 1>(xg, w_hh, b_hn, out, B, S, out_bf16, 16, s, nullptr);
-  if (2 * cdiv(B, 24) <= m2) return launch_rnn_tc<G, H, CL, 2>(xg, w_hh, b_hn, out, B, S, out_bf16, 24, s, nullptr);
-  return launch_rnn_tc<G, H, CL, 2>(xg, w_hh, b_hn, out, B, S, out_bf16, 32, s, nullptr);
+  int m8 = 0, m16 = 0, m32 = 0;
+  FTB_TRY((launch_rnn_tc<G, H, CL, 16, 4, 8>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 8, s, &m8)));
+  FTB_TRY((launch_rnn_tc<G, H, CL, 16, 8, 16>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 16, s, &m16)));
+  FTB_TRY((launch_rnn_tc<G, H, CL, 32, 8, 32>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 32, s, &m32)));
+  // 8 utterances: only the first column group of a 16-wide MMA carries data, 1 pair per gate thread
+  if (2 * cdiv(B, 8) <= m8) return launch_rnn_tc<G, H, CL, 16, 4, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, 8, s, nullptr);
+  if (2 * cdiv(B, 16) <= m16) return launch_rnn_tc<G, H, CL, 16, 8, 16>(xg, w_hh, b_hn, out, B, S, out_bf16, 16, s, nullptr);
+  if (2 * cdiv(B, 24) <= m32) return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 24, s, nullptr);
+  return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 32, s, nullptr);
 }
+
+int rnn_gru256_mma(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
+                   cudaStream_t s);  // rnn_mma.cu
 
 int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
                 int out_bf16, cudaStream_t s) {
   if (is_lstm && H == 512) return dispatch_rnn_tc<4, 512, 16>(xg, w_hh, nullptr, out, B, S, out_bf16, s);
-  if (!is_lstm && H == 256) {
-    FTB_REQUIRE(b_hn, FTB_ERR_INVALID, "rnn_cluster: GRU needs b_hn");
-    return dispatch_rnn_tc<3, 256, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
-  }
+  if (!is_lstm && H == 256) return rnn_gru256_mma(xg, w_hh, b_hn, out, B, S, out_bf16, s);
   set_error("rnn_bidir: no kernel for %s with H=%d (built: GRU 64/128/256, LSTM 512)", is_lstm ? "LSTM" : "GRU", H);
   return FTB_ERR_UNSUPPORTED;
 }
 
 }  // namespace ftb
+
+// developer hook (not part of include/ftb200.h): device buffer of 64*8 int64 clock stamps, or NULL to switch off
+extern "C" int ftb_debug_rnn_timing(long long* device_buf) {
+  return cudaMemcpyToSymbol(ftb::g_rnn_dbg, &device_buf, sizeof(device_buf)) == cudaSuccess ? 0 : -2;
+}
