@@ -14,6 +14,7 @@ _LIB = None
 _LIB_PATH = Path(__file__).resolve().parent / 'csrc' / 'libftb200.so'
 
 FTB_F32, FTB_I64, FTB_BF16, FTB_I32 = 0, 1, 2, 3
+FTB_OPT_OVERLAP_PRENET = 1
 
 
 class FtbError(RuntimeError):
@@ -90,6 +91,7 @@ SIGNATURES = {
     'ftb_ft_create': (_I, [C.POINTER(FtConfig), C.POINTER(Tensor), _I, _I, C.POINTER(_P)]),
     'ftb_ft_destroy': (None, [_P]),
     'ftb_ft_workspace_bytes': (_L, [_P, _I, _I, _I]),
+    'ftb_ft_set_option': (_I, [_P, _I, _I]),
     'ftb_ft_predict': (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _L, _P]),
     'ftb_ft_synthesize': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _L, _P]),
     'ftb_ft_series_predictor': (_I, [_P, _I, _P, _I, _I, _F, _P, _P, _L, _P]),

@@ -39,6 +39,29 @@ struct ftb_ft_handle : ftb::ModelBase {
   ftb::Rnn lstm;
   ftb::Layer lin, post_proj;
   bool bf16_mode() const { return cfg.gemm_mode == 0; }
+
+  // Stage A runs its three independent predictors on three side streams, forked from and joined back into the
+  // caller's stream with events.  With FTB_OPT_OVERLAP_PRENET the prenet CBHG of stage B (it depends on the
+  // tokens only) is started in stage A as well, on a fourth stream into handle-owned memory, and stage B picks it
+  // up: the T-step recurrences of stage A and the prenet leave most SMs idle when run one after the other.
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  int opt_overlap_prenet = 0;
+  char* pre_buf = nullptr;
+  int64_t pre_cap = 0;
+  const int64_t* pre_tok = nullptr;
+  int pre_B = 0, pre_T = 0;
+  bool pre_valid = false;
+  void* pre_enc = nullptr;
+
+  ~ftb_ft_handle() {
+    for (int i = 0; i < 4; ++i) {
+      if (side[i]) cudaStreamSynchronize(side[i]), cudaStreamDestroy(side[i]);
+      if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (pre_buf) cudaFree(pre_buf);
+  }
 };
 
 namespace ftb {
@@ -203,6 +226,9 @@ static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int 
 }
 
 template <typename T>
+static int run_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn, T* x0, T* enc, Arena& A, cudaStream_t s);
+
+template <typename T>
 static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* cum, const float* pitch,
                           const float* energy, int B, int Tn, int L, float* mel, float* mel_post, Arena& A,
                           cudaStream_t s) {
@@ -219,8 +245,13 @@ static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* c
   T* post = A.take<T>(ML * 2 * c.postnet_dims);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for synthesize");
 
-  FTB_TRY(embed<T>(tok, h->embedding, x0, MT, E, E, c.num_chars, s));
-  FTB_TRY(run_cbhg<T>(h, h->prenet, x0, E, B, Tn, enc, A, s));
+  if (h->pre_valid && h->pre_tok == tok && h->pre_B == B && h->pre_T == Tn) {
+    FTB_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_join[3], 0));  // prenet already computed (or in flight) on side stream 3
+    enc = (T*)h->pre_enc;
+  } else {
+    FTB_TRY(run_prenet<T>(h, tok, B, Tn, x0, enc, A, s));
+  }
+  h->pre_valid = false;
   FTB_TRY(cond_add<T>(enc, pitch, energy, h->pitch_w, h->pitch_b, h->energy_w, h->energy_b, c.pitch_strength,
                       c.energy_strength, B, Tn, D, s));
   FTB_TRY(ftb_length_expand(enc, cum, up, B, Tn, L, D, (int)sizeof(T), s));
@@ -235,6 +266,50 @@ static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* c
   op.t = mel_post;
   FTB_TRY(h->gemm<T>(h->post_proj, post, 2 * c.postnet_dims, B, L, op, nullptr, 0, 1.f, s));
   h->launches += 4;
+  return FTB_OK;
+}
+
+// embedding -> CBHG prenet into `enc` (B,T,2*prenet_dims); x0 and the CBHG scratch come from A
+template <typename T>
+static int run_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn, T* x0, T* enc, Arena& A, cudaStream_t s) {
+  const int E = h->cfg.embed_dims;
+  FTB_TRY(embed<T>(tok, h->embedding, x0, (int64_t)B * Tn, E, E, h->cfg.num_chars, s));
+  ++h->launches;
+  return run_cbhg<T>(h, h->prenet, x0, E, B, Tn, enc, A, s);
+}
+
+template <typename T>
+static int64_t prenet_bytes(const ftb_ft_handle* h, int B, int Tn) {
+  Arena A(nullptr, 0);
+  const int64_t MT = (int64_t)B * Tn;
+  A.take<T>(MT * h->cfg.embed_dims);
+  A.take<T>(MT * 2 * h->cfg.prenet_dims);
+  plan_cbhg<T>(A, h->prenet, B, Tn);
+  return A.mark() + 256;
+}
+
+// starts the prenet on side stream 3 into handle-owned memory (FTB_OPT_OVERLAP_PRENET)
+template <typename T>
+static int prefetch_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn) {
+  const int64_t need = prenet_bytes<T>(h, B, Tn);
+  if (need > h->pre_cap) {
+    FTB_CHECK_CUDA(cudaStreamSynchronize(h->side[3]));
+    if (h->pre_buf) FTB_CHECK_CUDA(cudaFree(h->pre_buf));
+    h->pre_buf = nullptr;
+    h->pre_cap = 0;
+    FTB_CHECK_CUDA(cudaMalloc((void**)&h->pre_buf, (size_t)need));
+    h->pre_cap = need;
+  }
+  Arena A(h->pre_buf, h->pre_cap);
+  const int64_t MT = (int64_t)B * Tn;
+  T* x0 = A.take<T>(MT * h->cfg.embed_dims);
+  T* enc = A.take<T>(MT * 2 * h->cfg.prenet_dims);
+  FTB_TRY(run_prenet<T>(h, tok, B, Tn, x0, enc, A, h->side[3]));
+  h->pre_enc = enc;
+  h->pre_tok = tok;
+  h->pre_B = B;
+  h->pre_T = Tn;
+  h->pre_valid = true;
   return FTB_OK;
 }
 
@@ -260,18 +335,20 @@ static int64_t synth_bytes(const ftb_ft_handle* h, int B, int Tn, int L) {
 }
 
 template <typename T>
+static int64_t series_bytes(const ftb_ft_handle* h, int i, int B, int Tn) {
+  Arena A(nullptr, 0);
+  if (h->series[i].f32_only || !h->bf16_mode())
+    plan_series<float>(A, h->series[i], B, Tn);
+  else
+    plan_series<T>(A, h->series[i], B, Tn);
+  return align_up(A.mark() + 256, 256);
+}
+// the three predictors run concurrently: their scratch regions are disjoint
+template <typename T>
 static int64_t predict_bytes(const ftb_ft_handle* h, int B, int Tn) {
-  int64_t best = 0;
-  for (int i = 0; i < 3; ++i) {
-    Arena A(nullptr, 0);
-    A.take<char>(256);
-    if (h->series[i].f32_only || !h->bf16_mode())
-      plan_series<float>(A, h->series[i], B, Tn);
-    else
-      plan_series<T>(A, h->series[i], B, Tn);
-    best = std::max(best, A.mark());
-  }
-  return best + 256;
+  int64_t sum = 512;
+  for (int i = 0; i < 3; ++i) sum += series_bytes<T>(h, i, B, Tn);
+  return sum;
 }
 
 }  // namespace ftb
@@ -311,6 +388,11 @@ extern "C" int ftb_ft_create(const ftb_ft_config* cfg, const ftb_tensor* tensors
                        c.postnet_num_highways));
     FTB_TRY(h->make_conv(h->post_proj, "post_proj.weight", c.n_mels, 2 * c.postnet_dims, 1, 0, false, "", "", w32, w16));
     FTB_CHECK_CUDA(cudaStreamSynchronize(h->prep));
+    for (int i = 0; i < 4; ++i) {
+      FTB_CHECK_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+      FTB_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    }
+    FTB_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     return FTB_OK;
   };
   const int st = build();
@@ -346,19 +428,49 @@ extern "C" int ftb_ft_series_predictor(ftb_ft_handle* h, int which, const int64_
   return run_series<bf16>(h, P, tokens, B, T, alpha, out, A, (cudaStream_t)stream);
 }
 
+extern "C" int ftb_ft_set_option(ftb_ft_handle* h, int option, int value) {
+  FTB_REQUIRE(h, FTB_ERR_INVALID, "ftb_ft_set_option: null handle");
+  if (option == FTB_OPT_OVERLAP_PRENET) {
+    h->opt_overlap_prenet = value != 0;
+    if (!value) h->pre_valid = false;
+    return FTB_OK;
+  }
+  set_error("ftb_ft_set_option: unknown option %d", option);
+  return FTB_ERR_INVALID;
+}
+
 extern "C" int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, int T, float alpha, float* dur,
                               float* pitch, float* energy, void* workspace, int64_t workspace_bytes, void* stream) {
   FTB_REQUIRE(h && tokens && dur && pitch && energy && workspace, FTB_ERR_INVALID, "ftb_ft_predict: bad arguments");
+  FTB_REQUIRE(B > 0 && T > 0 && alpha != 0.f, FTB_ERR_INVALID, "ftb_ft_predict: bad sizes / alpha");
   h->launches = 0;
   cudaStream_t s = (cudaStream_t)stream;
-  // the fallback's 8-byte accumulator lives at the head of the workspace
-  FTB_REQUIRE(workspace_bytes >= 256, FTB_ERR_WORKSPACE, "workspace too small");
-  char* ws = (char*)workspace;
-  FTB_TRY(ftb_ft_series_predictor(h, 0, tokens, B, T, alpha, dur, ws + 256, workspace_bytes - 256, stream));
-  FTB_TRY(ftb_duration_fallback(dur, (int64_t)B * T, ws, s));
-  h->launches += 2;
-  FTB_TRY(ftb_ft_series_predictor(h, 1, tokens, B, T, 1.f, pitch, ws + 256, workspace_bytes - 256, stream));
-  FTB_TRY(ftb_ft_series_predictor(h, 2, tokens, B, T, 1.f, energy, ws + 256, workspace_bytes - 256, stream));
+  const bool b16 = h->bf16_mode();
+  int64_t need = 512;
+  for (int i = 0; i < 3; ++i) need += b16 ? series_bytes<bf16>(h, i, B, T) : series_bytes<float>(h, i, B, T);
+  FTB_REQUIRE(workspace_bytes >= need, FTB_ERR_WORKSPACE, "workspace too small for ftb_ft_predict (%lld < %lld)",
+              (long long)workspace_bytes, (long long)need);
+  char* ws = (char*)workspace;  // the fallback's 8-byte accumulator lives at the head of the workspace
+  float* outs[3] = {dur, pitch, energy};
+  FTB_CHECK_CUDA(cudaEventRecord(h->ev_fork, s));
+  int64_t off = 512;
+  for (int i = 0; i < 3; ++i) {  // fork: one predictor per side stream
+    const int64_t bytes = b16 ? series_bytes<bf16>(h, i, B, T) : series_bytes<float>(h, i, B, T);
+    FTB_CHECK_CUDA(cudaStreamWaitEvent(h->side[i], h->ev_fork, 0));
+    FTB_TRY(ftb_ft_series_predictor(h, i, tokens, B, T, i == 0 ? alpha : 1.f, outs[i], ws + off, bytes, h->side[i]));
+    if (i == 0) {
+      FTB_TRY(ftb_duration_fallback(dur, (int64_t)B * T, ws, h->side[0]));
+      h->launches += 2;
+    }
+    FTB_CHECK_CUDA(cudaEventRecord(h->ev_join[i], h->side[i]));
+    off += bytes;
+  }
+  if (h->opt_overlap_prenet) {
+    FTB_CHECK_CUDA(cudaStreamWaitEvent(h->side[3], h->ev_fork, 0));
+    FTB_TRY(b16 ? prefetch_prenet<bf16>(h, tokens, B, T) : prefetch_prenet<float>(h, tokens, B, T));
+    FTB_CHECK_CUDA(cudaEventRecord(h->ev_join[3], h->side[3]));
+  }
+  for (int i = 0; i < 3; ++i) FTB_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_join[i], 0));  // join
   return FTB_OK;
 }
 

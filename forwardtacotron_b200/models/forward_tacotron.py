@@ -157,10 +157,19 @@ class ForwardTacotron(NativeModel):
                  energy_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x) -> Dict[str, torch.Tensor]:
         self.eval()
         with torch.no_grad():
-            dur_hat, pitch_hat, energy_hat = self.predict(x, alpha)
-            pitch_hat = pitch_function(pitch_hat)
-            energy_hat = energy_function(energy_hat)
-            return self.synthesize(x, dur_hat, pitch_hat, energy_hat)
+            x = self._check_tokens(x)
+            h = self._get_handle(x.device)
+            lib = _lib.lib()
+            # stage B's prenet depends on the tokens only: let stage A start it on a side stream (x is not
+            # touched between the two calls)
+            _lib.check(lib.ftb_ft_set_option(h, _lib.FTB_OPT_OVERLAP_PRENET, 1))
+            try:
+                dur_hat, pitch_hat, energy_hat = self.predict(x, alpha)
+                pitch_hat = pitch_function(pitch_hat)
+                energy_hat = energy_function(energy_hat)
+                return self.synthesize(x, dur_hat, pitch_hat, energy_hat)
+            finally:
+                _lib.check(lib.ftb_ft_set_option(h, _lib.FTB_OPT_OVERLAP_PRENET, 0))
 
     def last_launch_count(self) -> int:
         return int(_lib.lib().ftb_ft_last_launch_count(self._handle)) if self._handle is not None else 0

@@ -194,9 +194,18 @@ int64_t ftb_ft_workspace_bytes(const ftb_ft_handle* h, int B, int T, int L);
 
 /* Stage A (generate lines 251-262): three SeriesPredictors + duration fallback.
  * tokens (B,T) int64; dur (B,T), pitch (B,T), energy (B,T) f32 out
- * ((B,1,T) of the reference is the same memory). */
+ * ((B,1,T) of the reference is the same memory).  The three predictors are independent: they run on three
+ * internal streams forked from / joined into `stream` with events, so the call is ordered like any other
+ * launch on `stream`. */
 int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, int T, float alpha, float* dur, float* pitch,
                    float* energy, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Handle options.  FTB_OPT_OVERLAP_PRENET (default 0): ftb_ft_predict also starts the prenet CBHG of stage B -- it
+ * depends on the tokens only -- on an internal stream into handle-owned memory, and the NEXT ftb_ft_synthesize call
+ * with the same tokens pointer, B and T picks it up instead of recomputing it.  The caller must not modify the
+ * token buffer between the two calls (generate() does not); one-shot, dropped by any other call sequence. */
+#define FTB_OPT_OVERLAP_PRENET 1
+int ftb_ft_set_option(ftb_ft_handle* h, int option, int value);
 
 /* Between the stages the Python callbacks pitch_function / energy_function run
  * (generate lines 259, 263), then ftb_length_plan + the D2H of `total`. */
