@@ -130,7 +130,7 @@ struct alignas(64) TcArgs {
   CUtensorMap map_a;  // (Cin, S, B) bf16, box 64 x box_rows x 1
   TcProb prob[tc::MAXP];
   int nprob, B, S, Cin, cblocks;
-  int m_tiles, m_stride, box_rows, bn, total_tiles, pool;
+  int m_tiles, m_stride, box_rows, bn, total_tiles, pool, highway;
   int ldo, ldr, n_total;  // n_total: N of the (B,N,S) transposed output
   float out_scale;
   float* out_f32;
@@ -300,7 +300,46 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
       mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       bool released = false;
-      for (int ch = half; ch < nchunks; ch += 2) {
+      if (a.highway) {
+        // Highway layer (models/common_layers.py:30-35): columns come in groups of 64 = [32 x (W1 x + b1) | 32 x (W2 x + b2)]
+        // of the SAME 32 channels (weights interleaved at pack time); y = g relu(x1) + (1 - g) x, g = sigmoid(x2),
+        // is formed in the accumulator layout (thread = row), then transposed for the coalesced bf16 store.
+        const int npairs = nchunks >> 1;
+        for (int pr = half; pr < npairs; pr += 2) {
+          uint32_t r1[32], r2[32];
+          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX + pr * 64;
+          tmem_ld32(tcol, r1);
+          tmem_ld32(tcol + 32, r2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (pr + 2 >= npairs) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            released = true;
+          }
+          const int nb1 = c.n0 + pr * 64, oc0 = (c.n0 >> 1) + pr * 32;  // GEMM column of x1[0], output channel 0 of the pair
+          uint4 xin[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          if (lane < nrows) {
+            const uint4* xr = reinterpret_cast<const uint4*>(a.res_bf16 + (mrow0 + lane) * ldr + oc0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xin[i] = __ldg(xr + i);
+          }
+          const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xin);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x1 = __uint_as_float(r1[i]) + __ldg(P.bias + nb1 + i);
+            const float x2 = __uint_as_float(r2[i]) + __ldg(P.bias + nb1 + 32 + i);
+            const float g = __fdividef(1.f, 1.f + __expf(-x2));
+            stg[lane * STG_LD + i] = g * fmaxf(x1, 0.f) + (1.f - g) * __bfloat162float(xb[i]);
+          }
+          __syncwarp();
+          __nv_bfloat16* o16 = a.out_bf16 + mrow0 * ldo + oc0 + lane;
+          const float* sp = stg + lane;
+#pragma unroll 8
+          for (int rr = 0; rr < nrows; ++rr) o16[rr * ldo] = __float2bfloat16_rn(sp[rr * STG_LD]);
+          __syncwarp();
+        }
+      }
+      for (int ch = half; ch < (a.highway ? 0 : nchunks); ch += 2) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX + ch * 32, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -426,6 +465,10 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   FTB_REQUIRE(!o.pool || (!o.out_t && !o.res_f32 && !o.res_bf16), FTB_ERR_INVALID,
               "conv_gemm_bf16: the fused max-pool supports row-major outputs without residual only");
   FTB_REQUIRE(B <= 65535, FTB_ERR_INVALID, "conv_gemm_bf16: batch too large");
+  FTB_REQUIRE(!o.highway || (n_items == 1 && o.out_bf16 && !o.out_f32 && !o.out_t && !o.pool && o.res_bf16 && !o.res_f32 &&
+                             items[0].N % 64 == 0 && items[0].bias && !items[0].scale && !items[0].relu),
+              FTB_ERR_INVALID, "conv_gemm_bf16: highway epilogue needs one problem with interleaved N %% 64 == 0, bias, "
+              "bf16 input (residual) and bf16 output");
 
   TcArgs a;
   memset(&a, 0, sizeof(a));
@@ -435,6 +478,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.Cin = Cin;
   a.cblocks = Cin / BK;
   a.pool = o.pool ? 1 : 0;
+  a.highway = o.highway ? 1 : 0;
   a.m_stride = o.pool ? BM - 1 : BM;
   a.m_tiles = cdiv(S, a.m_stride);
   a.box_rows = BM;  // the box may exceed the tensor: rows outside [0,S) are zero-filled (conv padding, pool halo)

@@ -130,11 +130,19 @@ static int build_cbhg(ftb_ft_handle* h, CbhgW& W, const std::string& p, int K, i
       FTB_TRY(ftb_pack_conv_weight(w2, L.w32 + half, ch, ch, 1, ch, L.CinP, 0, h->prep));
     }
     if (w16) {
-      FTB_TRY(ftb_pack_conv_weight(w1, L.w16, ch, ch, 1, ch, L.CinP, 1, h->prep));
-      FTB_TRY(ftb_pack_conv_weight(w2, L.w16 + half, ch, ch, 1, ch, L.CinP, 1, h->prep));
+      // tensor-core layout: rows interleaved in groups of 32 -> [W1 rows 32g.. | W2 rows 32g..], same for the bias,
+      // so a 64-column accumulator group holds both halves of the same 32 channels (highway epilogue)
+      FTB_REQUIRE(ch % 32 == 0 && L.CinP == ch, FTB_ERR_UNSUPPORTED, "%s: highway width %d must be a multiple of 64", q.c_str(), ch);
+      for (int g = 0; g < ch / 32; ++g) {
+        FTB_TRY(ftb_pack_conv_weight(w1 + (int64_t)g * 32 * ch, L.w16 + (int64_t)(2 * g) * 32 * L.CinP, 32, ch, 1, 32, L.CinP, 1, h->prep));
+        FTB_TRY(ftb_pack_conv_weight(w2 + (int64_t)g * 32 * ch, L.w16 + (int64_t)(2 * g + 1) * 32 * L.CinP, 32, ch, 1, 32, L.CinP, 1, h->prep));
+        FTB_TRY(copy_f32(b1 + g * 32, L.bias + 2 * g * 32, 32, h->prep));
+        FTB_TRY(copy_f32(b2 + g * 32, L.bias + (2 * g + 1) * 32, 32, h->prep));
+      }
+    } else {
+      FTB_TRY(copy_f32(b1, L.bias, ch, h->prep));
+      FTB_TRY(copy_f32(b2, L.bias + ch, ch, h->prep));
     }
-    FTB_TRY(copy_f32(b1, L.bias, ch, h->prep));
-    FTB_TRY(copy_f32(b2, L.bias + ch, ch, h->prep));
   }
   FTB_TRY(h->make_rnn(W.rnn, p + ".rnn", ch, ch, false, w32, w16));
   return FTB_OK;
@@ -214,13 +222,18 @@ static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int 
   FTB_TRY(h->gemm<T>(W.pre_hw, w.p2, w.ld2, B, S, act_out(w.ha, W.ch), nullptr, 0, 1.f, s));
   T *cur = w.ha, *nxt = w.hb;
   for (int i = 0; i < W.nhw; ++i) {
-    FTB_TRY(h->gemm<T>(W.hw[i], cur, W.ch, B, S, act_out(w.t12, 2 * W.ch), nullptr, 0, 1.f, s));
-    FTB_TRY(highway_mix<T>(w.t12, cur, nxt, M, W.ch, s));
+    if (std::is_same<T, bf16>::value) {  // one launch: GEMM + gate mix in the epilogue
+      FTB_TRY(h->highway_tc(W.hw[i], (const bf16*)cur, W.ch, B, S, (bf16*)nxt, s));
+    } else {
+      FTB_TRY(h->gemm<T>(W.hw[i], cur, W.ch, B, S, act_out(w.t12, 2 * W.ch), nullptr, 0, 1.f, s));
+      FTB_TRY(highway_mix<T>(w.t12, cur, nxt, M, W.ch, s));
+      ++h->launches;
+    }
     std::swap(cur, nxt);
   }
   FTB_TRY(h->gemm<T>(W.rnn.in, cur, W.ch, B, S, act_out(w.xg, 6 * W.ch), nullptr, 0, 1.f, s));
   FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, std::is_same<T, bf16>::value, s));
-  h->launches += 1 + W.nhw;
+  h->launches += 1;
   A.reset(mark);
   return FTB_OK;
 }

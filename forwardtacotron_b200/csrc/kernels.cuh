@@ -25,6 +25,7 @@ struct TcOut {
   int ldo = 0, ldr = 0;
   float out_scale = 1.f;
   bool pool = false;
+  bool highway = false;  // N = 2C interleaved [32 x1 | 32 x2] groups -> y (C) = sigmoid(x2) relu(x1) + (1 - sigmoid(x2)) res_bf16
 };
 int tc_tile_n(int N);
 int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, const TcItem* items, int n_items,

@@ -196,6 +196,25 @@ struct ModelBase {
     return conv_gemm_bf16((const bf16*)x, L.w16, d, s);
   }
 
+  // One highway layer on the tensor cores: L packs W1/W2 interleaved in groups of 32 rows (pack_highway), the
+  // epilogue forms y = sigmoid(x2) relu(x1) + (1 - sigmoid(x2)) x and writes bf16.  (models/common_layers.py:30-35)
+  int highway_tc(const Layer& L, const bf16* x, int C, int B, int S, bf16* y, cudaStream_t s) {
+    TcItem it;
+    it.w = L.w16;
+    it.N = 2 * C;
+    it.ktaps = 1;
+    it.bias = L.bias;
+    TcOut o;
+    o.out_bf16 = y;
+    o.ldo = C;
+    o.res_bf16 = x;
+    o.ldr = C;
+    o.highway = true;
+    ++launches;
+    ProfScope prof(FAM_GEMM_TC, 2.0 * B * S * (double)(2 * C) * C, 0.0, s);
+    return conv_gemm_group(x, C, B, S, L.CinP, &it, 1, o, s);
+  }
+
   // CBHG conv bank (models/common_layers.py:92-100): K convs of x, concatenated along the channel axis,
   // then MaxPool1d(2,1,1)[:S].  bf16: ONE grouped tcgen05 launch with the pool fused into the epilogue.
   // fp32 validation mode: one SIMT launch per conv + the stand-alone pool kernel.
