@@ -15,6 +15,7 @@ _LIB_PATH = Path(__file__).resolve().parent / 'csrc' / 'libftb200.so'
 
 FTB_F32, FTB_I64, FTB_BF16, FTB_I32 = 0, 1, 2, 3
 FTB_OPT_OVERLAP_PRENET = 1
+FTB_OPT_SERIALIZE = 2
 
 
 class FtbError(RuntimeError):

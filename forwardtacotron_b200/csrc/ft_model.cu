@@ -46,7 +46,7 @@ struct ftb_ft_handle : ftb::ModelBase {
   // up: the T-step recurrences of stage A and the prenet leave most SMs idle when run one after the other.
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
-  int opt_overlap_prenet = 0;
+  int opt_overlap_prenet = 0, opt_serialize = 0;
   char* pre_buf = nullptr;
   int64_t pre_cap = 0;
   const int64_t* pre_tok = nullptr;
@@ -448,6 +448,10 @@ extern "C" int ftb_ft_set_option(ftb_ft_handle* h, int option, int value) {
     if (!value) h->pre_valid = false;
     return FTB_OK;
   }
+  if (option == FTB_OPT_SERIALIZE) {
+    h->opt_serialize = value != 0;
+    return FTB_OK;
+  }
   set_error("ftb_ft_set_option: unknown option %d", option);
   return FTB_ERR_INVALID;
 }
@@ -465,19 +469,22 @@ extern "C" int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, in
               (long long)workspace_bytes, (long long)need);
   char* ws = (char*)workspace;  // the fallback's 8-byte accumulator lives at the head of the workspace
   float* outs[3] = {dur, pitch, energy};
-  FTB_CHECK_CUDA(cudaEventRecord(h->ev_fork, s));
+  const bool fork = !h->opt_serialize;
+  if (fork) FTB_CHECK_CUDA(cudaEventRecord(h->ev_fork, s));
   int64_t off = 512;
   for (int i = 0; i < 3; ++i) {  // fork: one predictor per side stream
     const int64_t bytes = b16 ? series_bytes<bf16>(h, i, B, T) : series_bytes<float>(h, i, B, T);
-    FTB_CHECK_CUDA(cudaStreamWaitEvent(h->side[i], h->ev_fork, 0));
-    FTB_TRY(ftb_ft_series_predictor(h, i, tokens, B, T, i == 0 ? alpha : 1.f, outs[i], ws + off, bytes, h->side[i]));
+    cudaStream_t si = fork ? h->side[i] : s;
+    if (fork) FTB_CHECK_CUDA(cudaStreamWaitEvent(si, h->ev_fork, 0));
+    FTB_TRY(ftb_ft_series_predictor(h, i, tokens, B, T, i == 0 ? alpha : 1.f, outs[i], ws + off, bytes, si));
     if (i == 0) {
-      FTB_TRY(ftb_duration_fallback(dur, (int64_t)B * T, ws, h->side[0]));
+      FTB_TRY(ftb_duration_fallback(dur, (int64_t)B * T, ws, si));
       h->launches += 2;
     }
-    FTB_CHECK_CUDA(cudaEventRecord(h->ev_join[i], h->side[i]));
+    if (fork) FTB_CHECK_CUDA(cudaEventRecord(h->ev_join[i], si));
     off += bytes;
   }
+  if (!fork) return FTB_OK;
   if (h->opt_overlap_prenet) {
     FTB_CHECK_CUDA(cudaStreamWaitEvent(h->side[3], h->ev_fork, 0));
     FTB_TRY(b16 ? prefetch_prenet<bf16>(h, tokens, B, T) : prefetch_prenet<float>(h, tokens, B, T));

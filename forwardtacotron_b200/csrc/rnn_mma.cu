@@ -278,16 +278,16 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
         const int u = idx % HC, n = idx / HC;
         float hn;
         if (G == 4) {  // LSTM, gate order i, f, g, o; biases folded into xg
-          const float gi = sigmoid_fast(xc[0 * PAIRS + idx] + pre[(0 * HC + u) * PRE_LD + n]);
-          const float gf = sigmoid_fast(xc[1 * PAIRS + idx] + pre[(1 * HC + u) * PRE_LD + n]);
-          const float gg = tanh_fast(xc[2 * PAIRS + idx] + pre[(2 * HC + u) * PRE_LD + n]);
-          const float go = sigmoid_fast(xc[(3 % G) * PAIRS + idx] + pre[((3 % G) * HC + u) * PRE_LD + n]);
+          const float gi = sigmoid_mufu(xc[0 * PAIRS + idx] + pre[(0 * HC + u) * PRE_LD + n]);
+          const float gf = sigmoid_mufu(xc[1 * PAIRS + idx] + pre[(1 * HC + u) * PRE_LD + n]);
+          const float gg = tanh_mufu(xc[2 * PAIRS + idx] + pre[(2 * HC + u) * PRE_LD + n]);
+          const float go = sigmoid_mufu(xc[(3 % G) * PAIRS + idx] + pre[((3 % G) * HC + u) * PRE_LD + n]);
           cstate[p] = gf * cstate[p] + gi * gg;
-          hn = go * tanh_fast(cstate[p]);
+          hn = go * tanh_mufu(cstate[p]);
         } else {  // GRU, gate order r, z, n; b_hn stays inside r * (.)
-          const float gr = sigmoid_fast(xc[0 * PAIRS + idx] + pre[(0 * HC + u) * PRE_LD + n]);
-          const float gz = sigmoid_fast(xc[1 * PAIRS + idx] + pre[(1 * HC + u) * PRE_LD + n]);
-          const float gn = tanh_fast(xc[2 * PAIRS + idx] + gr * (pre[(2 * HC + u) * PRE_LD + n] + bhn[p]));
+          const float gr = sigmoid_mufu(xc[0 * PAIRS + idx] + pre[(0 * HC + u) * PRE_LD + n]);
+          const float gz = sigmoid_mufu(xc[1 * PAIRS + idx] + pre[(1 * HC + u) * PRE_LD + n]);
+          const float gn = tanh_mufu(xc[2 * PAIRS + idx] + gr * (pre[(2 * HC + u) * PRE_LD + n] + bhn[p]));
           hn = (1.f - gz) * gn + gz * hprev[p];
         }
         hprev[p] = hn;

@@ -205,6 +205,9 @@ int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, int T, float 
  * with the same tokens pointer, B and T picks it up instead of recomputing it.  The caller must not modify the
  * token buffer between the two calls (generate() does not); one-shot, dropped by any other call sequence. */
 #define FTB_OPT_OVERLAP_PRENET 1
+/* FTB_OPT_SERIALIZE (default 0): run every launch on the caller's stream, one after the other (no side streams, no
+ * prenet prefetch).  For profiling: per-launch CUDA-event timings are kernel durations only when nothing overlaps. */
+#define FTB_OPT_SERIALIZE 2
 int ftb_ft_set_option(ftb_ft_handle* h, int option, int value);
 
 /* Between the stages the Python callbacks pitch_function / energy_function run
