@@ -113,8 +113,13 @@ __device__ long long* g_rnn_dbg = nullptr;
 template <int G, int H, int CL, int NCOLS, int CW, int UC>
 struct RtCfg {
   static constexpr int HC = H / CL;                  // hidden units per CTA
-  static constexpr int KSPLIT = 2;                   // accumulators (slice r adds into accumulator r % KSPLIT)
-  static constexpr uint32_t TMEM_COLS = (KSPLIT * NCOLS <= 32) ? 32 : (KSPLIT * NCOLS <= 64) ? 64 : 128;
+  static constexpr int KSPLIT = 8;                   // accumulators = MMA-issuing warps: accumulator a receives the MMAs of
+                                                     // ring slices a, a + KSPLIT, ... from ONE thread in a fixed order, and
+                                                     // the gate warps add the accumulators in a fixed order, so the result
+                                                     // is bit-reproducible (16 issuers into 2 shared accumulators were 8 %
+                                                     // faster but added in arrival order: run-to-run noise that the bf16
+                                                     // rounding of h amplified to 2e-4 in the mels)
+  static constexpr uint32_t TMEM_COLS = (KSPLIT * NCOLS <= 32) ? 32 : (KSPLIT * NCOLS <= 64) ? 64 : (KSPLIT * NCOLS <= 128) ? 128 : 256;
   // W slice = A operand in shared memory, K-major SWIZZLE_128B (the layout TMA produces for the GEMM kernel):
   // k-block kb (64 units) is a 128-row x 128-byte tile at kb*16 KB; row m at m*128; the 16-byte chunk c of a row
   // (8 units) sits at chunk position c ^ (m % 8).
@@ -159,6 +164,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
   using C = RtCfg<G, H, CL, NCOLS, CW, UC>;
   using namespace rt;
   constexpr int THREADS = C::THREADS, WARPS = C::WARPS, PRE_LD = C::PRE_LD, PPT = C::PPT, KSPLIT = C::KSPLIT;
+  constexpr int NISS = KSPLIT < WARPS ? KSPLIT : WARPS;  // issuing warps 0..NISS-1
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* pre_all = reinterpret_cast<float*>(smem_raw + C::OFF_PRE);
   const uint32_t hb0 = smem_u32(smem_raw);                // hB[buf] at hb0 + buf * HB_BYTES
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
   for (int i = tid; i < (int)(C::OFF_W / 16); i += THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int i = 0; i < C::NBAR; ++i)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(i == C::NBAR - 1 ? WARPS : 1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(i == C::NBAR - 1 ? NISS : 1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
   const uint32_t cell0 = rank * C::SL + (uint32_t)(n0 >> 3) * 512u + (uint32_t)q * 128u + (uint32_t)(n0 & 7) * 16u + (lane >> 2) * 2u;
 
   if (lane == 0) {  // arm the first use of both buffers' slice barriers (the slices this warp will wait for)
-    for (int i = warp; i < CL; i += WARPS)
+    for (int i = warp; i < CL && warp < NISS; i += NISS)
       if (i > 0)
         for (int bf = 0; bf < 2; ++bf)
           if (S > 1 + (bf ^ 1))  // buffer 1 is first used for h_0 (step 1), buffer 0 for h_1 (step 2)
@@ -369,8 +375,12 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
         }
         RNN_STAMP(6);
         // issue the next step's MMAs of the slices this warp owns as soon as each has landed
+      }
+      if (lane == 0 && warp < NISS) {
+        const uint32_t hbn = hb0 + nbuf * C::HB_BYTES, bytes = (uint32_t)ng8 * 512u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int i = warp; i < CL; i += WARPS) {
+        const uint32_t d_acc = tmem_base + warp * NCOLS;
+        for (int i = warp; i < CL; i += NISS) {
           const uint32_t r = (rank + i) % CL;
           if (i > 0) {  // the own slice (i == 0) is complete since the barrier above
             const uint32_t hbar = bar0 + 8 * (nbuf * CL + r);
@@ -381,7 +391,6 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
               asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hbar), "r"(bytes) : "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
-          const uint32_t d_acc = tmem_base + (r % KSPLIT) * NCOLS;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const uint32_t ks = 2 * r + j;

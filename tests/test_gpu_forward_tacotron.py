@@ -107,3 +107,44 @@ def test_api_surface():
     model.refresh()
     out2 = model.generate(x)
     assert float((out2['mel'] - out['mel']).mean()) == pytest.approx(1.0, abs=1e-3)
+
+
+def test_prenet_overlap_and_serialised_paths_agree():
+    """generate() forks stage A onto side streams and prefetches the prenet; FTB_OPT_SERIALIZE runs every launch
+    on the caller's stream.  Same kernels, same order of arithmetic -> bit-identical outputs, run after run (the
+    LSTM's MMA-issuing threads each own an accumulator, so its accumulation order is fixed too)."""
+    from forwardtacotron_b200 import _lib
+    model, _ = cuda_model('forward_tacotron', 0)
+    x = synth.synthetic_tokens(5, 70, seed=9, ragged=True).cuda()
+    a = model.generate(x)
+    _lib.check(_lib.lib().ftb_ft_set_option(model._handle, _lib.FTB_OPT_SERIALIZE, 1))
+    b = model.generate(x)
+    _lib.check(_lib.lib().ftb_ft_set_option(model._handle, _lib.FTB_OPT_SERIALIZE, 0))
+    c = model.generate(x)
+    for k in ('mel', 'mel_post', 'dur', 'pitch', 'energy', 'mel_len'):
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
+
+
+def test_long_utterances_against_oracle():
+    """cfg5-like shape scaled to what the CPU oracle finishes in seconds: T = 900 phonemes -> L ~ 5.5 k frames."""
+    model, _ = cuda_model('forward_tacotron', 0)
+    x = synth.synthetic_tokens(3, 900, seed=11)
+    want = mo.ft_generate(cpu_state_dict(model), x)
+    out, res = check_against(model, x, want)
+    assert out['mel'].shape[-1] > 4000
+    print('B3xT900', res, 'L', out['mel'].shape[-1])
+
+
+def test_corpus_batching_matches_direct_generate():
+    """utils/batching.synthesize_corpus (row a14): bucketed batches give the same mels as generate() on the same
+    padded batch, cut at each row's own frame count."""
+    from forwardtacotron_b200.utils import batching
+    model, _ = cuda_model('forward_tacotron', 0)
+    g = torch.Generator().manual_seed(2)
+    utts = [torch.randint(1, 135, (int(n),), generator=g).tolist() for n in torch.randint(5, 40, (11,), generator=g)]
+    got = batching.synthesize_corpus(model, utts, max_tokens=160)
+    for b in batching.bucket_by_length(utts, max_tokens=160):
+        out = model.generate(b.tokens.cuda())
+        for r, i in enumerate(b.index.tolist()):
+            L = int(out['mel_len'][r])
+            assert torch.equal(got[i], out['mel_post'][r, :, :L])
