@@ -165,17 +165,36 @@ struct EpiCol {
 __device__ __forceinline__ float epi_affine(const EpiCol& e, float acc) {
   return fmaf(fmaxf(acc + e.bias, e.relu_lo), e.scale, e.shift);
 }
-template <int OUT /*1 f32, 2 bf16, 3 both*/, int RES /*0 none, 1 f32, 2 bf16*/>
-__device__ __forceinline__ void epi_rows(const float* sp, int nrows, const EpiCol& e, float* o32, __nv_bfloat16* o16,
-                                         int64_t ldo, const float* r32, const __nv_bfloat16* r16, int64_t ldr) {
+template <int OUT /*1 f32, 2 bf16, 3 both*/>
+__device__ __forceinline__ void epi_rows(const float* sp, int nrows, const EpiCol& e, float* o32, __nv_bfloat16* o16, int64_t ldo) {
 #pragma unroll 8
   for (int rr = 0; rr < nrows; ++rr) {
-    float v = epi_affine(e, sp[rr * tc::STG_LD]);
-    if (RES == 1) v += *r32, r32 += ldr;
-    if (RES == 2) v += __bfloat162float(*r16), r16 += ldr;
-    v *= e.out_scale;
+    const float v = epi_affine(e, sp[rr * tc::STG_LD]) * e.out_scale;
     if (OUT & 1) *o32 = v, o32 += ldo;
     if (OUT & 2) *o16 = __float2bfloat16_rn(v), o16 += ldo;
+  }
+}
+// Residual variant (a few launches per step).  The residual loads of 8 rows are issued together before they are
+// used: one by one inside the row loop each paid a full L2/HBM latency (proj2: 145 us for 20 GFLOP).
+template <int RES /*1 f32, 2 bf16*/>
+__device__ __forceinline__ void epi_rows_res(const float* sp, int nrows, const EpiCol& e, float* o32, __nv_bfloat16* o16,
+                                             bool has_o32, bool has_o16, int64_t ldo, const float* r32,
+                                             const __nv_bfloat16* r16, int64_t ldr) {
+  for (int r0 = 0; r0 < nrows; r0 += 8) {
+    float res[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      res[j] = 0.f;
+      if (r0 + j < nrows) res[j] = RES == 1 ? __ldg(r32 + (r0 + j) * ldr) : __bfloat162float(r16[(r0 + j) * ldr]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (r0 + j < nrows) {
+        const float v = (epi_affine(e, sp[(r0 + j) * tc::STG_LD]) + res[j]) * e.out_scale;
+        if (has_o32) o32[(r0 + j) * ldo] = v;
+        if (has_o16) o16[(r0 + j) * ldo] = __float2bfloat16_rn(v);
+      }
+    }
   }
 }
 template <int OUT>
@@ -342,13 +361,16 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
       for (int ch = half; ch < (a.highway ? 0 : nchunks); ch += 2) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX + ch * 32, r);
+        const int nb = c.n0 + ch * 32;  // first output column of the chunk
+        const int n = nb + lane;
+        const bool nok = n < pN;
+        const int nr = (nok && row_major) ? nrows : 0;
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (ch + 2 >= nchunks) {  // last TMEM read of this warp for this tile: hand the buffer back
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
           released = true;
         }
-        const int nb = c.n0 + ch * 32;  // first output column of the chunk
         if (has_ot) {                   // (B,N,S) output: lanes walk t (coalesced along the time axis)
           const int t = trow0 + lane;
           if (t < S) {
@@ -368,8 +390,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
             asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // the 4 quarters of this column half
           else
             __syncwarp();
-          const int n = nb + lane;
-          const bool nok = n < pN;
           EpiCol e;
           e.bias = (nok && P.bias) ? __ldg(P.bias + n) : 0.f;
           e.scale = (nok && P.scale) ? __ldg(P.scale + n) : 1.f;
@@ -380,23 +400,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
           float* o32 = a.out_f32 + ooff;
           __nv_bfloat16* o16 = a.out_bf16 + ooff;
           const float* sp = stg + lane;
-          const int nr = nok ? nrows : 0;
           if (!pool) {
-            const float* r32 = a.res_f32 + mrow0 * ldr + n;
-            const __nv_bfloat16* r16 = a.res_bf16 + mrow0 * ldr + n;
-            if (has_o16 && !has_o32) {
-              if (has_r16) epi_rows<2, 2>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
-              else if (has_r32) epi_rows<2, 1>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
-              else epi_rows<2, 0>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
-            } else if (has_o32 && !has_o16) {
-              if (has_r32) epi_rows<1, 1>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
-              else if (has_r16) epi_rows<1, 2>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
-              else epi_rows<1, 0>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
-            } else {
-              if (has_r32) epi_rows<3, 1>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
-              else if (has_r16) epi_rows<3, 2>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
-              else epi_rows<3, 0>(sp, nr, e, o32, o16, ldo, r32, r16, ldr);
-            }
+            if (has_r16) epi_rows_res<2>(sp, nr, e, o32, o16, has_o32, has_o16, ldo, nullptr, a.res_bf16 + mrow0 * ldr + n, ldr);
+            else if (has_r32) epi_rows_res<1>(sp, nr, e, o32, o16, has_o32, has_o16, ldo, a.res_f32 + mrow0 * ldr + n, nullptr, ldr);
+            else if (has_o16 && !has_o32) epi_rows<2>(sp, nr, e, o32, o16, ldo);
+            else if (has_o32 && !has_o16) epi_rows<1>(sp, nr, e, o32, o16, ldo);
+            else epi_rows<3>(sp, nr, e, o32, o16, ldo);
           } else {  // out[t] = max(v[t-1], v[t]); tile row 0 is the halo row t0 = first output row - 1
             const float prev = q > 0 ? epi_affine(e, stg_prev[31 * STG_LD + lane]) : -INFINITY;
             if (has_o16 && !has_o32) epi_rows_pool<2>(sp, nr, e, prev, q == 0, trow0, o32, o16, ldo);
