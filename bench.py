@@ -188,6 +188,31 @@ def stft_extra(torch, dev, pk):
                          'note': 'includes the host-side offset upload of wav_to_mel_packed'}}
 
 
+def fastpitch_extra(torch, dev):
+    """BASELINE.json configs[2]: FastPitch batch 128 x 300 phonemes with pitch + energy callbacks (per GPU)."""
+    from forwardtacotron_b200.utils import synth
+    model, _ = synth.synthetic_model('fast_pitch')
+    model = model.to(dev)
+    x = synth.synthetic_tokens(128, 300, seed=5).to(dev)
+    pf, ef = (lambda p: p * 1.2), (lambda e: e + 0.1)
+    out = model.generate(x, pitch_function=pf, energy_function=ef)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    e0.record()
+    for _ in range(reps):
+        out = model.generate(x, pitch_function=pf, energy_function=ef)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    frames = int(out['mel_len'].sum().item())
+    return {'metric': 'mel_frames_per_s', 'value': frames / (ms / 1e3), 'unit': 'frames/s', 'ms_per_step': ms,
+            'workload': 'FastPitch.generate batch 128 x 300 phonemes, pitch*1.2 / energy+0.1 callbacks',
+            'mel_frames_padded_L': int(out['mel'].shape[-1]), 'valid_frames': frames,
+            'numerics': 'IEEE-half tcgen05 GEMMs + mma.sync flash attention, fp32 accumulate / residual stream / '
+                        'LayerNorm; duration predictor fp32 (DESIGN.md 2)'}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -314,6 +339,10 @@ def run_ours(args):
                 line['extra'] = {'stft_mel': stft_extra(torch, dev, pk)}
             except Exception as e:  # the headline line must still be printed
                 line['extra'] = {'stft_mel': {'error': str(e)}}
+            try:
+                line['extra']['fast_pitch'] = fastpitch_extra(torch, dev)
+            except Exception as e:
+                line['extra']['fast_pitch'] = {'error': str(e)}
             cb, _ = cpu_generate_rate(3, 1)
             line['cpu_baseline'] = cb
         print(json.dumps(line), flush=True)

@@ -1,6 +1,7 @@
 // Shared host/device helpers for the ftb200 extension (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -139,6 +140,12 @@ template <>
 struct ActIO<__nv_bfloat16> {
   static __device__ __forceinline__ float load(const __nv_bfloat16* p) { return __bfloat162float(*p); }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+template <>
+struct ActIO<__half> {
+  static __device__ __forceinline__ float load(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ void store(__half* p, float v) { *p = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
 };
 
 }  // namespace ftb

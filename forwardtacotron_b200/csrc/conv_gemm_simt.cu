@@ -123,7 +123,9 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, void* __res
     const int j = (int)((i / Cin_pad) % k);
     const int n = (int)(i / ((int64_t)Cin_pad * k));
     const float v = (n < N && c < Cin) ? w[((int64_t)n * Cin + c) * k + j] : 0.f;
-    if (out_bf16)
+    if (out_bf16 == 2)
+      ((__half*)out)[i] = __float2half_rn(v);
+    else if (out_bf16)
       ((__nv_bfloat16*)out)[i] = __float2bfloat16_rn(v);
     else
       ((float*)out)[i] = v;

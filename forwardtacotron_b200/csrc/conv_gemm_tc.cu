@@ -40,9 +40,10 @@ constexpr int THREADS = 32 * (2 + EPI_WARPS);                     // 320
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // bounded wait: a protocol bug must not hang the GPU
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t idesc_bf16(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16 (format 1) or fp16 (format 0), both
+// K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t idesc_16(int n, bool fp16) {
+  return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 }  // namespace tc
 
@@ -130,7 +131,7 @@ struct alignas(64) TcArgs {
   CUtensorMap map_a;  // (Cin, S, B) bf16, box 64 x box_rows x 1
   TcProb prob[tc::MAXP];
   int nprob, B, S, Cin, cblocks;
-  int m_tiles, m_stride, box_rows, bn, total_tiles, pool, highway;
+  int m_tiles, m_stride, box_rows, bn, total_tiles, pool, highway, fp16;
   int ldo, ldr, n_total;  // n_total: N of the (B,N,S) transposed output
   float out_scale;
   float* out_f32;
@@ -159,8 +160,19 @@ __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile) {
 
 // Epilogue phase 2 for one 32x32 chunk: lane = output column, rows walk the time axis.  Specialised on
 // which outputs / residuals exist so the row loop is branch-free: LDS, 3-4 FP ops, coalesced LDG/STG.
+// 16-bit activation I/O: the buffers are typed __nv_bfloat16* throughout; in fp16 mode (FastPitch) the same 16 bits
+// hold an IEEE half.  fp16 stores saturate instead of overflowing to inf.
+__device__ __forceinline__ __nv_bfloat16 cvt16(float v, bool fp16) {
+  if (!fp16) return __float2bfloat16_rn(v);
+  const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  return *reinterpret_cast<const __nv_bfloat16*>(&h);
+}
+__device__ __forceinline__ float ld16(__nv_bfloat16 x, bool fp16) {
+  return fp16 ? __half2float(*reinterpret_cast<const __half*>(&x)) : __bfloat162float(x);
+}
 struct EpiCol {
   float bias, relu_lo, scale, shift, out_scale;
+  bool fp16;
 };
 __device__ __forceinline__ float epi_affine(const EpiCol& e, float acc) {
   return fmaf(fmaxf(acc + e.bias, e.relu_lo), e.scale, e.shift);
@@ -171,7 +183,7 @@ __device__ __forceinline__ void epi_rows(const float* sp, int nrows, const EpiCo
   for (int rr = 0; rr < nrows; ++rr) {
     const float v = epi_affine(e, sp[rr * tc::STG_LD]) * e.out_scale;
     if (OUT & 1) *o32 = v, o32 += ldo;
-    if (OUT & 2) *o16 = __float2bfloat16_rn(v), o16 += ldo;
+    if (OUT & 2) *o16 = cvt16(v, e.fp16), o16 += ldo;
   }
 }
 // Residual variant (a few launches per step).  The residual loads of 8 rows are issued together before they are
@@ -185,14 +197,14 @@ __device__ __forceinline__ void epi_rows_res(const float* sp, int nrows, const E
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       res[j] = 0.f;
-      if (r0 + j < nrows) res[j] = RES == 1 ? __ldg(r32 + (r0 + j) * ldr) : __bfloat162float(r16[(r0 + j) * ldr]);
+      if (r0 + j < nrows) res[j] = RES == 1 ? __ldg(r32 + (r0 + j) * ldr) : ld16(r16[(r0 + j) * ldr], e.fp16);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (r0 + j < nrows) {
         const float v = (epi_affine(e, sp[(r0 + j) * tc::STG_LD]) + res[j]) * e.out_scale;
         if (has_o32) o32[(r0 + j) * ldo] = v;
-        if (has_o16) o16[(r0 + j) * ldo] = __float2bfloat16_rn(v);
+        if (has_o16) o16[(r0 + j) * ldo] = cvt16(v, e.fp16);
       }
     }
   }
@@ -206,7 +218,7 @@ __device__ __forceinline__ void epi_rows_pool(const float* sp, int nrows, const 
     if (!(first_is_halo && rr == 0)) {
       const float v = fmaxf(prev, cur) * e.out_scale;
       if (OUT & 1) *o32 = v;
-      if (OUT & 2) *o16 = __float2bfloat16_rn(v);
+      if (OUT & 2) *o16 = cvt16(v, e.fp16);
     }
     o32 += ldo, o16 += ldo;
     prev = trow0 + rr >= 0 ? cur : -INFINITY;
@@ -396,6 +408,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
           e.shift = (nok && P.shift) ? __ldg(P.shift + n) : 0.f;
           e.relu_lo = relu_lo;
           e.out_scale = out_scale;
+          e.fp16 = a.fp16 != 0;
           const int64_t ooff = mrow0 * ldo + P.n_offset + n;
           float* o32 = a.out_f32 + ooff;
           __nv_bfloat16* o16 = a.out_bf16 + ooff;
@@ -488,6 +501,8 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.cblocks = Cin / BK;
   a.pool = o.pool ? 1 : 0;
   a.highway = o.highway ? 1 : 0;
+  a.fp16 = o.fp16 ? 1 : 0;
+  FTB_REQUIRE(!(o.fp16 && o.highway), FTB_ERR_INVALID, "conv_gemm_bf16: the highway epilogue is bf16 only");
   a.m_stride = o.pool ? BM - 1 : BM;
   a.m_tiles = cdiv(S, a.m_stride);
   a.box_rows = BM;  // the box may exceed the tensor: rows outside [0,S) are zero-filled (conv padding, pool halo)
@@ -502,6 +517,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.res_bf16 = o.res_bf16;
   a.n_total = items[0].N;
   FTB_REQUIRE(!o.out_t || n_items == 1, FTB_ERR_INVALID, "conv_gemm_bf16: transposed output needs a single problem");
+  FTB_REQUIRE(!(o.out_t && o.fp16 && o.res_bf16), FTB_ERR_INVALID, "conv_gemm_bf16: fp16 residual with transposed output");
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)S, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)lda * 2, (cuuint64_t)S * lda * 2};
@@ -535,7 +551,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
     P.n_tiles = cdiv(it.N, a.bn);
     P.nkb = it.ktaps * a.cblocks;
     P.tile_begin = tiles;
-    P.idesc = idesc_bf16(it.N >= a.bn ? a.bn : (int)align_up(it.N, 16));
+    P.idesc = idesc_16(it.N >= a.bn ? a.bn : (int)align_up(it.N, 16), o.fp16);
     tiles += P.n_tiles * a.m_tiles * B;
   }
   a.total_tiles = tiles;

@@ -99,7 +99,7 @@ __global__ void head1_kernel(const T* __restrict__ x, const float* __restrict__ 
 // copy that feeds the next tensor-core GEMM.  One warp per row; C <= 1024.  In place (y32 == x) is
 // fine: a row is fully read before it is written.  (models/fast_pitch.py:70-71,84,91,116,128)
 __global__ void layernorm_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 float* y32, __nv_bfloat16* y16, int64_t rows, int C) {
+                                 float* y32, void* y16, int y16_fp16, int64_t rows, int C) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -130,7 +130,10 @@ __global__ void layernorm_kernel(const float* x, const float* __restrict__ gamma
     if (c < C) {
       const float o = (v[n] - mean) * rstd * gamma[c] + beta[c];
       if (y32) y32[r * C + c] = o;
-      if (y16) y16[r * C + c] = __float2bfloat16_rn(o);
+      if (y16) {
+        if (y16_fp16) ActIO<__half>::store((__half*)y16 + r * C + c, o);
+        else ((__nv_bfloat16*)y16)[r * C + c] = __float2bfloat16_rn(o);
+      }
     }
   }
 }
@@ -197,6 +200,7 @@ int embed(const int64_t* tok, const float* table, T* out, int64_t rows, int C, i
 }
 template int embed<float>(const int64_t*, const float*, float*, int64_t, int, int, int, cudaStream_t);
 template int embed<__nv_bfloat16>(const int64_t*, const float*, __nv_bfloat16*, int64_t, int, int, int, cudaStream_t);
+template int embed<__half>(const int64_t*, const float*, __half*, int64_t, int, int, int, cudaStream_t);
 
 template <typename T>
 int maxpool_inplace(T* x, int B, int S, int C, cudaStream_t s) {
@@ -231,6 +235,8 @@ template int cond_add<float>(float*, const float*, const float*, const float*, c
                              const float*, float, float, int, int, int, cudaStream_t);
 template int cond_add<__nv_bfloat16>(__nv_bfloat16*, const float*, const float*, const float*, const float*,
                                      const float*, const float*, float, float, int, int, int, cudaStream_t);
+template int cond_add<__half>(__half*, const float*, const float*, const float*, const float*, const float*, const float*,
+                              float, float, int, int, int, cudaStream_t);
 
 template <typename T>
 int head1(const T* x, const float* w, const float* b, float alpha, float* out, int64_t rows, int C, cudaStream_t s) {
@@ -243,11 +249,11 @@ template int head1<float>(const float*, const float*, const float*, float, float
 template int head1<__nv_bfloat16>(const __nv_bfloat16*, const float*, const float*, float, float*, int64_t, int,
                                   cudaStream_t);
 
-int layernorm(const float* x, const float* gamma, const float* beta, float* y32, __nv_bfloat16* y16, int64_t rows,
+int layernorm(const float* x, const float* gamma, const float* beta, float* y32, void* y16, int y16_fp16, int64_t rows,
               int C, cudaStream_t s) {
   ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   FTB_REQUIRE(C <= 1024, FTB_ERR_UNSUPPORTED, "layernorm: C=%d > 1024", C);
-  layernorm_kernel<<<cdiv(rows, 8), 256, 0, s>>>(x, gamma, beta, y32, y16, rows, C);
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, s>>>(x, gamma, beta, y32, y16, y16_fp16, rows, C);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }
@@ -290,6 +296,7 @@ int cast_rows(const float* in, T* out, int64_t rows, int C, int ldi, int ldo, cu
 }
 template int cast_rows<float>(const float*, float*, int64_t, int, int, int, cudaStream_t);
 template int cast_rows<__nv_bfloat16>(const float*, __nv_bfloat16*, int64_t, int, int, int, cudaStream_t);
+template int cast_rows<__half>(const float*, __half*, int64_t, int, int, int, cudaStream_t);
 
 template <typename T>
 int to_f32(const T* in, float* out, int64_t n, cudaStream_t s) {
@@ -300,5 +307,6 @@ int to_f32(const T* in, float* out, int64_t n, cudaStream_t s) {
 }
 template int to_f32<float>(const float*, float*, int64_t, cudaStream_t);
 template int to_f32<__nv_bfloat16>(const __nv_bfloat16*, float*, int64_t, cudaStream_t);
+template int to_f32<__half>(const __half*, float*, int64_t, cudaStream_t);
 
 }  // namespace ftb

@@ -37,10 +37,13 @@ struct ftb_fp_handle : ftb::ModelBase {
   ftb::TransformerW prenet, postnet;
   const float *pitch_w = nullptr, *pitch_b = nullptr, *energy_w = nullptr, *energy_b = nullptr;
   ftb::Layer lin;
-  // gemm_mode 0 (default) and 1: every GEMM fp32.  gemm_mode 2: prenet / postnet / lin on the bf16 tcgen05
-  // kernel.  bf16 operands put the post-LN transformer stack at mean-abs 1.7e-3 on the fixtures, outside the
-  // 1e-3 budget (mel std is ~0.6 here, 10x ForwardTacotron's), so bf16 is opt-in for FastPitch.
-  bool bf16_mode() const { return cfg.gemm_mode == 2; }
+  // gemm_mode 0 (default): prenet / postnet / lin GEMMs on the tcgen05 kernel with IEEE-half operands (fp32
+  // accumulate, fp32 residual stream); 1: every GEMM fp32 SIMT; 2: bf16 operands.  bf16's 8-bit significand puts the
+  // post-LN transformer stack at mean-abs 1.7e-3 on the fixtures, outside the 1e-3 budget (mel std is ~0.6 here,
+  // 10x ForwardTacotron's); half has 11 bits at the same tensor-core rate and these activations are LayerNorm-bounded
+  // (stores saturate at +-65504), so half is the default and bf16 the opt-in.
+  bool half_mode() const { return cfg.gemm_mode == 0 || cfg.gemm_mode == 2; }
+  bool is_fp16() const { return cfg.gemm_mode == 0; }
 };
 
 namespace ftb {
@@ -51,7 +54,7 @@ static int build_transformer(ftb_fp_handle* h, TransformerW& W, const std::strin
   W.dfft = dfft;
   W.heads = heads;
   W.f32_only = f32_only;
-  const bool w16 = h->bf16_mode() && !f32_only, w32 = !w16;
+  const bool w16 = h->half_mode() && !f32_only, w32 = !w16;
   FTB_REQUIRE(heads > 0 && E % heads == 0 && (E / heads == 64 || E / heads == 128), FTB_ERR_UNSUPPORTED,
               "%s: head dim %d not built (64, 128)", p.c_str(), heads ? E / heads : 0);
   FTB_REQUIRE(E % 64 == 0 && dfft % 64 == 0 && E <= 1024, FTB_ERR_UNSUPPORTED, "%s: d_model/d_fft must be multiples of 64",
@@ -114,7 +117,8 @@ static int run_transformer(ftb_fp_handle* h, TransformerW& W, T* x, float* x32_b
   const int E = W.E;
   constexpr bool kF32 = std::is_same<T, float>::value;
   float* x32 = kF32 ? (float*)x : x32_buf;  // caller-owned fp32 stream (B,S,E) in bf16 mode
-  bf16* x16 = kF32 ? nullptr : (bf16*)x;
+  void* x16 = kF32 ? nullptr : (void*)x;
+  const int x16_fp16 = std::is_same<T, f16>::value;
   if (!kF32) FTB_TRY(to_f32<T>(x, x32, M * E, s));
   FTB_TRY(posenc_add<float>(x32, W.pe, W.scale, B, S, E, s));
   if (!kF32) FTB_TRY(cast_rows<T>(x32, x, M, E, E, E, s));
@@ -125,13 +129,13 @@ static int run_transformer(ftb_fp_handle* h, TransformerW& W, T* x, float* x32_b
     FTB_TRY(h->gemm<T>(L.qkv, x, E, B, S, act_out(w.qkv, 3 * E), nullptr, 0, 1.f, s));
     FTB_TRY(attention<T>(w.qkv, mask_tokens, w.ctx, B, S, E, W.heads, s));
     FTB_TRY(h->gemm<T>(L.out_proj, w.ctx, E, B, S, a32, nullptr, E, 1.f, s, x32));  // + bias + residual (fp32)
-    FTB_TRY(layernorm(w.a32, L.n1w, L.n1b, x32, x16, M, E, s));
+    FTB_TRY(layernorm(w.a32, L.n1w, L.n1b, x32, x16, x16_fp16, M, E, s));
     FTB_TRY(h->gemm<T>(L.conv1, x, E, B, S, act_out(w.f1, W.dfft), nullptr, 0, 1.f, s));  // + bias, ReLU
     FTB_TRY(h->gemm<T>(L.conv2, w.f1, W.dfft, B, S, a32, nullptr, E, 1.f, s, x32));       // + bias + residual
-    FTB_TRY(layernorm(w.a32, L.n2w, L.n2b, x32, x16, M, E, s));
+    FTB_TRY(layernorm(w.a32, L.n2w, L.n2b, x32, x16, x16_fp16, M, E, s));
     h->launches += 3;
   }
-  FTB_TRY(layernorm(x32, W.nw, W.nb, x32, x16, M, E, s));
+  FTB_TRY(layernorm(x32, W.nw, W.nb, x32, x16, x16_fp16, M, E, s));
   h->launches += 4;
   A.reset(mark);
   return FTB_OK;
@@ -182,7 +186,7 @@ static int64_t fp_bytes(const ftb_fp_handle* h, int B, int Tn, int L) {
   for (int i = 0; i < 3; ++i) {
     Arena A(nullptr, 0);
     A.take<char>(256);
-    if (h->series[i].tr.f32_only || !h->bf16_mode()) {
+    if (h->series[i].tr.f32_only || !h->half_mode()) {
       A.take<float>((int64_t)B * Tn * h->series[i].tr.E);
       plan_tr<float>(A, h->series[i].tr, B, Tn);
     } else {
@@ -219,6 +223,7 @@ extern "C" int ftb_fp_create(const ftb_fp_config* cfg, const ftb_tensor* tensors
   ftb_fp_handle* h = new ftb_fp_handle();
   h->cfg = *cfg;
   h->device = device;
+  h->pack16 = h->is_fp16() ? 2 : 1;
   for (int i = 0; i < n_tensors; ++i) h->sd[tensors[i].name] = tensors[i];
   const ftb_fp_config& c = h->cfg;
   auto build_series = [&](FpSeriesW& P, const std::string& p, int E, int heads, int layers, int dfft, bool f32) -> int {
@@ -231,12 +236,13 @@ extern "C" int ftb_fp_create(const ftb_fp_config* cfg, const ftb_tensor* tensors
   auto build = [&]() -> int {
     FTB_TRY(build_series(h->series[0], "dur_pred", c.durpred_d_model, c.durpred_n_heads, c.durpred_layers,
                          c.durpred_d_fft, true));
-    // The three predictors are small (d_model 128, phoneme rate) and their post-LN stacks amplify bf16
-    // operand rounding past the 1e-3 mean-abs budget (measured 2.9e-3 on pitch), so all of them run fp32.
+    // The duration predictor is always fp32 (bit-exact durations).  Pitch / energy: bf16 operands put their post-LN
+    // stacks at 2.9e-3 mean-abs, past the 1e-3 budget, so they stay fp32 unless the 16-bit type is IEEE half.
+    const bool pe32 = !h->is_fp16();
     FTB_TRY(build_series(h->series[1], "pitch_pred", c.pitch_d_model, c.pitch_n_heads, c.pitch_layers, c.pitch_d_fft,
-                         true));
+                         pe32));
     FTB_TRY(build_series(h->series[2], "energy_pred", c.energy_d_model, c.energy_n_heads, c.energy_layers,
-                         c.energy_d_fft, true));
+                         c.energy_d_fft, pe32));
     FTB_TRY(h->get("embedding.weight", {c.num_chars, c.d_model}, &h->embedding));
     FTB_TRY(build_transformer(h, h->prenet, "prenet", c.d_model, c.prenet_fft, c.prenet_layers, c.prenet_heads,
                               c.conv1_kernel, c.conv2_kernel, false));
@@ -246,7 +252,7 @@ extern "C" int ftb_fp_create(const ftb_fp_config* cfg, const ftb_tensor* tensors
     FTB_TRY(h->get("pitch_proj.bias", {c.d_model}, &h->pitch_b));
     FTB_TRY(h->get("energy_proj.weight", {c.d_model, 1, 3}, &h->energy_w));
     FTB_TRY(h->get("energy_proj.bias", {c.d_model}, &h->energy_b));
-    const bool w16 = h->bf16_mode(), w32 = !w16;
+    const bool w16 = h->half_mode(), w32 = !w16;
     FTB_TRY(h->make_conv(h->lin, "lin.weight", c.n_mels, c.d_model, 1, 0, false, "", "lin.bias", w32, w16));
     FTB_CHECK_CUDA(cudaStreamSynchronize(h->prep));
     return FTB_OK;
@@ -264,7 +270,7 @@ extern "C" void ftb_fp_destroy(ftb_fp_handle* h) { delete h; }
 
 extern "C" int64_t ftb_fp_workspace_bytes(const ftb_fp_handle* h, int B, int T, int L) {
   if (!h || B <= 0 || T <= 0) return -1;
-  return h->bf16_mode() ? fp_bytes<bf16>(h, B, T, L) : fp_bytes<float>(h, B, T, L);
+  return h->half_mode() ? fp_bytes<bf16>(h, B, T, L) : fp_bytes<float>(h, B, T, L);  // bf16 and half: same sizes
 }
 
 extern "C" int ftb_fp_predict(ftb_fp_handle* h, const int64_t* tokens, int B, int T, float alpha, float* dur,
@@ -280,10 +286,11 @@ extern "C" int ftb_fp_predict(ftb_fp_handle* h, const int64_t* tokens, int B, in
   for (int i = 0; i < 3; ++i) {
     Arena A(ws + 256, workspace_bytes - 256);
     const float a = i == 0 ? alpha : 1.f;
-    if (h->series[i].tr.f32_only || !h->bf16_mode())
+    if (h->series[i].tr.f32_only || !h->half_mode())
       FTB_TRY(run_fp_series<float>(h, h->series[i], tokens, B, T, a, outs[i], A, s));
     else
-      FTB_TRY(run_fp_series<bf16>(h, h->series[i], tokens, B, T, a, outs[i], A, s));
+      FTB_TRY(h->is_fp16() ? run_fp_series<f16>(h, h->series[i], tokens, B, T, a, outs[i], A, s)
+                           : run_fp_series<bf16>(h, h->series[i], tokens, B, T, a, outs[i], A, s));
     if (i == 0) {
       FTB_TRY(ftb_duration_fallback(dur, (int64_t)B * T, ws, s));
       h->launches += 2;
@@ -300,7 +307,9 @@ extern "C" int ftb_fp_synthesize(ftb_fp_handle* h, const int64_t* tokens, const 
   FTB_REQUIRE(B > 0 && T > 0 && L > 0, FTB_ERR_INVALID, "ftb_fp_synthesize: bad sizes B=%d T=%d L=%d", B, T, L);
   h->launches = 0;
   Arena A(workspace, workspace_bytes);
-  if (h->bf16_mode()) return run_fp_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, A, (cudaStream_t)stream);
+  if (h->half_mode())
+    return h->is_fp16() ? run_fp_synthesize<f16>(h, tokens, cum, pitch, energy, B, T, L, mel, A, (cudaStream_t)stream)
+                        : run_fp_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, A, (cudaStream_t)stream);
   return run_fp_synthesize<float>(h, tokens, cum, pitch, energy, B, T, L, mel, A, (cudaStream_t)stream);
 }
 

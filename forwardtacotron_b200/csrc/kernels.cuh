@@ -25,6 +25,7 @@ struct TcOut {
   int ldo = 0, ldr = 0;
   float out_scale = 1.f;
   bool pool = false;
+  bool fp16 = false;     // the 16-bit operands / outputs / residual are IEEE half instead of bfloat16
   bool highway = false;  // N = 2C interleaved [32 x1 | 32 x2] groups -> y (C) = sigmoid(x2) relu(x1) + (1 - sigmoid(x2)) res_bf16
 };
 int tc_tile_n(int N);
@@ -51,7 +52,7 @@ int cond_add(T* x, const float* pitch, const float* energy, const float* wp, con
              const float* be, float ps, float es, int B, int Tn, int C, cudaStream_t s);
 template <typename T>
 int head1(const T* x, const float* w, const float* b, float alpha, float* out, int64_t rows, int C, cudaStream_t s);
-int layernorm(const float* x, const float* gamma, const float* beta, float* y32, __nv_bfloat16* y16, int64_t rows,
+int layernorm(const float* x, const float* gamma, const float* beta, float* y32, void* y16, int y16_fp16, int64_t rows,
               int C, cudaStream_t s);
 template <typename T>
 int posenc_add(T* x, const float* pe, const float* scale, int B, int S, int E, cudaStream_t s);

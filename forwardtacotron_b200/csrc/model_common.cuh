@@ -8,6 +8,7 @@
 namespace ftb {
 
 using bf16 = __nv_bfloat16;
+using f16 = __half;  // FastPitch's 16-bit activation / weight type: same bytes, 11-bit significand
 
 // One conv / linear layer in GEMM form.  CinP = Cin rounded up to 64 (zero weights for the
 // padded channels) so the same activation buffers serve the tcgen05 and the fp32 kernel.
@@ -29,7 +30,7 @@ struct Rnn {  // bidirectional single layer
 
 struct Out {  // where a GEMM writes
   float* f32 = nullptr;
-  bf16* b16 = nullptr;
+  bf16* b16 = nullptr;  // 16-bit output (bf16, or IEEE half when the GEMM runs with T = f16)
   float* t = nullptr;  // (B,N,S) f32
   int ldo = 0, n_offset = 0;
 };
@@ -39,7 +40,7 @@ inline Out act_out(T* p, int ldo, int n_offset = 0) {
   if (std::is_same<T, float>::value)
     o.f32 = (float*)p;
   else
-    o.b16 = (bf16*)p;
+    o.b16 = (bf16*)p;  // f16 buffers travel as 16-bit words too
   o.ldo = ldo;
   o.n_offset = n_offset;
   return o;
@@ -77,6 +78,8 @@ struct ModelBase {
   }
   bool has(const std::string& name) const { return sd.count(name) != 0; }
 
+  int pack16 = 1;  // ftb_pack_conv_weight type of the 16-bit weight copies: 1 bf16, 2 IEEE half
+
   // conv weight (N,Cin,k) [+ BatchNorm `bn` prefix] [+ bias] -> Layer
   int make_conv(Layer& L, const std::string& wname, int N, int Cin, int k, int pad, bool relu, const std::string& bn,
                 const std::string& bias, bool want32, bool want16) {
@@ -100,7 +103,7 @@ struct ModelBase {
     if (want16) {
       L.w16 = dalloc<bf16>(n);
       FTB_REQUIRE(L.w16, FTB_ERR_CUDA, "out of device memory packing %s", wname.c_str());
-      FTB_TRY(ftb_pack_conv_weight(w, L.w16, N, Cin, k, N, L.CinP, 1, prep));
+      FTB_TRY(ftb_pack_conv_weight(w, L.w16, N, Cin, k, N, L.CinP, pack16, prep));
     }
     if (!bn.empty()) {
       const float *g, *b, *m, *v;
@@ -149,7 +152,7 @@ struct ModelBase {
       FTB_TRY(get(p + ".bias_ih_l0" + sfx, {G * H}, &b_ih));
       FTB_TRY(get(p + ".bias_hh_l0" + sfx, {G * H}, &b_hh));
       if (want32) FTB_TRY(ftb_pack_conv_weight(w_ih, L.w32 + d * per_dir, G * H, in, 1, G * H, L.CinP, 0, prep));
-      if (want16) FTB_TRY(ftb_pack_conv_weight(w_ih, L.w16 + d * per_dir, G * H, in, 1, G * H, L.CinP, 1, prep));
+      if (want16) FTB_TRY(ftb_pack_conv_weight(w_ih, L.w16 + d * per_dir, G * H, in, 1, G * H, L.CinP, pack16, prep));
       // b_hh folds into the input projection for every gate except the GRU n gate
       FTB_TRY(rnn_bias(b_ih, b_hh, L.bias + d * G * H, G * H, lstm ? G * H : 2 * H, prep));
       FTB_TRY(copy_f32(w_hh, R.w_hh + (int64_t)d * G * H * H, (int64_t)G * H * H, prep));
@@ -190,10 +193,28 @@ struct ModelBase {
       FTB_REQUIRE(L.w32, FTB_ERR_INVALID, "layer has no fp32 weights packed");
       return conv_gemm_f32((const float*)x, L.w32, d, s);
     }
-    d.residual_bf16 = residual;
-    d.residual_f32 = residual32;
-    FTB_REQUIRE(L.w16, FTB_ERR_INVALID, "layer has no bf16 weights packed");
-    return conv_gemm_bf16((const bf16*)x, L.w16, d, s);
+    FTB_REQUIRE(L.w16, FTB_ERR_INVALID, "layer has no 16-bit weights packed");
+    TcItem it;
+    it.w = L.w16;
+    it.N = L.N;
+    it.ktaps = L.k;
+    it.pad_left = L.pad;
+    it.n_offset = o.n_offset;
+    it.relu = L.relu;
+    it.bias = L.bias;
+    it.scale = L.scale;
+    it.shift = L.shift;
+    TcOut to;
+    to.out_f32 = o.f32;
+    to.out_bf16 = o.b16;
+    to.out_t = o.t;
+    to.res_f32 = residual32;
+    to.res_bf16 = (const bf16*)residual;
+    to.ldo = o.ldo;
+    to.ldr = ldr;
+    to.out_scale = out_scale;
+    to.fp16 = std::is_same<T, f16>::value;
+    return conv_gemm_group((const bf16*)x, lda, B, S, L.CinP, &it, 1, to, s);
   }
 
   // One highway layer on the tensor cores: L packs W1/W2 interleaved in groups of 32 rows (pack_highway), the

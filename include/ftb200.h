@@ -131,7 +131,7 @@ int ftb_conv_bank_bf16(const void* x, const void* const* w_packed, const ftb_con
  * this returns how many waits gave up since the library was loaded (0 in a healthy run). */
 int ftb_tc_timeout_count(void);
 /* Pack a reference-layout conv weight (N, Cin, k) f32 into (Npad, k*Cin_pad) K-major
- * f32 or bf16 (zero padded). */
+ * f32 (out_bf16 = 0), bf16 (1) or IEEE half (2), zero padded. */
 int ftb_pack_conv_weight(const float* w, void* out, int N, int Cin, int k, int Npad, int Cin_pad,
                          int out_bf16, void* stream);
 
@@ -242,7 +242,7 @@ typedef struct ftb_fp_config { /* keys of config.yaml fast_pitch.model + num_cha
   int32_t prenet_layers, prenet_heads, prenet_fft;
   int32_t postnet_layers, postnet_heads, postnet_fft;
   float pitch_strength, energy_strength;
-  int32_t gemm_mode;
+  int32_t gemm_mode; /* 0: IEEE-half tcgen05 GEMMs + tensor-core attention (duration predictor fp32); 1: all fp32; 2: bf16 */
 } ftb_fp_config;
 
 typedef struct ftb_fp_handle ftb_fp_handle;
