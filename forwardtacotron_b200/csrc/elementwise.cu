@@ -98,12 +98,12 @@ __global__ void head1_kernel(const T* __restrict__ x, const float* __restrict__ 
 // y32 = LN(x) kept in fp32 (the residual stream of the FFT blocks stays fp32), y16 = optional bf16
 // copy that feeds the next tensor-core GEMM.  One warp per row; C <= 1024.  In place (y32 == x) is
 // fine: a row is fully read before it is written.  (models/fast_pitch.py:70-71,84,91,116,128)
+template <int MAXV>  // values per lane: C <= 32 * MAXV (instantiated for C <= 128, <= 256 and <= 1024)
 __global__ void layernorm_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float* y32, void* y16, int y16_fp16, int64_t rows, int C) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
-  constexpr int MAXV = 32;  // C <= 1024
   float v[MAXV];
   float s = 0.f;
 #pragma unroll
@@ -253,7 +253,12 @@ int layernorm(const float* x, const float* gamma, const float* beta, float* y32,
               int C, cudaStream_t s) {
   ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   FTB_REQUIRE(C <= 1024, FTB_ERR_UNSUPPORTED, "layernorm: C=%d > 1024", C);
-  layernorm_kernel<<<cdiv(rows, 8), 256, 0, s>>>(x, gamma, beta, y32, y16, y16_fp16, rows, C);
+  if (C <= 128)
+    layernorm_kernel<4><<<cdiv(rows, 8), 256, 0, s>>>(x, gamma, beta, y32, y16, y16_fp16, rows, C);
+  else if (C <= 256)
+    layernorm_kernel<8><<<cdiv(rows, 8), 256, 0, s>>>(x, gamma, beta, y32, y16, y16_fp16, rows, C);
+  else
+    layernorm_kernel<32><<<cdiv(rows, 8), 256, 0, s>>>(x, gamma, beta, y32, y16, y16_fp16, rows, C);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }
