@@ -148,3 +148,14 @@ def test_corpus_batching_matches_direct_generate():
         for r, i in enumerate(b.index.tolist()):
             L = int(out['mel_len'][r])
             assert torch.equal(got[i], out['mel_post'][r, :, :L])
+
+
+@pytest.mark.parametrize('B,T', [(1, 1), (1, 3), (70, 33), (9, 129)])
+def test_odd_shapes_against_oracle(B, T):
+    """Batch sizes that do not divide the recurrence chunking (70 -> clusters of 24, 24, 22), single tokens,
+    sequences one past a 128-row tile."""
+    model, _ = cuda_model('forward_tacotron', 0)
+    x = synth.synthetic_tokens(B, T, seed=B * 100 + T, ragged=T > 3)
+    want = mo.ft_generate(cpu_state_dict(model), x)
+    out, res = check_against(model, x, want)
+    assert out['mel'].shape == want['mel'].shape
