@@ -75,6 +75,10 @@ SIGNATURES = {
     'ftb_profile_family_name': (C.c_char_p, [_I]),
     'ftb_profile_enable': (_I, [_I]),
     'ftb_profile_collect': (_I, [_P, _P, _P, _P]),
+    'ftb_enable_peer_access': (_I, [_I, _I]),
+    'ftb_ipc_alloc': (_I, [_L, _I, C.POINTER(_P), _P]),
+    'ftb_ipc_open': (_I, [_P, _I, C.POINTER(_P)]),
+    'ftb_ipc_release': (_I, [_P, _I]),
     'ftb_device_check': (_I, [_I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     'ftb_length_plan': (_I, [_P, _P, _P, _I, _I, _P]),
     'ftb_length_expand': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -141,3 +141,54 @@ extern "C" int ftb_device_check(int device, int* sm_count, int* cc_major, int* c
               "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, maj, mnr);
   return FTB_OK;
 }
+
+// Lets kernels launched on `device` address memory that lives on `peer` (same node, NVLink / PCIe P2P).  Used by the
+// peer-mapped result window of the sharded run (utils/peer_window.py); already-enabled is not an error.
+extern "C" int ftb_enable_peer_access(int device, int peer) {
+  if (device == peer) return FTB_OK;
+  int can = 0;
+  FTB_CHECK_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+  FTB_REQUIRE(can, FTB_ERR_UNSUPPORTED, "GPU %d cannot access GPU %d peer-to-peer", device, peer);
+  int cur = 0;
+  FTB_CHECK_CUDA(cudaGetDevice(&cur));
+  FTB_CHECK_CUDA(cudaSetDevice(device));
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    e = cudaSuccess;
+  }
+  cudaSetDevice(cur);
+  FTB_CHECK_CUDA(e);
+  return FTB_OK;
+}
+
+// ---- peer-mapped result window (utils/peer_window.py): CUDA IPC allocation shared by the ranks of one node ----------
+// The owner allocates with cudaMalloc (so the IPC handle maps exactly this range) and exports a 64-byte handle; every
+// other process imports it WHILE ITS OWN DEVICE IS CURRENT, which is what makes the mapping addressable by kernels of
+// that device (cudaIpcMemLazyEnablePeerAccess turns on the NVLink peer path).
+extern "C" int ftb_ipc_alloc(int64_t bytes, int device, void** dev_ptr, unsigned char* handle64) {
+  FTB_REQUIRE(bytes > 0 && dev_ptr && handle64, FTB_ERR_INVALID, "ftb_ipc_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  FTB_CHECK_CUDA(cudaSetDevice(device));
+  FTB_CHECK_CUDA(cudaMalloc(dev_ptr, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  FTB_CHECK_CUDA(cudaIpcGetMemHandle(&h, *dev_ptr));
+  memcpy(handle64, &h, 64);
+  return FTB_OK;
+}
+extern "C" int ftb_ipc_open(const unsigned char* handle64, int device, void** dev_ptr) {
+  FTB_REQUIRE(handle64 && dev_ptr, FTB_ERR_INVALID, "ftb_ipc_open: bad arguments");
+  FTB_CHECK_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  FTB_CHECK_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return FTB_OK;
+}
+extern "C" int ftb_ipc_release(void* dev_ptr, int owner) {
+  if (!dev_ptr) return FTB_OK;
+  if (owner)
+    FTB_CHECK_CUDA(cudaFree(dev_ptr));
+  else
+    FTB_CHECK_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return FTB_OK;
+}

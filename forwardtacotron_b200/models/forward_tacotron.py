@@ -127,8 +127,12 @@ class ForwardTacotron(NativeModel):
         return dur, pitch, energy
 
     def synthesize(self, x: torch.Tensor, dur_hat: torch.Tensor, pitch_hat: torch.Tensor,
-                   energy_hat: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """Stage B == the reference's ``_generate_mel`` (:289-330); clamps ``dur_hat`` in place."""
+                   energy_hat: torch.Tensor, mel_post_alloc=None) -> Dict[str, torch.Tensor]:
+        """Stage B == the reference's ``_generate_mel`` (:289-330); clamps ``dur_hat`` in place.
+
+        ``mel_post_alloc(B, n_mels, L) -> float32 tensor`` (or utils/peer_window.PeerSlot; optional) supplies the memory ``mel_post`` is written to
+        by the last GEMM's epilogue.  It may live on ANOTHER GPU of the node (peer-mapped, utils/peer_window.py): the
+        final gather of a sharded run then costs no extra pass."""
         x = self._check_tokens(x)
         lib, dev = _lib.lib(), x.device
         B, T = x.shape
@@ -144,7 +148,13 @@ class ForwardTacotron(NativeModel):
         ws = self._workspace_for(h, B, T, L, dev)
         n_mels = self._dims['n_mels']
         mel = torch.empty((B, n_mels, L), dtype=torch.float32, device=dev)
-        mel_post = torch.empty((B, n_mels, L), dtype=torch.float32, device=dev)
+        if mel_post_alloc is None:
+            mel_post = torch.empty((B, n_mels, L), dtype=torch.float32, device=dev)
+        else:
+            mel_post = mel_post_alloc(B, n_mels, L)
+            if not (mel_post.is_cuda and mel_post.dtype == torch.float32 and mel_post.is_contiguous()
+                    and tuple(mel_post.shape) == (B, n_mels, L)):
+                raise TypeError('mel_post_alloc must return a contiguous float32 CUDA tensor of shape (B, n_mels, L)')
         with torch.cuda.device(dev):
             _lib.check(lib.ftb_ft_synthesize(h, _lib.ptr(x), _lib.ptr(cum), _lib.ptr(pitch_c), _lib.ptr(energy_c),
                                              B, T, L, _lib.ptr(mel), _lib.ptr(mel_post), _lib.ptr(ws), ws.numel(),
@@ -154,7 +164,8 @@ class ForwardTacotron(NativeModel):
 
     def generate(self, x: torch.Tensor, alpha=1.0,
                  pitch_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x,
-                 energy_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x) -> Dict[str, torch.Tensor]:
+                 energy_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x,
+                 mel_post_alloc=None) -> Dict[str, torch.Tensor]:
         self.eval()
         with torch.no_grad():
             x = self._check_tokens(x)
@@ -167,7 +178,7 @@ class ForwardTacotron(NativeModel):
                 dur_hat, pitch_hat, energy_hat = self.predict(x, alpha)
                 pitch_hat = pitch_function(pitch_hat)
                 energy_hat = energy_function(energy_hat)
-                return self.synthesize(x, dur_hat, pitch_hat, energy_hat)
+                return self.synthesize(x, dur_hat, pitch_hat, energy_hat, mel_post_alloc)
             finally:
                 _lib.check(lib.ftb_ft_set_option(h, _lib.FTB_OPT_OVERLAP_PRENET, 0))
 

@@ -122,17 +122,23 @@ def gather_mels(mels: Sequence[torch.Tensor], index: Sequence[int], n_total: int
 
 
 def synthesize_corpus(model, utterances: Sequence[Sequence[int]], alpha: float = 1.0, max_tokens: int = 16384,
-                      max_batch: int = 256, key: str = 'mel_post', device=None,
+                      max_batch: int = 256, key: str = 'mel_post', device=None, window=None,
                       **callbacks) -> Optional[List[Optional[torch.Tensor]]]:
     """gen_forward.py's loop, batched and sharded: bucket, run ``model.generate`` on this rank's batches, cut every
     row at its own frame count (``mel_len``) and gather on rank 0.  ``model`` is a ForwardTacotron / FastPitch
-    mirror already on its device."""
+    mirror already on its device.
+
+    ``window`` (utils/peer_window.PeerWindow): instead of the NCCL gather, every rank's last GEMM stores ``mel_post``
+    directly into rank 0's memory over NVLink; rank 0 slices views out of the window (ForwardTacotron only)."""
     import torch.distributed as dist
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     device = device or next(model.parameters()).device
     mels: List[torch.Tensor] = []
     index: List[int] = []
+    if window is not None:
+        return _synthesize_into_window(model, utterances, alpha, max_tokens, max_batch, device, window, rank, world,
+                                       callbacks)
     for b in shard_for_rank(bucket_by_length(utterances, max_tokens, max_batch), rank, world):
         out = model.generate(b.tokens.to(device), alpha, **callbacks)
         lens = out['mel_len'].tolist()
@@ -140,3 +146,32 @@ def synthesize_corpus(model, utterances: Sequence[Sequence[int]], alpha: float =
             mels.append(out[key][r, :, :lens[r]])
             index.append(i)
     return gather_mels(mels, index, len(utterances))
+
+
+def _synthesize_into_window(model, utterances, alpha, max_tokens, max_batch, device, window, rank, world, callbacks):
+    import torch.distributed as dist
+    batches = bucket_by_length(utterances, max_tokens, max_batch)
+    mine = shard_for_rank(batches, rank, world)
+    steps = torch.tensor([len(mine)], dtype=torch.long, device=device)
+    dist.all_reduce(steps, op=dist.ReduceOp.MAX)
+    window.reset()
+    meta = []  # per produced slot on this rank: (utterance indices, frame counts)
+    for k in range(int(steps)):
+        if k < len(mine):
+            out = model.generate(mine[k].tokens.to(device), alpha, mel_post_alloc=window.alloc, **callbacks)
+            meta.append((mine[k].index.tolist(), out['mel_len'].tolist()))
+        else:
+            window.alloc(0, 0, 0)  # keep the collective call sequence aligned
+    metas = [None] * world
+    dist.all_gather_object(metas, meta)
+    slots = window.collect()
+    if slots is None:
+        return None
+    out = [None] * len(utterances)
+    seen = [0] * world
+    for r, t in slots:
+        idx, lens = metas[r][seen[r]]
+        seen[r] += 1
+        for row, (i, L) in enumerate(zip(idx, lens)):
+            out[i] = t[row, :, :L]
+    return out

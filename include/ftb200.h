@@ -69,6 +69,16 @@ int ftb_profile_families(void);
 const char* ftb_profile_family_name(int family);
 int ftb_profile_enable(int on);
 int ftb_profile_collect(double* ms, double* flops, double* bytes, long long* launches);
+/* Enables kernels on `device` to load / store memory resident on `peer` (one node, NVLink / NVSwitch).  The output
+ * pointers of every entry point may then point into a peer GPU: a sharded run lets the last epilogue store its result
+ * directly into the collecting rank's buffer (no separate gather pass). */
+int ftb_enable_peer_access(int device, int peer);
+/* Peer-mapped result window of a sharded run: the collecting rank allocates and exports a CUDA IPC handle (64 bytes,
+ * to be sent to the other processes of the node by any means), the others import it with their own device current and
+ * pass pointers into it as output arguments.  ftb_ipc_release: owner != 0 frees, otherwise un-maps. */
+int ftb_ipc_alloc(int64_t bytes, int device, void** dev_ptr, unsigned char* handle64);
+int ftb_ipc_open(const unsigned char* handle64, int device, void** dev_ptr);
+int ftb_ipc_release(void* dev_ptr, int owner);
 /* Number of SMs / compute capability of `device`; fails on anything but sm_100. */
 int ftb_device_check(int device, int* sm_count, int* cc_major, int* cc_minor);
 
