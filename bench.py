@@ -213,6 +213,37 @@ def fastpitch_extra(torch, dev):
                         'LayerNorm; duration predictor fp32 (DESIGN.md 2)'}
 
 
+def gather_extra(torch, dist, model, dev, world):
+    """N > 1 only: the path's one exchange step, both ways.  A corpus of 96 x world utterances is
+    bucketed, sharded, synthesised and collected on rank 0 with (a) the NCCL gather, (b) the peer window the last
+    GEMM's epilogue stores into directly.  Wall clock incl. host bucketing, max over ranks."""
+    from forwardtacotron_b200.utils import batching
+    from forwardtacotron_b200.utils.peer_window import PeerWindow
+    g = torch.Generator().manual_seed(3)
+    n = 96 * world
+    utts = [torch.randint(1, 135, (int(k),), generator=g).tolist() for k in torch.randint(40, 200, (n,), generator=g)]
+    window = PeerWindow(4 << 30)
+    res = {}
+    for mode in ('nccl', 'peer_window', 'nccl', 'peer_window'):   # first pair = warm-up
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        t0 = time.perf_counter()
+        out = batching.synthesize_corpus(model, utts, max_tokens=8192, window=window if mode == 'peer_window' else None)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        res[mode] = time.perf_counter() - t0
+        if out is not None:
+            frames = sum(int(m.shape[1]) for m in out)
+    t = torch.tensor([res['nccl'], res['peer_window']], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    window.close()
+    if dist.get_rank() != 0:
+        return None
+    return {'utterances': n, 'frames': frames, 'nccl_gather_ms': float(t[0]) * 1e3, 'peer_window_ms': float(t[1]) * 1e3,
+            'note': 'whole sharded corpus run (bucket, generate, collect on rank 0); peer window = post_proj epilogue '
+                    'stores into rank 0 HBM over NVLink, no gather pass'}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -311,6 +342,12 @@ def run_ours(args):
     else:
         frames_all = float(frames_per_step)
 
+    gather = None
+    if world > 1 and not args.no_extras:
+        try:
+            gather = gather_extra(torch, dist, model, dev, world)
+        except Exception as e:  # the headline line must still be printed
+            gather = {'error': str(e)}
     if rank == 0:
         value = frames_all * args.steps / (ms_total / 1e3)
         e2e_value = frames_all * args.steps / (e2e_ms / 1e3)
@@ -334,6 +371,8 @@ def run_ours(args):
             'kernels_note': f'share = fraction of the serialised step ({serial_ms:.3f} ms kernel time); the timed step '
                             'overlaps stage A and the prenet on side streams',
         }
+        if gather is not None:
+            line.setdefault('extra', {})['final_gather'] = gather
         if world == 1 and not args.no_extras:
             try:
                 line['extra'] = {'stft_mel': stft_extra(torch, dev, pk)}
