@@ -154,7 +154,7 @@ class FastPitch(NativeModel):
                                           _lib.ptr(energy), _lib.ptr(ws), ws.numel(), _lib.current_stream(dev)))
         return dur, pitch, energy
 
-    def synthesize(self, x, dur_hat, pitch_hat, energy_hat) -> Dict[str, torch.Tensor]:
+    def synthesize(self, x, dur_hat, pitch_hat, energy_hat, mel_post_alloc=None) -> Dict[str, torch.Tensor]:
         x = self._check_tokens(x)
         lib, dev = _lib.lib(), x.device
         B, T = x.shape
@@ -169,7 +169,12 @@ class FastPitch(NativeModel):
             raise RuntimeError('all rounded durations are zero: nothing to synthesize')
         self._check_len(L)
         ws = self._workspace_for(h, B, T, L, dev)
-        mel = torch.empty((B, self._dims['n_mels'], L), dtype=torch.float32, device=dev)
+        # optional caller-supplied output memory (may be peer-mapped, utils/peer_window.py), as in ForwardTacotron
+        mel = torch.empty((B, self._dims['n_mels'], L), dtype=torch.float32, device=dev) if mel_post_alloc is None \
+            else mel_post_alloc(B, self._dims['n_mels'], L)
+        if not (mel.is_cuda and mel.dtype == torch.float32 and mel.is_contiguous()
+                and tuple(mel.shape) == (B, self._dims['n_mels'], L)):
+            raise TypeError('mel_post_alloc must return a contiguous float32 CUDA tensor of shape (B, n_mels, L)')
         with torch.cuda.device(dev):
             _lib.check(lib.ftb_fp_synthesize(h, _lib.ptr(x), _lib.ptr(cum), _lib.ptr(pitch_c), _lib.ptr(energy_c),
                                              B, T, L, _lib.ptr(mel), _lib.ptr(ws), ws.numel(),
@@ -179,13 +184,14 @@ class FastPitch(NativeModel):
 
     def generate(self, x: torch.Tensor, alpha=1.0,
                  pitch_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x,
-                 energy_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x) -> Dict[str, torch.Tensor]:
+                 energy_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x,
+                 mel_post_alloc=None) -> Dict[str, torch.Tensor]:
         self.eval()
         with torch.no_grad():
             dur_hat, pitch_hat, energy_hat = self.predict(x, alpha)
             pitch_hat = pitch_function(pitch_hat)
             energy_hat = energy_function(energy_hat)
-            return self.synthesize(x, dur_hat, pitch_hat, energy_hat)
+            return self.synthesize(x, dur_hat, pitch_hat, energy_hat, mel_post_alloc)
 
     def last_launch_count(self) -> int:
         return int(_lib.lib().ftb_fp_last_launch_count(self._handle)) if self._handle is not None else 0

@@ -129,7 +129,7 @@ def synthesize_corpus(model, utterances: Sequence[Sequence[int]], alpha: float =
     mirror already on its device.
 
     ``window`` (utils/peer_window.PeerWindow): instead of the NCCL gather, every rank's last GEMM stores ``mel_post``
-    directly into rank 0's memory over NVLink; rank 0 slices views out of the window (ForwardTacotron only)."""
+    directly into rank 0's memory over NVLink; rank 0 slices views out of the window."""
     import torch.distributed as dist
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
