@@ -78,3 +78,28 @@ def test_unsupported_fft_size_is_an_error():
     cfg['dsp']['n_fft'] = 2048
     with pytest.raises(Exception, match='1024'):
         DSP.from_config(cfg).wav_to_mel(np.zeros(4096, np.float32))
+
+
+def test_featurize_folder_of_wavs(tmp_path):
+    """preprocess.py's wav -> mel/{id}.npy step, batched on the GPU, against the numpy oracle (row f-2)."""
+    from scipy.io import wavfile
+    from forwardtacotron_b200 import preprocess
+    from forwardtacotron_b200.utils.config import default_config
+    from forwardtacotron_b200.utils.dsp import DSP
+    from oracle import dsp_oracle
+    rng = np.random.default_rng(3)
+    wavs = {}
+    for i, n in enumerate([22050, 30001, 4096]):
+        y = (0.3 * rng.standard_normal(n)).astype(np.float32)
+        if i == 1:
+            y *= 5.0                                     # exceeds full scale -> peak scaling kicks in (preprocess.py:72)
+        wavfile.write(str(tmp_path / f'clip{i}.wav'), 22050, y)
+        wavs[f'clip{i}'] = y
+    dsp = DSP.from_config(default_config())
+    done = preprocess.featurize(sorted(tmp_path.glob('*.wav')), dsp, tmp_path / 'data')
+    assert [d[0] for d in done] == ['clip0', 'clip1', 'clip2']
+    for name, y in wavs.items():
+        got = np.load(tmp_path / 'data' / 'mel' / f'{name}.npy')
+        want = dsp_oracle.wav_to_mel(preprocess.peak_scale(y, False))
+        assert got.dtype == np.float32 and got.shape == want.shape == (80, 1 + len(y) // 256)
+        assert np.abs(got - want).max() < 1e-2 and np.abs(got - want).mean() < 1e-3
