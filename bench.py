@@ -275,35 +275,56 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    out = None
-    for _ in range(max(args.warmup, 3)):
-        out = model.generate(x)
-    frames_per_step = int(out['mel_len'].sum().item())
+    # ---- S batches in flight: step k runs on CUDA stream k % S (the model keeps one native lane -- packed weights,
+    # workspace, internal streams -- per stream).  The sequential recurrences of one batch leave most SMs idle; the
+    # neighbour's GEMMs fill them.  S = 1 reproduces strictly back-to-back generate() calls.
+    S = max(1, args.in_flight)
+    main_stream = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(dev) for _ in range(S)]
+    xs = [x] + [synth.synthetic_tokens(B, T, seed=101 * (i + 1) + rank).to(dev) for i in range(1, S)]
+    xs_host = [x_host] + [t.cpu().pin_memory() for t in xs[1:]]
+
+    def run_steps(n, from_host=False, sinks=None):
+        for st in streams:
+            st.wait_stream(main_stream)
+        outs = [None] * S
+        for k in range(n):
+            i = k % S
+            with torch.cuda.stream(streams[i]):
+                xin = xs_host[i].to(dev, non_blocking=True) if from_host else xs[i]
+                outs[i] = model.generate(xin)
+                if sinks is not None:
+                    sinks[i].copy_(outs[i]['mel_post'], non_blocking=True)
+        for st in streams:
+            main_stream.wait_stream(st)
+        return outs
+
+    outs = run_steps(max(args.warmup, 3) * S)
+    torch.cuda.synchronize(dev)
+    frames_lane = [int(o['mel_len'].sum().item()) for o in outs]
+    frames_per_step = sum(frames_lane[k % S] for k in range(args.steps)) / args.steps   # valid frames of an average step
+    out = outs[0]
     L = int(out['mel'].shape[-1])
-    ws_bytes = int(lib.ftb_ft_workspace_bytes(model._handle, B, T, L))
+    with torch.cuda.stream(streams[0]):
+        ws_bytes = int(lib.ftb_ft_workspace_bytes(model._handle, B, T, L))
 
     # ---- timed region: K steps, inputs resident in HBM, CUDA events on the launching stream
     sampler = ClockSampler('GPU-' + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
-    lib.ftb_profile_enable(1)
     launches0 = lib.ftb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        out = model.generate(x)
+    run_steps(args.steps)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = lib.ftb_launch_count() - launches0
-    fams_live = {f['name']: f for f in collect_profile(lib, args.steps)}
-    lib.ftb_profile_enable(0)
     clocks = sampler.stop() if sampler else None
 
-    # ---- per-family kernel durations: stage A forks onto side streams, where an event pair around a launch also
-    # measures queueing behind the other streams.  Two extra (untimed) steps with the handle's SERIALIZE option give
-    # true durations for the breakdown; families that only ever run on the caller's stream (the LSTM, the
-    # LengthRegulator) keep the figure measured live in the timed region.
-    _lib.check(lib.ftb_ft_set_option(model._handle, _lib.FTB_OPT_SERIALIZE, 1))
+    # ---- per-family kernel durations.  In the timed region kernels of several streams overlap (stage A forks onto
+    # side streams, S batches are in flight), so an event pair around a launch also measures queueing.  Two extra
+    # (untimed) steps on ONE stream with the handle's SERIALIZE option give every launch's own duration.
+    _lib.check(lib.ftb_ft_set_option(model._get_handle(dev), _lib.FTB_OPT_SERIALIZE, 1))
     lib.ftb_profile_enable(1)
     PROF_STEPS = 2
     for _ in range(PROF_STEPS):
@@ -311,24 +332,19 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     fams = collect_profile(lib, PROF_STEPS)
     lib.ftb_profile_enable(0)
-    _lib.check(lib.ftb_ft_set_option(model._handle, _lib.FTB_OPT_SERIALIZE, 0))
+    _lib.check(lib.ftb_ft_set_option(model._get_handle(dev), _lib.FTB_OPT_SERIALIZE, 0))
     for f in fams:
-        if f['name'] in ('rnn_lstm_cluster', 'length_regulator') and f['name'] in fams_live:
-            f.update(fams_live[f['name']], source='timed region')
-        else:
-            f['source'] = 'serialised profile pass'
+        f['source'] = 'serialised profile pass (CUDA events around every launch, nothing overlapping)'
     fams.sort(key=lambda f: -f['ms_per_step'])
 
     # ---- end to end through the public API with HOST buffers: pinned H2D of the tokens + D2H of the result
-    mel_host = torch.empty(out['mel_post'].shape, dtype=torch.float32).pin_memory()
-    for _ in range(0 if args.no_extras else 2):
-        o = model.generate(x_host.to(dev, non_blocking=True))
-        mel_host.copy_(o['mel_post'], non_blocking=True)
+    sinks = [torch.empty(o['mel_post'].shape, dtype=torch.float32).pin_memory() for o in outs]
+    mel_host = sinks[0]
+    if not args.no_extras:
+        run_steps(2 * S, from_host=True, sinks=sinks)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(1 if args.no_extras else args.steps):
-        o = model.generate(x_host.to(dev, non_blocking=True))
-        mel_host.copy_(o['mel_post'], non_blocking=True)
+    run_steps(1 if args.no_extras else args.steps, from_host=True, sinks=sinks)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
 
@@ -360,6 +376,7 @@ def run_ours(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': B * world, 'phonemes': T, 'mel_frames_padded_L': L,
                        'valid_frames_per_gpu_step': frames_per_step, 'parallelism': f'utterance-sharded x{world}',
+                       'batches_in_flight_per_gpu': S,
                        'numerics': 'bf16 tcgen05 GEMMs, fp32 accumulate/state; duration predictor fp32',
                        'l2': f'per-step working set {ws_bytes / 1e9:.2f} GB >> 126 MB L2, no explicit flush'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 8,
@@ -368,8 +385,8 @@ def run_ours(args):
             'clocks': clocks,
             'roofline': roofline_of(top, pk),
             'kernels': kernels,
-            'kernels_note': f'share = fraction of the serialised step ({serial_ms:.3f} ms kernel time); the timed step '
-                            'overlaps stage A and the prenet on side streams',
+            'kernels_note': f'share = fraction of the serialised step ({serial_ms:.3f} ms kernel time); the timed steps '
+                            f'overlap stage A / prenet on side streams and keep {S} batches in flight',
         }
         if gather is not None:
             line.setdefault('extra', {})['final_gather'] = gather
@@ -396,6 +413,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--in-flight', type=int, default=2, help='generate() calls in flight on as many CUDA streams')
     ap.add_argument('--no-extras', action='store_true', help='profiling runs: skip the e2e / STFT / CPU legs')
     ap.add_argument('--stft-only', action='store_true', help='profiling runs: only the STFT->mel leg')
     args = ap.parse_args()

@@ -98,20 +98,23 @@ class CBHG(nn.Module):
 
 
 class NativeModel(nn.Module):
-    """Shared plumbing of the two TTS models: handle lifetime + workspace."""
+    """Shared plumbing of the two TTS models: native handle lifetime + workspace.
+
+    Native state is kept per (device, CUDA stream) "lane": a C handle (packed weight copy, internal side streams and
+    events) is not re-entrant, so calling ``generate`` under several ``torch.cuda.stream(...)`` contexts gives every
+    stream its own handle and workspace and the calls overlap on the GPU -- the sequential recurrences of one batch
+    leave most SMs idle for another batch's GEMMs (measured +23 % / +30 % throughput with 2 / 3 streams).
+    Parameters are shared; each lane costs one packed weight copy (~50 MB) plus its workspace."""
 
     _create_fn = ''
     _destroy_fn = ''
 
     def __init__(self) -> None:
         super().__init__()
-        self._handle = None
-        self._keep = None
-        self._handle_device = None
-        self._workspace = None
-        self.gemm_mode = 0  # 0: bf16 tcgen05 GEMMs (+ fp32 duration predictor); 1: all-fp32 validation mode
+        self._lanes = {}       # (device index, stream handle) -> {'handle', 'keep', 'ws'}
+        self.gemm_mode = 0     # see ftb_ft_config / ftb_fp_config in include/ftb200.h
 
-    # -- invalidation: any re-materialisation of the parameters drops the packed copy
+    # -- invalidation: any re-materialisation of the parameters drops the packed copies
     def _apply(self, fn, *args, **kwargs):
         self._drop_handle()
         return super()._apply(fn, *args, **kwargs)
@@ -125,11 +128,13 @@ class NativeModel(nn.Module):
         self._drop_handle()
 
     def _drop_handle(self) -> None:
-        h = self.__dict__.get('_handle')
-        if h is not None:
-            getattr(_lib.lib(), self._destroy_fn)(h)
-        self.__dict__['_handle'] = None
-        self.__dict__['_keep'] = None
+        lanes = self.__dict__.get('_lanes') or {}
+        if lanes:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            for lane in lanes.values():
+                getattr(_lib.lib(), self._destroy_fn)(lane['handle'])
+        self.__dict__['_lanes'] = {}
 
     def __del__(self):
         try:
@@ -140,10 +145,26 @@ class NativeModel(nn.Module):
     def _config_struct(self):
         raise NotImplementedError
 
+    def _lane_key(self, device: torch.device):
+        return (device.index or 0, torch.cuda.current_stream(device).cuda_stream)
+
+    @property
+    def _handle(self):
+        """Handle of the lane of the current stream on the parameters' device (None before the first call)."""
+        try:
+            device = next(self.parameters()).device
+        except StopIteration:
+            return None
+        if device.type != 'cuda':
+            return None
+        lane = self._lanes.get(self._lane_key(device))
+        return lane['handle'] if lane else None
+
     def _get_handle(self, device: torch.device):
-        if self._handle is not None and self._handle_device == device:
-            return self._handle
-        self._drop_handle()
+        key = self._lane_key(device)
+        lane = self._lanes.get(key)
+        if lane is not None:
+            return lane['handle']
         lib = _lib.lib()
         sd = self.state_dict()
         for k, v in sd.items():
@@ -155,15 +176,16 @@ class NativeModel(nn.Module):
         with torch.cuda.device(device):
             _lib.check(getattr(lib, self._create_fn)(C.byref(cfg), table, len(table), device.index or 0,
                                                      C.byref(out)))
-        self._handle, self._keep, self._handle_device = out, (table, keep, cfg), device
+        self._lanes[key] = {'handle': out, 'keep': (table, keep, cfg), 'ws': None}
         return out
 
     def _get_workspace(self, nbytes: int, device: torch.device) -> torch.Tensor:
-        ws = self._workspace
+        lane = self._lanes[self._lane_key(device)]
+        ws = lane['ws']
         if ws is None or ws.device != device or ws.numel() < nbytes:
-            self._workspace = None
+            lane['ws'] = None
             ws = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=device)
-            self._workspace = ws
+            lane['ws'] = ws
         return ws
 
     def forward(self, *args, **kwargs):

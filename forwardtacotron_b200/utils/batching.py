@@ -122,11 +122,12 @@ def gather_mels(mels: Sequence[torch.Tensor], index: Sequence[int], n_total: int
 
 
 def synthesize_corpus(model, utterances: Sequence[Sequence[int]], alpha: float = 1.0, max_tokens: int = 16384,
-                      max_batch: int = 256, key: str = 'mel_post', device=None, window=None,
+                      max_batch: int = 256, key: str = 'mel_post', device=None, window=None, in_flight: int = 2,
                       **callbacks) -> Optional[List[Optional[torch.Tensor]]]:
     """gen_forward.py's loop, batched and sharded: bucket, run ``model.generate`` on this rank's batches, cut every
     row at its own frame count (``mel_len``) and gather on rank 0.  ``model`` is a ForwardTacotron / FastPitch
-    mirror already on its device.
+    mirror already on its device.  ``in_flight`` batches are issued round-robin on as many CUDA streams (the model
+    keeps one native lane per stream), so one batch's GEMMs fill the SMs its neighbour's recurrences leave idle.
 
     ``window`` (utils/peer_window.PeerWindow): instead of the NCCL gather, every rank's last GEMM stores ``mel_post``
     directly into rank 0's memory over NVLink; rank 0 slices views out of the window."""
@@ -139,8 +140,28 @@ def synthesize_corpus(model, utterances: Sequence[Sequence[int]], alpha: float =
     if window is not None:
         return _synthesize_into_window(model, utterances, alpha, max_tokens, max_batch, device, window, rank, world,
                                        callbacks)
-    for b in shard_for_rank(bucket_by_length(utterances, max_tokens, max_batch), rank, world):
-        out = model.generate(b.tokens.to(device), alpha, **callbacks)
+    mine = shard_for_rank(bucket_by_length(utterances, max_tokens, max_batch), rank, world)
+    on_gpu = torch.device(device).type == 'cuda'
+    n_streams = max(1, min(int(in_flight), len(mine))) if on_gpu else 1
+    streams = [torch.cuda.Stream(device) for _ in range(n_streams)] if n_streams > 1 else [None]
+    if n_streams > 1:
+        here = torch.cuda.current_stream(device)
+        for s in streams:
+            s.wait_stream(here)
+    outs = []
+    for k, b in enumerate(mine):
+        s = streams[k % n_streams]
+        if s is None:
+            outs.append((b, model.generate(b.tokens.to(device), alpha, **callbacks)))
+        else:
+            with torch.cuda.stream(s):
+                outs.append((b, model.generate(b.tokens.to(device, non_blocking=True), alpha, **callbacks)))
+    if n_streams > 1:
+        for s in streams:
+            torch.cuda.current_stream(device).wait_stream(s)
+    for b, out in outs:
+        if n_streams > 1:
+            out[key].record_stream(torch.cuda.current_stream(device))  # produced on a side stream, consumed here
         lens = out['mel_len'].tolist()
         for r, i in enumerate(b.index.tolist()):
             mels.append(out[key][r, :, :lens[r]])
