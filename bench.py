@@ -413,7 +413,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--in-flight', type=int, default=2, help='generate() calls in flight on as many CUDA streams')
+    ap.add_argument('--in-flight', type=int, default=3, help='generate() calls in flight on as many CUDA streams')
     ap.add_argument('--no-extras', action='store_true', help='profiling runs: skip the e2e / STFT / CPU legs')
     ap.add_argument('--stft-only', action='store_true', help='profiling runs: only the STFT->mel leg')
     args = ap.parse_args()

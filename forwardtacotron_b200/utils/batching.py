@@ -122,7 +122,7 @@ def gather_mels(mels: Sequence[torch.Tensor], index: Sequence[int], n_total: int
 
 
 def synthesize_corpus(model, utterances: Sequence[Sequence[int]], alpha: float = 1.0, max_tokens: int = 16384,
-                      max_batch: int = 256, key: str = 'mel_post', device=None, window=None, in_flight: int = 2,
+                      max_batch: int = 256, key: str = 'mel_post', device=None, window=None, in_flight: int = 3,
                       **callbacks) -> Optional[List[Optional[torch.Tensor]]]:
     """gen_forward.py's loop, batched and sharded: bucket, run ``model.generate`` on this rank's batches, cut every
     row at its own frame count (``mel_len``) and gather on rank 0.  ``model`` is a ForwardTacotron / FastPitch
