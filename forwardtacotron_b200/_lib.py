@@ -16,6 +16,7 @@ _LIB_PATH = Path(__file__).resolve().parent / 'csrc' / 'libftb200.so'
 FTB_F32, FTB_I64, FTB_BF16, FTB_I32 = 0, 1, 2, 3
 FTB_OPT_OVERLAP_PRENET = 1
 FTB_OPT_SERIALIZE = 2
+FTB_TUNE_LSTM_MIN_CHUNK = 1
 
 
 class FtbError(RuntimeError):
@@ -79,6 +80,7 @@ SIGNATURES = {
     'ftb_ipc_alloc': (_I, [_L, _I, C.POINTER(_P), _P]),
     'ftb_ipc_open': (_I, [_P, _I, C.POINTER(_P)]),
     'ftb_ipc_release': (_I, [_P, _I]),
+    'ftb_tune': (_I, [_I, _I]),
     'ftb_device_check': (_I, [_I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     'ftb_length_plan': (_I, [_P, _P, _P, _I, _I, _P]),
     'ftb_length_expand': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),

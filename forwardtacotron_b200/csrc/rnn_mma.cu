@@ -20,6 +20,8 @@
 // 128 x 512 tile by a <= 32-column operand and is bound by latency, not MMA throughput.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;

@@ -20,6 +20,9 @@
 // received this CTA's h_t, i.e. after this CTA's MMA finished reading h_{t-1}.
 #include <cooperative_groups.h>
 
+#include <atomic>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -451,6 +454,11 @@ static int launch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, 
 // Utterances per cluster: the smallest chunk whose cluster count still fits on the GPU in ONE wave (the
 // clusters are independent, so a second wave would double the latency of the whole recurrence).  Fewer
 // utterances per cluster = fewer gate-maths pairs per thread and fewer bytes per hand-off.
+// FTB_TUNE_LSTM_MIN_CHUNK: smallest utterance chunk per cluster.  8 (default) = lowest latency of a single call: as
+// many clusters as fit in one wave.  32 = throughput mode for several batches in flight: 4 instead of 6 clusters hold
+// 64 instead of 96 SMs for the whole recurrence (one call +12 %, three streams -9 % per step).
+static std::atomic<int> g_lstm_min_chunk{getenv("FTB_LSTM_MIN_CHUNK") ? atoi(getenv("FTB_LSTM_MIN_CHUNK")) : 8};
+
 template <int G, int H, int CL>
 static int dispatch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
                            cudaStream_t s) {
@@ -461,7 +469,8 @@ static int dispatch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn
   // 8 utterances: only the first column group of a 16-wide MMA carries data, 1 pair per gate thread
   if (2 * cdiv(B, 8) <= m8) return launch_rnn_tc<G, H, CL, 16, 4, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, 8, s, nullptr);
   if (2 * cdiv(B, 16) <= m16) return launch_rnn_tc<G, H, CL, 16, 8, 16>(xg, w_hh, b_hn, out, B, S, out_bf16, 16, s, nullptr);
-  if (2 * cdiv(B, 24) <= m32) return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 24, s, nullptr);
+  const int min_chunk = g_lstm_min_chunk.load(std::memory_order_relaxed);
+  if (min_chunk <= 24 && 2 * cdiv(B, 24) <= m32) return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 24, s, nullptr);
   return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 32, s, nullptr);
 }
 
@@ -477,6 +486,15 @@ int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out
 }
 
 }  // namespace ftb
+
+extern "C" int ftb_tune(int key, int value) {
+  if (key == FTB_TUNE_LSTM_MIN_CHUNK && value >= 8 && value <= 32) {
+    ftb::g_lstm_min_chunk.store(value);
+    return FTB_OK;
+  }
+  ftb::set_error("ftb_tune: unknown key %d / bad value %d", key, value);
+  return FTB_ERR_INVALID;
+}
 
 // developer hook (not part of include/ftb200.h): device buffer of 64*8 int64 clock stamps, or NULL to switch off
 extern "C" int ftb_debug_rnn_timing(long long* device_buf) {

@@ -177,6 +177,10 @@ class NativeModel(nn.Module):
             _lib.check(getattr(lib, self._create_fn)(C.byref(cfg), table, len(table), device.index or 0,
                                                      C.byref(out)))
         self._lanes[key] = {'handle': out, 'keep': (table, keep, cfg), 'ws': None}
+        if len(self._lanes) == 2:
+            # a second stream means batches in flight: trade a little single-call latency of the decoder LSTM for
+            # fewer SMs held during its recurrence (include/ftb200.h, FTB_TUNE_LSTM_MIN_CHUNK)
+            _lib.check(lib.ftb_tune(_lib.FTB_TUNE_LSTM_MIN_CHUNK, 32))
         return out
 
     def _get_workspace(self, nbytes: int, device: torch.device) -> torch.Tensor:

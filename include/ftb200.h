@@ -79,6 +79,11 @@ int ftb_enable_peer_access(int device, int peer);
 int ftb_ipc_alloc(int64_t bytes, int device, void** dev_ptr, unsigned char* handle64);
 int ftb_ipc_open(const unsigned char* handle64, int device, void** dev_ptr);
 int ftb_ipc_release(void* dev_ptr, int owner);
+/* Process-wide tuning.  FTB_TUNE_LSTM_MIN_CHUNK (8..32, default 8): smallest number of utterances a decoder-LSTM
+ * cluster takes.  8 = lowest latency of one call (as many clusters as fit in a wave); 32 = throughput mode for
+ * several generate() calls in flight on different streams (fewer SMs pinned by the latency-bound recurrence). */
+#define FTB_TUNE_LSTM_MIN_CHUNK 1
+int ftb_tune(int key, int value);
 /* Number of SMs / compute capability of `device`; fails on anything but sm_100. */
 int ftb_device_check(int device, int* sm_count, int* cc_major, int* cc_minor);
 
