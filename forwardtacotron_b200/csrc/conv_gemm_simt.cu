@@ -24,7 +24,7 @@ struct SimtConvArgs {
   EpiParams epi;
 };
 
-__global__ void __launch_bounds__(simt::THREADS) conv_gemm_f32_kernel(const SimtConvArgs a) {
+__global__ void __launch_bounds__(simt::THREADS, 3) conv_gemm_f32_kernel(const SimtConvArgs a) {
   using namespace simt;
   __shared__ float As[BK][A_LD];
   __shared__ float Ws[BK][W_LD];
