@@ -159,3 +159,24 @@ def test_odd_shapes_against_oracle(B, T):
     want = mo.ft_generate(cpu_state_dict(model), x)
     out, res = check_against(model, x, want)
     assert out['mel'].shape == want['mel'].shape
+
+
+def test_concurrent_streams_match_single_stream():
+    """generate() under different torch streams uses one native lane per stream; results are bit-identical to the
+    single-stream run (same kernels; the LSTM's throughput-mode chunking does not change the arithmetic)."""
+    model, _ = cuda_model('forward_tacotron', 0)
+    xs = [synth.synthetic_tokens(6, 50 + 7 * i, seed=20 + i).cuda() for i in range(3)]
+    ref = [model.generate(x) for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in xs]
+    outs = [None] * len(xs)
+    for rep in range(2):
+        for i, (x, st) in enumerate(zip(xs, streams)):
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                outs[i] = model.generate(x)
+    torch.cuda.synchronize()
+    assert len(model._lanes) == 4
+    for a, b in zip(ref, outs):
+        for k in ('mel', 'mel_post', 'dur', 'mel_len'):
+            assert torch.equal(a[k], b[k]), k
