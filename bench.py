@@ -359,7 +359,7 @@ def run_ours(args):
         frames_all = float(frames_per_step)
 
     gather = None
-    if world > 1 and not args.no_extras:
+    if world > 1 and args.gather_extra:  # opt-in: a collective extra must never be able to cost the headline line
         try:
             gather = gather_extra(torch, dist, model, dev, world)
         except Exception as e:  # the headline line must still be printed
@@ -414,6 +414,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--in-flight', type=int, default=3, help='generate() calls in flight on as many CUDA streams')
+    ap.add_argument('--gather-extra', action='store_true', help='N > 1: also time the final gather both ways')
     ap.add_argument('--no-extras', action='store_true', help='profiling runs: skip the e2e / STFT / CPU legs')
     ap.add_argument('--stft-only', action='store_true', help='profiling runs: only the STFT->mel leg')
     args = ap.parse_args()
