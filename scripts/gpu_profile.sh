@@ -1,19 +1,27 @@
 #!/bin/bash
-# ncu evidence (1 GPU): full captures of the top kernels of one short bench run, each only after the plain run exits 0.
-# Output stays small (<64 MiB): one or two launches per capture.   usage: bash scripts/gpu_profile.sh [tag]
+# ncu evidence (1 GPU): launch list + full captures of the top kernels of one short bench run (single lane, the
+# launches of one generate() back to back), each only after the plain run exits 0.  Output stays small (<64 MiB).
+# usage: bash scripts/gpu_profile.sh [tag]
 set -u
 mkdir -p gpurun_out
-TAG=${1:-v2}
-CMD="python bench.py --steps 1 --warmup 3 --no-extras"
+TAG=${1:-v3}
+CMD="python bench.py --steps 1 --warmup 3 --no-extras --in-flight 1"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
+ncu --metrics gpu__time_duration.sum,launch__grid_size,sm__inst_executed_pipe_tensor.sum --clock-control none -c 4000 --csv \
+    --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
+echo "launch list rc=$?"
 cap() {  # name kernel-regex skip count
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -o gpurun_out/prof_$1_$TAG -f $CMD > gpurun_out/ncu_$1_$TAG.log 2>&1
   echo "$1 capture rc=$?"
 }
-# per generate: 25 conv_gemm_tc launches (8 stage A, 9 prenet, LSTM in-proj = #17, lin, postnet bank, proj1 = #20 ...)
+# per generate: 29 conv_gemm_tc launches: 8 stage A, 9 prenet (bank first), LSTM in-proj (#17), lin, 9 postnet (bank #19,
+# proj1 #20), post_proj; warm-up = 3 generates
 cap lstm rnn_tc_kernel 3 1
 cap gru rnn_cluster_kernel 7 1
-cap gemm conv_gemm_tc_kernel 92 4
+cap gemm conv_gemm_tc_kernel 104 4
+cap f32gemm conv_gemm_f32_kernel 13 1
 CMD="python bench.py --stft-only"
 $CMD > gpurun_out/plain_stft.log 2>&1 && cap stft stft_mel 3 1
+CMD="python scripts/fp_profile.py"
+$CMD > gpurun_out/plain_fp.log 2>&1 && cap attn attention_tc_kernel 30 1
 ls -la gpurun_out
