@@ -1,23 +1,20 @@
-// Bidirectional GRU (H=256: the two CBHG RNNs, models/common_layers.py:84,118) and LSTM (H=512: the
-// decoder, models/forward_tacotron.py:165-168,321) recurrences on tcgen05 with the recurrent weights
-// RESIDENT IN TENSOR MEMORY.
+// Decoder LSTM recurrence (H=512, bidirectional; models/forward_tacotron.py:165-168,321) on tcgen05.
+// (The kernel template also instantiates for the H=256 GRU; the CBHG GRUs run on rnn_mma.cu, see there.)
 //
-// One thread-block cluster owns (direction, chunk of <= 16*NSUB utterances) for all S steps.  The G*H rows
-// of W_hh are split over the CL CTAs of the cluster: CTA `rank` owns 32 hidden units = 128 gate rows
-// (row 4*u + gate; the 4th GRU row is zero), kept for the whole kernel as the bf16 A operand of
-// tcgen05.mma in TMEM (128 lanes x H/2 columns).  Per step and per sub-chunk of 16 utterances:
-//   control warp : waits until all CL slices of h_{t-1} have landed in this CTA's shared-memory
-//                  B-operand buffer, issues H/16 MMAs  D[128 x 16] = W_slice[128 x H] . h_{t-1}[H x 16]
-//                  (A from TMEM, B from smem, fp32 accumulator in TMEM) and commits to an mbarrier;
-//   8 gate warps : tcgen05.ld the accumulator (lane = gate row), regroup the 4 gates of a unit inside the
-//                  warp, fp32 gate maths with the input pre-activations prefetched one step ahead, write
-//                  h_t to global and, as bf16, into the own slice of the NEXT step's B buffer; then one
-//                  cp.async.bulk (shared::cta -> shared::cluster) per peer pushes that 512-byte slice into
-//                  the peer's buffer and completes bytes on the peer's mbarrier.
-// No cluster-wide barrier and no global-memory round trip on the sequential path.  With NSUB = 2 the two
-// sub-chunks are independent recurrences that alternate, so the DSMEM flight of one overlaps the maths
-// of the other.  Double-buffered h makes the hand-off hazard-free: a peer can only send h_{t+1} after it
-// received this CTA's h_t, i.e. after this CTA's MMA finished reading h_{t-1}.
+// One thread-block cluster of CL = 16 CTAs owns (direction, chunk of <= 32 utterances) for all S steps.  CTA `rank`
+// owns 32 hidden units = 128 gate rows of W_hh (row 4*u + gate), resident in shared memory for the whole kernel as
+// the SWIZZLE_128B A operand of tcgen05.mma.  Per step:
+//   1. every warp: wait for the accumulators (mbarrier fed by tcgen05.commit), tcgen05.ld its window, clear it,
+//      regroup the 4 gates of a unit inside the warp, fp32 gate maths with the input pre-activations prefetched one
+//      step ahead, write h_t to global and -- as bf16 -- into the own 32-unit slice of the NEXT step's B operand;
+//   2. block barrier; one cp.async.bulk (shared::cta -> shared::cluster) per peer pushes that slice into the peer's
+//      B buffer and completes bytes on the peer's per-slice mbarrier (armed by the consumer);
+//   3. warps 0..7 are the MMA issuers of the next step: issuer a waits for ring slices a, a + 8 and issues their
+//      K = 32 worth of MMAs  D_a[128 x N] += W[:, slice] . h_t[slice, :]  into its OWN TMEM accumulator as soon as
+//      the slice has landed, so the MMAs overlap the remaining flights and every accumulator sees a fixed order.
+// No cluster-wide barrier and no global-memory round trip on the sequential path.  Double-buffered h makes the
+// hand-off hazard-free: a peer can only send h_{t+1} after it received this CTA's h_t, i.e. after this CTA's MMAs
+// finished reading h_{t-1}.
 #include <cooperative_groups.h>
 
 #include <atomic>
