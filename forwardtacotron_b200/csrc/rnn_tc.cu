@@ -153,8 +153,7 @@ struct RtCfg {
 // Every warp is gate warp AND MMA issuer.  Issuing one tcgen05.mma costs the issuing thread ~60-90 cycles however
 // small N is (measured, scripts/rnn_phase_timing.py), so the 2*CL MMAs of a step are issued by up to 16 threads in
 // parallel: warp w owns slices w, w + WARPS, ... (ring order from the own slice), waits for exactly those slices
-// to land and issues their two MMAs into accumulator (slice % KSPLIT).  All MMAs accumulate; the accumulators are
-// cleared by the warps right after they read them.
+// to land and issues their MMAs into its own accumulator (the first one of a step overwrites it).
 template <int G, int H, int CL, int NCOLS, int CW, int UC>
 __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
     rnn_tc_kernel(const float* __restrict__ xg,    // (B,S,2,G*H)
@@ -294,11 +293,6 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
                        : "=r"(r[a][i]), "=r"(r[a][i + 1]), "=r"(r[a][i + 2]), "=r"(r[a][i + 3])
                        : "r"(tacc + a * NCOLS + i));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-      for (int a = 0; a < KSPLIT; ++a)
-#pragma unroll
-        for (int i = 0; i < CW; i += 4) tmem_st4(tacc + a * NCOLS + i, z);  // cleared for the next step's MMAs
 #pragma unroll
       for (int i = 0; i < CW; ++i) {
         float v = __uint_as_float(r[0][i]);
@@ -359,7 +353,6 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
       for (int e = 0; e < PPT; ++e)
         if (ok[e]) *reinterpret_cast<__nv_bfloat16*>(hb_next + cell0 + e * 16) = __float2bfloat16_rn(hn[e]);
       RNN_STAMP(4);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");       // accumulator clear has landed
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic writes -> visible to UMMA / bulk copy
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("bar.sync 1, %0;" ::"r"(THREADS) : "memory");
@@ -392,10 +385,10 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < 2; ++j) {  // the issuer's first MMA of a step overwrites its accumulator
             const uint32_t ks = 2 * r + j;
             umma_ss_bf16(d_acc, adesc_sw128(wa0 + (ks >> 2) * 16384 + (ks & 3) * 32), bdesc_kmajor(hbn + r * C::SL + j * 256, 512),
-                         C::IDESC, 1u);
+                         C::IDESC, (i >= NISS || j > 0) ? 1u : 0u);
           }
         }
         umma_commit(dfull);
