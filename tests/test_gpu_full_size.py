@@ -1,0 +1,74 @@
+"""BASELINE.json's full-size configurations, checked through size-independent properties (the CPU oracle only runs
+the cheap parts at this size): cfg2 = ForwardTacotron 64 x 200, cfg3 = FastPitch 128 x 300."""
+import pytest
+import torch
+
+from oracle import model_oracle as mo
+
+from util import cpu_state_dict, cuda_model, near_tie_mask, rounded
+from forwardtacotron_b200.models.common_layers import LengthRegulator
+from forwardtacotron_b200.utils import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cfg2_forward_tacotron_64x200():
+    model, _ = cuda_model('forward_tacotron', 0)
+    x = synth.synthetic_tokens(64, 200, seed=1)
+    out = model.generate(x.cuda())
+    B, T = x.shape
+    # (1) durations: the fp32 predictor against the oracle's predictor (seconds on the CPU), integer-exact up to near-ties
+    sd = cpu_state_dict(model)
+    want = mo.ft_series_predictor(sd, 'dur_pred', x).squeeze(-1)
+    flips = rounded(out['dur']) != rounded(want)
+    assert bool((near_tie_mask(want) | ~flips).all()) and int(flips.sum()) <= 2
+    # (2) frame bookkeeping: per-row totals, padded length, cumulative sums
+    r = rounded(out['dur'])
+    assert torch.equal(out['mel_len'].cpu().long(), r.sum(1))
+    L = int(r.sum(1).max())
+    assert out['mel'].shape == (B, 80, L) and out['mel_post'].shape == (B, 80, L)
+    assert 1000 < L < 1600 and torch.isfinite(out['mel']).all() and torch.isfinite(out['mel_post']).all()
+    # (3) LengthRegulator at this size: frame j of row b is a copy of the phoneme whose cumulative range holds j
+    enc = torch.randn(B, T, 512, device='cuda')
+    up = LengthRegulator()(enc, out['dur'].clone())
+    cum = r.cumsum(1)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(200):
+        b = int(torch.randint(0, B, (1,), generator=g))
+        j = int(torch.randint(0, L, (1,), generator=g))
+        if j < int(cum[b, -1]):
+            t = int(torch.searchsorted(cum[b], torch.tensor(j), right=True))
+            assert torch.equal(up[b, j], enc[b, t])
+        else:
+            assert not up[b, j].any()                       # zero padding (common_layers.py:18)
+    # (4) run-to-run reproducibility at full size
+    again = model.generate(x.cuda())
+    assert torch.equal(again['mel_post'], out['mel_post']) and torch.equal(again['dur'], out['dur'])
+
+
+def test_cfg2_alpha_scales_durations():
+    """alpha divides the predicted durations (forward_tacotron.py:55): totals shrink / grow monotonically."""
+    model, _ = cuda_model('forward_tacotron', 0)
+    x = synth.synthetic_tokens(64, 200, seed=1).cuda()
+    tot = [int(model.generate(x, alpha=a)['mel_len'].sum()) for a in (0.8, 1.0, 1.2)]
+    assert tot[0] > tot[1] > tot[2]
+    assert abs(tot[0] / tot[1] - 1.25) < 0.05 and abs(tot[2] / tot[1] - 1 / 1.2) < 0.05
+
+
+def test_cfg3_fast_pitch_128x300():
+    model, _ = cuda_model('fast_pitch', 0)
+    x = synth.synthetic_tokens(128, 300, seed=5)
+    pf, ef = (lambda p: p * 1.2), (lambda e: e + 0.1)
+    out = model.generate(x.cuda(), pitch_function=pf, energy_function=ef)
+    r = rounded(out['dur'])
+    L = int(r.sum(1).max())
+    assert out['mel'].shape == (128, 80, L) and L < 5000 and out['mel_post'] is out['mel']
+    assert torch.equal(out['mel_len'].cpu().long(), r.sum(1)) and torch.isfinite(out['mel']).all()
+    # the callbacks really sit between the stages: pitch / energy returned are the transformed ones
+    base = model.generate(x.cuda())
+    assert torch.allclose(out['pitch'], base['pitch'] * 1.2) and torch.allclose(out['energy'], base['energy'] + 0.1)
+    assert not torch.equal(out['mel'], base['mel'])
+    # a row's valid frames do not depend on the other rows' padding: the postnet of FastPitch has no mask (reference
+    # semantics), so compare only the duration bookkeeping across a sub-batch
+    sub = model.generate(x[:16].cuda(), pitch_function=pf, energy_function=ef)
+    assert torch.equal(rounded(sub['dur']), r[:16])
