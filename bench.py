@@ -166,7 +166,8 @@ def stft_extra(torch, dev, pk):
     from forwardtacotron_b200.utils.config import default_config
     from forwardtacotron_b200.utils.dsp import DSP
     dsp = DSP.from_config(default_config())
-    audio, offs = synth.synthetic_audio(320, seed=7)          # ~42 M samples = 169 MB of fp32 > 126 MB L2
+    n_clips = 1250                                            # cfg4: 10 000 clips over 8 GPUs = 1 250 per GPU
+    audio, offs = synth.synthetic_audio(n_clips, seed=7)      # ~165 M samples = 660 MB of fp32 >> 126 MB L2
     a = audio.to(dev)
     for _ in range(3):
         out, fo = dsp.wav_to_mel_packed(a, offs)
@@ -182,7 +183,8 @@ def stft_extra(torch, dev, pk):
     secs = a.numel() / 22050.0
     nbytes = a.numel() * 4 + out.numel() * 4
     return {'metric': 'stft_mel_audio_seconds_per_s', 'value': secs / (ms / 1e3), 'unit': 'audio-s/s',
-            'ms_per_step': ms, 'clips': 320, 'audio_seconds': secs,
+            'ms_per_step': ms, 'clips': n_clips, 'audio_seconds': secs,
+            'workload': 'DSP.wav_to_mel, 22.05 kHz clips of 2-10 s (noise, sines, silence), n_fft 1024 / hop 256 / 80 mels',
             'roofline': {'kernel': 'stft_mel', 'bound': 'hbm', 'achieved': nbytes / (ms / 1e3) / 1e9,
                          'peak': pk['hbm'], 'unit': 'GB/s', 'frac': nbytes / (ms / 1e3) / 1e9 / pk['hbm'],
                          'note': 'includes the host-side offset upload of wav_to_mel_packed'}}
@@ -242,6 +244,29 @@ def gather_extra(torch, dist, model, dev, world):
     return {'utterances': n, 'frames': frames, 'nccl_gather_ms': float(t[0]) * 1e3, 'peer_window_ms': float(t[1]) * 1e3,
             'note': 'whole sharded corpus run (bucket, generate, collect on rank 0); peer window = post_proj epilogue '
                     'stores into rank 0 HBM over NVLink, no gather pass'}
+
+
+def long_article_extra(torch, dev):
+    """BASELINE.json configs[4] at 1/4 of its utterance count: ForwardTacotron on 64 x 2000-phoneme utterances,
+    length-bucketed into batches of 32 (utils/batching.synthesize_corpus, batches in flight on separate streams),
+    alpha sweep 0.8 / 1.0 / 1.2.  Wall clock including the host-side bucketing and the per-row slicing."""
+    from forwardtacotron_b200.utils import batching, synth
+    model, _ = synth.synthetic_model('forward_tacotron')
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(11)
+    utts = [torch.randint(1, 135, (int(n),), generator=g).tolist() for n in torch.randint(1900, 2001, (64,), generator=g)]
+    res = {}
+    batching.synthesize_corpus(model, utts[:32], max_tokens=65536, in_flight=2)   # warm-up: lanes, workspaces
+    torch.cuda.synchronize(dev)
+    for alpha in (0.8, 1.0, 1.2):
+        t0 = time.perf_counter()
+        mels = batching.synthesize_corpus(model, utts, alpha=alpha, max_tokens=65536, in_flight=2)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        frames = sum(int(m.shape[1]) for m in mels)
+        res[f'alpha_{alpha}'] = {'frames': frames, 'ms': dt * 1e3, 'frames_per_s': frames / dt}
+    return {'metric': 'mel_frames_per_s', 'unit': 'frames/s', 'utterances': 64, 'phonemes_per_utterance': '1900-2000',
+            'batching': 'length-bucketed, 32 utterances per batch, 2 batches in flight', **res}
 
 
 def run_ours(args):
@@ -399,6 +424,10 @@ def run_ours(args):
                 line['extra']['fast_pitch'] = fastpitch_extra(torch, dev)
             except Exception as e:
                 line['extra']['fast_pitch'] = {'error': str(e)}
+            try:
+                line['extra']['long_article'] = long_article_extra(torch, dev)
+            except Exception as e:
+                line['extra']['long_article'] = {'error': str(e)}
             cb, _ = cpu_generate_rate(3, 1)
             line['cpu_baseline'] = cb
         print(json.dumps(line), flush=True)
