@@ -123,6 +123,11 @@ __device__ __forceinline__ float tanh_mufu(float x) {
   return y;
 }
 __device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(tanh_mufu(0.5f * x), 0.5f, 0.5f); }
+// two floats -> one 32-bit word of IEEE halves (lo in the low 16 bits)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -360,13 +360,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
             const float x1 = __uint_as_float(r1[i]) + __ldg(P.bias + nb1 + i);
             const float x2 = __uint_as_float(r2[i]) + __ldg(P.bias + nb1 + 32 + i);
             const float g = __fdividef(1.f, 1.f + __expf(-x2));
-            stg[lane * STG_LD + i] = g * fmaxf(x1, 0.f) + (1.f - g) * __bfloat162float(xb[i]);
+            stg[lane * STG_LD + i] = g * fmaxf(x1, 0.f) + (1.f - g) * ld16(xb[i], a.fp16 != 0);
           }
           __syncwarp();
           __nv_bfloat16* o16 = a.out_bf16 + mrow0 * ldo + oc0 + lane;
           const float* sp = stg + lane;
 #pragma unroll 8
-          for (int rr = 0; rr < nrows; ++rr) o16[rr * ldo] = __float2bfloat16_rn(sp[rr * STG_LD]);
+          for (int rr = 0; rr < nrows; ++rr) o16[rr * ldo] = cvt16(sp[rr * STG_LD], a.fp16 != 0);
           __syncwarp();
         }
       }
@@ -502,7 +502,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.pool = o.pool ? 1 : 0;
   a.highway = o.highway ? 1 : 0;
   a.fp16 = o.fp16 ? 1 : 0;
-  FTB_REQUIRE(!(o.fp16 && o.highway), FTB_ERR_INVALID, "conv_gemm_bf16: the highway epilogue is bf16 only");
+
   a.m_stride = o.pool ? BM - 1 : BM;
   a.m_tiles = cdiv(S, a.m_stride);
   a.box_rows = BM;  // the box may exceed the tensor: rows outside [0,S) are zero-filled (conv padding, pool halo)

@@ -4,11 +4,16 @@
 //   (host: pitch_function / energy_function callbacks, ftb_length_plan, D2H of frame counts)
 //   stage B  ftb_ft_synthesize : embedding -> CBHG prenet -> conditioning -> LengthRegulator ->
 //                                biLSTM -> lin -> CBHG postnet -> post_proj
-// Activation dtype T is bf16 (tcgen05 GEMMs) or float (gemm_mode 1, all-fp32 validation mode).
+// Activation dtype T is bf16 (gemm_mode 0, tcgen05 GEMMs), IEEE half (gemm_mode 2: same kernels and rate, 11-bit
+// significand -- the choice for trained-magnitude mels) or float (gemm_mode 1, all-fp32 validation mode).
 // The duration predictor is always fp32 (bit-exact durations).
 #include "model_common.cuh"
 
 namespace ftb {
+
+// ftb_rnn_bidir output type code of an activation type: 0 f32, 1 bf16, 2 IEEE half
+template <typename T>
+constexpr int out_kind() { return std::is_same<T, float>::value ? 0 : std::is_same<T, f16>::value ? 2 : 1; }
 
 struct SeriesW {  // SeriesPredictor, models/forward_tacotron.py:14-55
   const float* emb = nullptr;
@@ -38,7 +43,8 @@ struct ftb_ft_handle : ftb::ModelBase {
   const float *pitch_w = nullptr, *pitch_b = nullptr, *energy_w = nullptr, *energy_b = nullptr;
   ftb::Rnn lstm;
   ftb::Layer lin, post_proj;
-  bool bf16_mode() const { return cfg.gemm_mode == 0; }
+  bool bf16_mode() const { return cfg.gemm_mode == 0 || cfg.gemm_mode == 2; }  // a 16-bit tensor-core mode
+  bool is_fp16() const { return cfg.gemm_mode == 2; }
 
   // Stage A runs its three independent predictors on three side streams, forked from and joined back into the
   // caller's stream with events.  With FTB_OPT_OVERLAP_PRENET the prenet CBHG of stage B (it depends on the
@@ -134,8 +140,8 @@ static int build_cbhg(ftb_ft_handle* h, CbhgW& W, const std::string& p, int K, i
       // so a 64-column accumulator group holds both halves of the same 32 channels (highway epilogue)
       FTB_REQUIRE(ch % 32 == 0 && L.CinP == ch, FTB_ERR_UNSUPPORTED, "%s: highway width %d must be a multiple of 64", q.c_str(), ch);
       for (int g = 0; g < ch / 32; ++g) {
-        FTB_TRY(ftb_pack_conv_weight(w1 + (int64_t)g * 32 * ch, L.w16 + (int64_t)(2 * g) * 32 * L.CinP, 32, ch, 1, 32, L.CinP, 1, h->prep));
-        FTB_TRY(ftb_pack_conv_weight(w2 + (int64_t)g * 32 * ch, L.w16 + (int64_t)(2 * g + 1) * 32 * L.CinP, 32, ch, 1, 32, L.CinP, 1, h->prep));
+        FTB_TRY(ftb_pack_conv_weight(w1 + (int64_t)g * 32 * ch, L.w16 + (int64_t)(2 * g) * 32 * L.CinP, 32, ch, 1, 32, L.CinP, h->pack16, h->prep));
+        FTB_TRY(ftb_pack_conv_weight(w2 + (int64_t)g * 32 * ch, L.w16 + (int64_t)(2 * g + 1) * 32 * L.CinP, 32, ch, 1, 32, L.CinP, h->pack16, h->prep));
         FTB_TRY(copy_f32(b1 + g * 32, L.bias + 2 * g * 32, 32, h->prep));
         FTB_TRY(copy_f32(b2 + g * 32, L.bias + (2 * g + 1) * 32, 32, h->prep));
       }
@@ -222,8 +228,8 @@ static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int 
   FTB_TRY(h->gemm<T>(W.pre_hw, w.p2, w.ld2, B, S, act_out(w.ha, W.ch), nullptr, 0, 1.f, s));
   T *cur = w.ha, *nxt = w.hb;
   for (int i = 0; i < W.nhw; ++i) {
-    if (std::is_same<T, bf16>::value) {  // one launch: GEMM + gate mix in the epilogue
-      FTB_TRY(h->highway_tc(W.hw[i], (const bf16*)cur, W.ch, B, S, (bf16*)nxt, s));
+    if (!std::is_same<T, float>::value) {  // one launch: GEMM + gate mix in the epilogue
+      FTB_TRY(h->highway_tc(W.hw[i], (const bf16*)cur, W.ch, B, S, (bf16*)nxt, std::is_same<T, f16>::value, s));
     } else {
       FTB_TRY(h->gemm<T>(W.hw[i], cur, W.ch, B, S, act_out(w.t12, 2 * W.ch), nullptr, 0, 1.f, s));
       FTB_TRY(highway_mix<T>(w.t12, cur, nxt, M, W.ch, s));
@@ -232,7 +238,7 @@ static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int 
     std::swap(cur, nxt);
   }
   FTB_TRY(h->gemm<T>(W.rnn.in, cur, W.ch, B, S, act_out(w.xg, 6 * W.ch), nullptr, 0, 1.f, s));
-  FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, std::is_same<T, bf16>::value, s));
+  FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, out_kind<T>(), s));
   h->launches += 1;
   A.reset(mark);
   return FTB_OK;
@@ -269,7 +275,7 @@ static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* c
                       c.energy_strength, B, Tn, D, s));
   FTB_TRY(ftb_length_expand(enc, cum, up, B, Tn, L, D, (int)sizeof(T), s));
   FTB_TRY(h->gemm<T>(h->lstm.in, up, D, B, L, act_out(xg, 8 * RH), nullptr, 0, 1.f, s));
-  FTB_TRY(rnn_bidir(xg, h->lstm.w_hh, nullptr, dec, B, L, RH, 1, std::is_same<T, bf16>::value, s));
+  FTB_TRY(rnn_bidir(xg, h->lstm.w_hh, nullptr, dec, B, L, RH, 1, out_kind<T>(), s));
   if (melP != NM) FTB_CHECK_CUDA(cudaMemsetAsync(mel_cl, 0, (size_t)ML * melP * sizeof(T), s));
   Out o = act_out(mel_cl, melP);
   o.t = mel;  // 'mel' (B,80,L) and the channel-last copy the postnet reads, from one epilogue
@@ -377,6 +383,7 @@ extern "C" int ftb_ft_create(const ftb_ft_config* cfg, const ftb_tensor* tensors
   ftb_ft_handle* h = new ftb_ft_handle();
   h->cfg = *cfg;
   h->device = device;
+  h->pack16 = h->is_fp16() ? 2 : 1;
   for (int i = 0; i < n_tensors; ++i) h->sd[tensors[i].name] = tensors[i];
   const ftb_ft_config& c = h->cfg;
   auto build = [&]() -> int {
@@ -438,7 +445,8 @@ extern "C" int ftb_ft_series_predictor(ftb_ft_handle* h, int which, const int64_
   Arena A(workspace, workspace_bytes);
   SeriesW& P = h->series[which];
   if (P.f32_only || !h->bf16_mode()) return run_series<float>(h, P, tokens, B, T, alpha, out, A, (cudaStream_t)stream);
-  return run_series<bf16>(h, P, tokens, B, T, alpha, out, A, (cudaStream_t)stream);
+  return h->is_fp16() ? run_series<f16>(h, P, tokens, B, T, alpha, out, A, (cudaStream_t)stream)
+                      : run_series<bf16>(h, P, tokens, B, T, alpha, out, A, (cudaStream_t)stream);
 }
 
 extern "C" int ftb_ft_set_option(ftb_ft_handle* h, int option, int value) {
@@ -487,7 +495,8 @@ extern "C" int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, in
   if (!fork) return FTB_OK;
   if (h->opt_overlap_prenet) {
     FTB_CHECK_CUDA(cudaStreamWaitEvent(h->side[3], h->ev_fork, 0));
-    FTB_TRY(b16 ? prefetch_prenet<bf16>(h, tokens, B, T) : prefetch_prenet<float>(h, tokens, B, T));
+    FTB_TRY(!b16 ? prefetch_prenet<float>(h, tokens, B, T)
+                 : h->is_fp16() ? prefetch_prenet<f16>(h, tokens, B, T) : prefetch_prenet<bf16>(h, tokens, B, T));
     FTB_CHECK_CUDA(cudaEventRecord(h->ev_join[3], h->side[3]));
   }
   for (int i = 0; i < 3; ++i) FTB_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_join[i], 0));  // join
@@ -503,7 +512,8 @@ extern "C" int ftb_ft_synthesize(ftb_ft_handle* h, const int64_t* tokens, const 
   h->launches = 0;
   Arena A(workspace, workspace_bytes);
   if (h->bf16_mode())
-    return run_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, (cudaStream_t)stream);
+    return h->is_fp16() ? run_synthesize<f16>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, (cudaStream_t)stream)
+                        : run_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, (cudaStream_t)stream);
   return run_synthesize<float>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, (cudaStream_t)stream);
 }
 
@@ -520,6 +530,11 @@ extern "C" int ftb_ft_cbhg(ftb_ft_handle* h, int which, const float* x, int B, i
     bf16* xi = A.take<bf16>(M * ldx);
     bf16* yo = A.take<bf16>(M * 2 * W.ch);
     FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small");
+    if (h->is_fp16()) {
+      FTB_TRY(cast_rows<f16>(x, (f16*)xi, M, W.Cin, W.Cin, ldx, s));
+      FTB_TRY(run_cbhg<f16>(h, W, (f16*)xi, ldx, B, S, (f16*)yo, A, s));
+      return to_f32<f16>((f16*)yo, out, M * 2 * W.ch, s);
+    }
     FTB_TRY(cast_rows<bf16>(x, xi, M, W.Cin, W.Cin, ldx, s));
     FTB_TRY(run_cbhg<bf16>(h, W, xi, ldx, B, S, yo, A, s));
     return to_f32<bf16>(yo, out, M * 2 * W.ch, s);

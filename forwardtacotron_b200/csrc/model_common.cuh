@@ -219,7 +219,7 @@ struct ModelBase {
 
   // One highway layer on the tensor cores: L packs W1/W2 interleaved in groups of 32 rows (pack_highway), the
   // epilogue forms y = sigmoid(x2) relu(x1) + (1 - sigmoid(x2)) x and writes bf16.  (models/common_layers.py:30-35)
-  int highway_tc(const Layer& L, const bf16* x, int C, int B, int S, bf16* y, cudaStream_t s) {
+  int highway_tc(const Layer& L, const bf16* x, int C, int B, int S, bf16* y, bool fp16, cudaStream_t s) {
     TcItem it;
     it.w = L.w16;
     it.N = 2 * C;
@@ -231,6 +231,7 @@ struct ModelBase {
     o.res_bf16 = x;
     o.ldr = C;
     o.highway = true;
+    o.fp16 = fp16;
     ++launches;
     ProfScope prof(FAM_GEMM_TC, 2.0 * B * S * (double)(2 * C) * C, 0.0, s);
     return conv_gemm_group(x, C, B, S, L.CinP, &it, 1, o, s);
@@ -267,6 +268,7 @@ struct ModelBase {
     o.out_bf16 = (bf16*)out;
     o.ldo = bank_c;
     o.pool = true;
+    o.fp16 = std::is_same<T, f16>::value;
     ++launches;
     ProfScope prof(FAM_GEMM_TC, flops, 0.0, s);
     return conv_gemm_group((const bf16*)x, lda, B, S, bank[0].CinP, items.data(), K, o, s);

@@ -28,11 +28,18 @@ namespace cg = cooperative_groups;
 
 namespace ftb {
 
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (F16)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
@@ -99,7 +106,7 @@ struct RnnCfg {
   static_assert(R % 16 == 0 && H % 32 == 0 && BC % 8 == 0 && BC >= 8 && BC <= 32 && HC % 8 == 0, "unsupported RNN tiling");
 };
 
-template <int G, int H, int CL, int BC>
+template <int G, int H, int CL, int BC, bool F16>
 __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
     rnn_cluster_kernel(const float* __restrict__ xg,    // (B,S,2,G*H)
                        const float* __restrict__ w_hh,  // (2,G*H,H)
@@ -132,10 +139,10 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
       const float2 v10 = *reinterpret_cast<const float2*>(w1 + kt * 16);
       const float2 v01 = *reinterpret_cast<const float2*>(w0 + kt * 16 + 8);
       const float2 v11 = *reinterpret_cast<const float2*>(w1 + kt * 16 + 8);
-      wf[kt][0] = pack_bf16x2(v00.x, v00.y);
-      wf[kt][1] = pack_bf16x2(v10.x, v10.y);
-      wf[kt][2] = pack_bf16x2(v01.x, v01.y);
-      wf[kt][3] = pack_bf16x2(v11.x, v11.y);
+      wf[kt][0] = F16 ? pack_f16x2(v00.x, v00.y) : pack_bf16x2(v00.x, v00.y);
+      wf[kt][1] = F16 ? pack_f16x2(v10.x, v10.y) : pack_bf16x2(v10.x, v10.y);
+      wf[kt][2] = F16 ? pack_f16x2(v01.x, v01.y) : pack_bf16x2(v01.x, v01.y);
+      wf[kt][3] = F16 ? pack_f16x2(v11.x, v11.y) : pack_bf16x2(v11.x, v11.y);
     }
   }
   for (int i = tid; i < 2 * BC * HP; i += NT) hbuf[i] = __float2bfloat16_rn(0.f);
@@ -229,8 +236,8 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
       for (int kt = 0; kt < KT; kt += 2) {
         uint32_t bf[4];
         ldmatrix_x4(bf, hb + kt * 32);
-        mma_bf16_16816(acc[0][0], wf[kt], bf[0], bf[1]);
-        mma_bf16_16816(acc[1][0], wf[kt + 1], bf[2], bf[3]);
+        mma_16816<F16>(acc[0][0], wf[kt], bf[0], bf[1]);
+        mma_16816<F16>(acc[1][0], wf[kt + 1], bf[2], bf[3]);
       }
     } else {
       const uint32_t hb01 = smem_u32(hcur + lm4_n * HP + lm4_k);
@@ -240,18 +247,18 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
       for (int kt = 0; kt < KT; ++kt) {
         uint32_t bf[4];
         ldmatrix_x4(bf, hb01 + kt * 32);
-        mma_bf16_16816(acc[kt & 1][0], wf[kt], bf[0], bf[1]);
-        mma_bf16_16816(acc[kt & 1][1], wf[kt], bf[2], bf[3]);
+        mma_16816<F16>(acc[kt & 1][0], wf[kt], bf[0], bf[1]);
+        mma_16816<F16>(acc[kt & 1][1], wf[kt], bf[2], bf[3]);
         if (NTL == 3) {
           uint32_t b2[2];
           ldmatrix_x2(b2, hb2 + kt * 32);
-          mma_bf16_16816(acc[kt & 1][NTL - 1], wf[kt], b2[0], b2[1]);
+          mma_16816<F16>(acc[kt & 1][NTL - 1], wf[kt], b2[0], b2[1]);
         }
         if (NTL == 4) {
           uint32_t b4[4];
           ldmatrix_x4(b4, hb23 + kt * 32);
-          mma_bf16_16816(acc[kt & 1][NTL - 2], wf[kt], b4[0], b4[1]);
-          mma_bf16_16816(acc[kt & 1][NTL - 1], wf[kt], b4[2], b4[3]);
+          mma_16816<F16>(acc[kt & 1][NTL - 2], wf[kt], b4[0], b4[1]);
+          mma_16816<F16>(acc[kt & 1][NTL - 1], wf[kt], b4[2], b4[3]);
         }
       }
     }
@@ -293,10 +300,13 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
           hn = (1.f - gz) * gn + gz * hprev[p];
         }
         hprev[p] = hn;
-        hstage[n * HC + u] = __float2bfloat16_rn(hn);
+        reinterpret_cast<unsigned short*>(hstage)[n * HC + u] =
+            F16 ? __half_as_ushort(__float2half_rn(hn)) : __bfloat16_as_ushort(__float2bfloat16_rn(hn));
         if (pvalid[p]) {
           const int64_t o = optr[p] + (int64_t)t * 2 * H;
-          if (out_bf16)
+          if (out_bf16 == 2)
+            reinterpret_cast<__half*>(out)[o] = __float2half_rn(hn);
+          else if (out_bf16)
             reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(hn);
           else
             reinterpret_cast<float*>(out)[o] = hn;
@@ -322,11 +332,11 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
   cluster.sync();  // no CTA exits while a peer may still address its shared memory
 }
 
-template <int G, int H, int CL, int BC>
+template <int G, int H, int CL, int BC, bool F16 = false>
 static int launch_rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S,
                               int out_bf16, cudaStream_t s, int* max_clusters) {
   using C = RnnCfg<G, H, CL, BC>;
-  auto kern = rnn_cluster_kernel<G, H, CL, BC>;
+  auto kern = rnn_cluster_kernel<G, H, CL, BC, F16>;
   static bool configured = false;
   static int max_active = 0;
   cudaLaunchConfig_t cfg = {};
@@ -366,10 +376,20 @@ static int dispatch_bc(const float* xg, const float* w_hh, const float* b_hn, vo
   FTB_TRY((launch_rnn_cluster<G, H, CL, 8>(nullptr, nullptr, nullptr, nullptr, B, S, 0, s, &m8)));
   FTB_TRY((launch_rnn_cluster<G, H, CL, 16>(nullptr, nullptr, nullptr, nullptr, B, S, 0, s, &m16)));
   FTB_TRY((launch_rnn_cluster<G, H, CL, 24>(nullptr, nullptr, nullptr, nullptr, B, S, 0, s, &m24)));
-  if (2 * cdiv(B, 8) <= m8) return launch_rnn_cluster<G, H, CL, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr);
-  if (2 * cdiv(B, 16) <= m16) return launch_rnn_cluster<G, H, CL, 16>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr);
-  if (2 * cdiv(B, 24) <= m24) return launch_rnn_cluster<G, H, CL, 24>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr);
-  return launch_rnn_cluster<G, H, CL, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr);
+  const int bc = 2 * cdiv(B, 8) <= m8 ? 8 : 2 * cdiv(B, 16) <= m16 ? 16 : 2 * cdiv(B, 24) <= m24 ? 24 : 32;
+  // IEEE-half activations (output type 2) take IEEE-half recurrent operands as well: same kernel, f16 mma
+#define FTB_RNN_BC(N)                                                                                         \
+  case N:                                                                                                     \
+    return out_bf16 == 2 ? launch_rnn_cluster<G, H, CL, N, true>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr) \
+                         : launch_rnn_cluster<G, H, CL, N, false>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr);
+  switch (bc) {
+    FTB_RNN_BC(8)
+    FTB_RNN_BC(16)
+    FTB_RNN_BC(24)
+    FTB_RNN_BC(32)
+  }
+#undef FTB_RNN_BC
+  return FTB_ERR_INVALID;
 }
 
 // GRU H=256 (the two CBHG RNNs): 8 utterances per cluster make the register-resident mma.sync step cheaper than

@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(3 * H) gru_small_kernel(const float* __restric
       const float hn = (1.f - z) * n + z * h[tid];
       h[tid] = hn;
       const int64_t o = ((int64_t)b * S + t) * (2 * H) + dir * H + tid;
-      if (out_bf16)
+      if (out_bf16 == 2)
+        ((__half*)out)[o] = __float2half_rn(hn);
+      else if (out_bf16)
         ((__nv_bfloat16*)out)[o] = __float2bfloat16_rn(hn);
       else
         ((float*)out)[o] = hn;

@@ -170,6 +170,8 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
   const uint32_t bar0 = smem_u32(smem_raw + C::OFF_BAR);  // h_full[buf][slice] at bar0 + 8*(buf*CL + slice); then d_full
   const uint32_t dfull = bar0 + 8 * 2 * CL;
   const uint32_t wa0 = smem_u32(smem_raw + C::OFF_W);
+  const bool f16op = out_bf16 == 2;  // IEEE-half recurrent operands go with IEEE-half activations (gemm_mode 2)
+  const uint32_t idesc = f16op ? (C::IDESC & ~((1u << 7) | (1u << 10))) : C::IDESC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + C::OFF_BAR + 8 * C::NBAR);
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -211,7 +213,8 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
       uint4 v = make_uint4(0, 0, 0, 0);
       if (g < G) {
         const float4 a = *reinterpret_cast<const float4*>(wrow + kc * 8), b = *reinterpret_cast<const float4*>(wrow + kc * 8 + 4);
-        v = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+        v = f16op ? make_uint4(pack_f16x2(a.x, a.y), pack_f16x2(a.z, a.w), pack_f16x2(b.x, b.y), pack_f16x2(b.z, b.w))
+                  : make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
       }
       *reinterpret_cast<uint4*>(wdst + (kc >> 3) * 16384 + (((kc & 7) ^ (m & 7)) << 4)) = v;
     }
@@ -337,7 +340,9 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
       }
       hprev[e] = hn[e];
       if (ok[e]) {
-        if (out_bf16)
+        if (out_bf16 == 2)
+          reinterpret_cast<__half*>(out)[op[e]] = __float2half_rn(hn[e]);
+        else if (out_bf16)
           reinterpret_cast<__nv_bfloat16*>(out)[op[e]] = __float2bfloat16_rn(hn[e]);
         else
           reinterpret_cast<float*>(out)[op[e]] = hn[e];
@@ -351,7 +356,9 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
       unsigned char* hb_next = smem_raw + nbuf * C::HB_BYTES;
 #pragma unroll
       for (int e = 0; e < PPT; ++e)
-        if (ok[e]) *reinterpret_cast<__nv_bfloat16*>(hb_next + cell0 + e * 16) = __float2bfloat16_rn(hn[e]);
+        if (ok[e])
+          *reinterpret_cast<unsigned short*>(hb_next + cell0 + e * 16) =
+              f16op ? __half_as_ushort(__float2half_rn(hn[e])) : __bfloat16_as_ushort(__float2bfloat16_rn(hn[e]));
       RNN_STAMP(4);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic writes -> visible to UMMA / bulk copy
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
           for (int j = 0; j < 2; ++j) {  // the issuer's first MMA of a step overwrites its accumulator
             const uint32_t ks = 2 * r + j;
             umma_ss_bf16(d_acc, adesc_sw128(wa0 + (ks >> 2) * 16384 + (ks & 3) * 32), bdesc_kmajor(hbn + r * C::SL + j * 256, 512),
-                         C::IDESC, (i >= NISS || j > 0) ? 1u : 0u);
+                         idesc, (i >= NISS || j > 0) ? 1u : 0u);
           }
         }
         umma_commit(dfull);

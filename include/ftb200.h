@@ -155,7 +155,7 @@ int ftb_pack_conv_weight(const float* w, void* out, int N, int Cin, int k, int N
  * xg (B,S,2,G*H) f32 holds W_ih x + b_ih (+ b_hh for the gates where it can be
  * folded: all LSTM gates, GRU r and z); w_hh (2,G*H,H) f32 in torch gate order;
  * b_hn (2,H) f32 is the GRU n-gate hidden bias (NULL for LSTM).
- * out (B,S,2H): f32 when out_bf16 == 0, else bf16.
+ * out (B,S,2H): f32 when out_bf16 == 0, bf16 when 1, IEEE half when 2.
  * H in {64,128}: one-CTA-per-row fp32 kernel (W_hh in shared memory, exact fp32).
  * H in {256,512}: thread-block-cluster kernel, W_hh resident in registers as
  * bf16 MMA fragments, hidden state exchanged through distributed shared memory. */
@@ -192,7 +192,8 @@ typedef struct ftb_ft_config { /* keys of config.yaml forward_tacotron.model + n
   int32_t postnet_dims, postnet_k, postnet_num_highways;
   int32_t n_mels;
   float pitch_strength, energy_strength;
-  int32_t gemm_mode; /* 0: bf16 tcgen05 GEMMs (duration predictor stays fp32); 1: all GEMMs fp32 SIMT */
+  int32_t gemm_mode; /* 0: bf16 tcgen05 GEMMs (duration predictor stays fp32); 1: all GEMMs fp32 SIMT;
+                        2: IEEE-half tcgen05 GEMMs (same rate, 11-bit significand: for trained-magnitude mels) */
 } ftb_ft_config;
 
 typedef struct ftb_ft_handle ftb_ft_handle;

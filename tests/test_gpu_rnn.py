@@ -35,7 +35,7 @@ def run_kernel(sd, x, H, lstm, out_bf16=False):
     xg = torch.stack(xg, dim=2).contiguous().cuda()                  # (B,S,2,G*H)
     whh = torch.stack(whh).contiguous().cuda()
     bhn = torch.stack(bhn).contiguous().cuda()
-    out = torch.empty(B, S, 2 * H, dtype=torch.bfloat16 if out_bf16 else torch.float32, device='cuda')
+    out = torch.empty(B, S, 2 * H, dtype=(torch.float32, torch.bfloat16, torch.float16)[int(out_bf16)], device='cuda')
     _lib.check(_lib.lib().ftb_rnn_bidir(_lib.ptr(xg), _lib.ptr(whh), None if lstm else _lib.ptr(bhn), _lib.ptr(out),
                                         B, S, H, int(lstm), int(out_bf16), _lib.current_stream(out.device)))
     torch.cuda.synchronize()
@@ -64,6 +64,11 @@ def test_cluster_rnn(H, lstm, B, S):
     assert mx < 1e-2 and mn < 1e-3, (mx, mn)
     got16 = run_kernel(sd, x, H, lstm, out_bf16=True)
     assert float((got16 - got).abs().max()) < 8e-3
+    # output type 2: IEEE-half output AND IEEE-half recurrent operands (3 more significand bits than bf16)
+    goth = run_kernel(sd, x, H, lstm, out_bf16=2)
+    mxh, mnh = float((goth - want).abs().max()), float((goth - want).abs().mean())
+    print(f'H{H} lstm{int(lstm)} B{B} S{S}: bf16 operands {mx:.2e}/{mn:.2e}  half operands {mxh:.2e}/{mnh:.2e}')
+    assert mxh < 2e-3 and mnh < 2e-4 and mnh < mn, (mxh, mnh)
 
 
 def test_unsupported_size_is_an_error():
