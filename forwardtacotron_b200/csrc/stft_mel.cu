@@ -2,15 +2,16 @@
 //   reflect-pad framing -> periodic Hann -> 1024-point real FFT -> |X| -> 80-row sparse Slaney mel
 //   filterbank -> log(max(., 1e-5)) -> (n_mels, frames) store.
 //
-// One warp = one frame.  The 1024-point real FFT is a 512-point complex FFT (z[m] = x[2m] + i x[2m+1])
-// plus the split post-pass; the complex FFT is three radix-8 Stockham passes, 2 butterflies per lane
-// per pass, exchanged through a 4 KB per-warp shared-memory buffer (first pass reads straight from
-// global, in the strided order the Stockham pass needs).  The magnitude spectrum overwrites the same
-// buffer and the mel rows are dot products over each triangle's contiguous support (727 non-zeros in
-// total for the reference config), so the dense (80 x 513) GEMM never exists.
-// 8 warps per CTA = 8 consecutive frames; their 80 x 8 results are staged in shared memory and written
-// as 32-byte row segments.  Algorithmic HBM traffic: 4 B/sample read + 80*4/256 B/sample written; the 4x
-// frame overlap is served by L1/L2.
+// One warp = one frame at a time, no CTA-wide synchronisation after the table prologue.  The 1024-point real FFT
+// is a 512-point complex FFT (z[m] = x[2m] + i x[2m+1]) plus the split post-pass; the complex FFT is three radix-8
+// Stockham passes, 2 butterflies per lane per pass, exchanged through a 4.25 KB per-warp shared-memory buffer whose
+// padding (pad()) keeps the passes' access patterns off each other's banks.  The split pass handles bins k and
+// 512 - k together (same two inputs, conjugate twiddle).  The magnitude spectrum overwrites the buffer; the mel rows
+// are cut into "virtual rows" of 8 taps (the triangles have 2..33 taps: one lane per whole row would leave most lanes
+// idle behind the longest), 727 non-zeros in total for the reference config, so the dense (80 x 513) GEMM never
+// exists.  The 8 warps of a CTA work on 8 consecutive frames, so their 4-byte stores into a mel row meet in the same
+// 32-byte sector in L2.  Algorithmic HBM traffic: 4 B/sample read + 80*4/256 B/sample written; the 4x frame overlap
+// is served by L1/L2.  The kernel is bound by instruction issue + shared-memory wavefronts, not by HBM.
 #include <cmath>
 
 #include "common.cuh"
@@ -19,23 +20,40 @@ namespace ftb {
 
 namespace mel {
 constexpr int NFFT = 1024, NC = 512, NBINS = 513, WARPS = 8, MAX_MELS = 128;
+constexpr int NCP = NC + NC / 16;  // padded per-warp FFT buffer (float2): see pad()
+constexpr int VL = 8;              // taps per virtual mel row
+constexpr int PART_OFF = NCP;      // virtual-row partial sums: floats [PART_OFF, 2 NCP) of the warp's buffer
+constexpr int MAX_VR = NCP;
+constexpr int GROUPS = 8;          // 8-frame groups per CTA: amortises the table prologue
 }
 
 struct MelTables {  // device pointers
-  const float* window;   // [1024] periodic Hann
-  const float2* w512;    // [512]  exp(-2 pi i m / 512)
-  const float2* w1024;   // [513]  exp(-2 pi i k / 1024)
-  const float* mel_w;    // [nnz]  packed non-zero filter weights, row after row
-  const int* row_start;  // [n_mels] first bin of the row's support
-  const int* row_len;    // [n_mels]
-  const int* row_off;    // [n_mels] offset into mel_w
-  int n_mels, nnz, hop;
+  const float2* window;  // [512]  periodic Hann, as (w[2m], w[2m+1])
+  const float2* tw8;     // [8][9]  pass-2 twiddles exp(-2 pi i r k / 64) at [k * 9 + r]
+  const float2* tw64;    // [7][64] pass-3 twiddles exp(-2 pi i r k / 512) at [(r - 1) * 64 + k]
+  const float2* w1024;   // [257]  exp(-2 pi i k / 1024)
+  const float* vr_w;     // [VL][nvrp] tap weights of the virtual rows (0 where a row has fewer taps)
+  const int* vr_start;   // [nvrp] first bin of the virtual row (start + VL <= 513)
+  const int* row_first;  // [n_mels] first virtual row of the mel row
+  const int* row_cnt;    // [n_mels] number of virtual rows
+  int n_mels, nvrp, hop;
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Index into the padded FFT buffer: one float2 of padding after every 16.  A 64-bit shared access is served per
+// half-warp over 16 bank pairs; with this padding pass 1's stride-8 scatter and every unit-stride pattern are
+// conflict-free and pass 2's two 8-wide groups are 2-way (exhaustive search over paddings / XOR swizzles: the only
+// better layout costs an extra LOP3 per access).  Unpadded, pass 1 was 8-way conflicted and shared-memory wavefronts
+// bounded the kernel.
+__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
 
 // 8-point DFT, natural order in and out (decimation in time, 3 radix-2 levels)
 __device__ __forceinline__ void fft8(float2 (&v)[8]) {
@@ -66,65 +84,113 @@ __device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t N) {
   return i < N ? i : p - i;
 }
 
-__global__ void __launch_bounds__(mel::WARPS * 32)
+// last c in [0, n_clips) with frame_off[c] <= g: 32 probes per round instead of a dependent bisection chain
+__device__ __forceinline__ int find_clip(const int64_t* __restrict__ frame_off, int n_clips, int64_t g, int lane) {
+  int lo = 0, n = n_clips;  // candidates [lo, lo + n); invariant frame_off[lo] <= g
+  while (n > 1) {
+    const int step = (n + 31) >> 5;
+    const int idx = lo + lane * step;
+    const bool le = idx < lo + n && __ldg(frame_off + idx) <= g;  // true for a prefix of the lanes
+    const int last = 31 - __clz(__ballot_sync(0xffffffffu, le));
+    const int nlo = lo + last * step;
+    n = min(step, lo + n - nlo);
+    lo = nlo;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(mel::WARPS * 32, 4)
     stft_mel_kernel(const float* __restrict__ audio, const int64_t* __restrict__ clip_off,
                     const int64_t* __restrict__ frame_off, int n_clips, int64_t total_frames, float* __restrict__ out,
                     int normalize, const MelTables tb) {
   using namespace mel;
-  __shared__ float2 s_w512[NC];
-  __shared__ float2 s_w1024[NBINS];
-  __shared__ float2 s_buf[WARPS][NC];       // per-warp FFT buffer, later the magnitude spectrum
-  __shared__ float s_mel[WARPS][MAX_MELS];  // staged results
-  __shared__ int64_t s_dst[WARPS];          // element offset of (row 0, this frame) in out, -1 if no frame
-  __shared__ int s_frames[WARPS];           // frames of the owning clip (row stride)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_tw8 = reinterpret_cast<float2*>(smem_raw);  // 72
+  float2* s_tw64 = s_tw8 + 72;                           // 448
+  float2* s_w1024 = s_tw64 + 448;                        // 257 (+1)
+  float2* s_win = s_w1024 + 258;                         // 512
+  float2* s_bufs = s_win + NC;                           // WARPS x NCP
+  float* s_vrw = reinterpret_cast<float*>(s_bufs + WARPS * NCP);  // VL x nvrp
+  int* s_vrs = reinterpret_cast<int*>(s_vrw + VL * tb.nvrp);      // nvrp
+  int* s_rfirst = s_vrs + tb.nvrp;                                // n_mels
+  int* s_rcnt = s_rfirst + tb.n_mels;                             // n_mels
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < NC; i += WARPS * 32) s_w512[i] = tb.w512[i];
-  for (int i = tid; i < NBINS; i += WARPS * 32) s_w1024[i] = tb.w1024[i];
+  for (int i = tid; i < 72; i += WARPS * 32) s_tw8[i] = tb.tw8[i];
+  for (int i = tid; i < 448; i += WARPS * 32) s_tw64[i] = tb.tw64[i];
+  for (int i = tid; i < 257; i += WARPS * 32) s_w1024[i] = tb.w1024[i];
+  for (int i = tid; i < NC; i += WARPS * 32) s_win[i] = tb.window[i];
+  for (int i = tid; i < VL * tb.nvrp; i += WARPS * 32) s_vrw[i] = tb.vr_w[i];
+  for (int i = tid; i < tb.nvrp; i += WARPS * 32) s_vrs[i] = tb.vr_start[i];
+  for (int i = tid; i < tb.n_mels; i += WARPS * 32) s_rfirst[i] = tb.row_first[i], s_rcnt[i] = tb.row_cnt[i];
   __syncthreads();
 
-  const int64_t g = (int64_t)blockIdx.x * WARPS + warp;  // global frame index
-  float2* buf = s_buf[warp];
-  if (g < total_frames) {
-    // owning clip: last c with frame_off[c] <= g
-    int lo = 0, hi = n_clips - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (frame_off[mid] <= g) lo = mid; else hi = mid - 1;
+  float2* buf = s_bufs + warp * NCP;
+  float* magbuf = reinterpret_cast<float*>(buf);
+  float* part = magbuf + PART_OFF;
+
+  int clip = -1;
+  int64_t c0 = 0, N = 0, f_first = 0, f_next = 0;  // the current clip: samples [c0, c0 + N), frames [f_first, f_next)
+  for (int grp = 0; grp < GROUPS; ++grp) {
+    const int64_t g = ((int64_t)blockIdx.x * GROUPS + grp) * WARPS + warp;  // global frame index
+    if (g >= total_frames) break;
+    if (clip < 0) {
+      clip = find_clip(frame_off, n_clips, g, lane);
+      f_next = frame_off[clip];
+      --clip;
     }
-    const int64_t c0 = clip_off[lo], N = clip_off[lo + 1] - c0;
-    const int64_t f = g - frame_off[lo];
-    const int64_t nframes = frame_off[lo + 1] - frame_off[lo];
-    if (lane == 0) {
-      s_dst[warp] = (int64_t)tb.n_mels * frame_off[lo] + f;
-      s_frames[warp] = (int)nframes;
+    while (g >= f_next) {  // consecutive groups: same clip or one of the next few
+      ++clip;
+      f_first = f_next;
+      f_next = __ldg(frame_off + clip + 1);
+      c0 = __ldg(clip_off + clip);
+      N = __ldg(clip_off + clip + 1) - c0;
     }
+    const int64_t f = g - f_first;
+    const int64_t nframes = f_next - f_first;
     const float* y = audio + c0;
     const int64_t s0 = f * tb.hop - NFFT / 2;  // first sample of the frame in un-padded coordinates
     const bool interior = s0 >= 0 && s0 + NFFT <= N;
 
-    // ---- pass 1 (Ns = 1): inputs z[j + 64 r], j = lane + 32 jj, straight from global, windowed
+    // ---- frame -> registers: z[m] = (x[2m], x[2m+1]) for m = lane + 32 jj + 64 r (the order pass 1 wants).
+    // Three warp-uniform paths so the common one is 16 plain 8-byte loads with immediate offsets.
+    float2 x[2][8];
+    if (interior && (((c0 + s0) & 1) == 0)) {
+      const float2* p2 = reinterpret_cast<const float2*>(y + s0) + lane;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[jj][r] = __ldg(p2 + 32 * jj + 64 * r);
+    } else if (interior) {  // clip starts on an odd sample: 4-byte loads
+      const float* p1 = y + s0 + 2 * lane;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          x[jj][r] = make_float2(__ldg(p1 + 64 * jj + 128 * r), __ldg(p1 + 64 * jj + 128 * r + 1));
+    } else {  // first / last frames of a clip: reflect padding, staged through the warp's buffer
+#pragma unroll 1
+      for (int i = lane; i < NFFT; i += 32) magbuf[i] = __ldg(y + reflect_index(s0 + i, N));
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[jj][r] = buf[lane + 32 * jj + 64 * r];
+      __syncwarp();
+    }
+    // ---- pass 1 (Ns = 1): window, 8-point DFTs without twiddles (k = j % 1 = 0)
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
       const int j = lane + 32 * jj;
-      float2 v[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const int m = j + 64 * r;
-        float x0, x1;
-        if (interior) {
-          x0 = __ldg(y + s0 + 2 * m);
-          x1 = __ldg(y + s0 + 2 * m + 1);
-        } else {
-          x0 = __ldg(y + reflect_index(s0 + 2 * m, N));
-          x1 = __ldg(y + reflect_index(s0 + 2 * m + 1, N));
-        }
-        const float2 wn = __ldg(reinterpret_cast<const float2*>(tb.window) + m);
-        v[r] = make_float2(x0 * wn.x, x1 * wn.y);
+        const float2 wn = s_win[j + 64 * r];
+        x[jj][r] = make_float2(x[jj][r].x * wn.x, x[jj][r].y * wn.y);
       }
-      fft8(v);  // k = j % 1 = 0: no twiddles
+      fft8(x[jj]);
+      const int b1 = 8 * j + (j >> 1);  // pad(8 j + r) = 8 j + (j >> 1) + r
 #pragma unroll
-      for (int r = 0; r < 8; ++r) buf[j * 8 + r] = v[r];
+      for (int r = 0; r < 8; ++r) buf[b1 + r] = x[jj][r];
     }
     __syncwarp();
     // ---- passes 2, 3 (Ns = 8, 64): all reads, then all writes, in place
@@ -135,10 +201,11 @@ __global__ void __launch_bounds__(mel::WARPS * 32)
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int j = lane + 32 * jj, k = j % Ns;
+        const int jp = pad(j);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const float2 x = buf[j + 64 * r];
-          v[jj][r] = r ? cmul(x, s_w512[r * k * (64 / Ns)]) : x;
+          const float2 xx = buf[jp + 68 * r];  // pad(j + 64 r)
+          v[jj][r] = r ? cmul(xx, pass ? s_tw64[(r - 1) * 64 + k] : s_tw8[k * 9 + r]) : xx;
         }
         fft8(v[jj]);
       }
@@ -146,52 +213,58 @@ __global__ void __launch_bounds__(mel::WARPS * 32)
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int j = lane + 32 * jj, k = j % Ns;
-        const int j0 = (j / Ns) * Ns * 8 + k;
+        const int j0 = (j / Ns) * Ns * 8 + k;  // a multiple of 64 plus k < Ns
+        const int jp = pad(j0 - k) + pad(k);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) buf[j0 + r * Ns] = v[jj][r];
+        for (int r = 0; r < 8; ++r) buf[jp + pad(r * Ns)] = v[jj][r];  // = pad(j0 + r Ns): no carries between the terms
       }
       __syncwarp();
     }
-    // ---- real-FFT split + magnitude: bins k = lane + 32 i (i < 16) and k = 512 on lane 0
-    float mag[17];
+    // ---- real-FFT split + magnitude: bins k = lane + 32 t (t < 8) together with 512 - k; k = 256 on lane 0.
+    //      X[k] = (e - i w o) / 2 with e = z[k] + conj z[512-k], o = z[k] - conj z[512-k], w = exp(-2 pi i k / 1024);
+    //      the mirrored bin has e' = conj e, o' = -conj o, w' = -conj w.
+    float ma[9], mb[8];
 #pragma unroll
-    for (int i = 0; i < 17; ++i) {
-      const int k = i < 16 ? lane + 32 * i : 512;
-      float m = 0.f;
-      if (i < 16 || lane == 0) {
-        const float2 zk = buf[k & (NC - 1)];
-        const float2 zr = buf[(NC - k) & (NC - 1)];
-        const float2 zc = make_float2(zr.x, -zr.y);
-        const float2 e = cadd(zk, zc), o = cmul(s_w1024[k], csub(zk, zc));
-        // X = 0.5 * (e - i * o)
-        const float xr = 0.5f * (e.x + o.y), xi = 0.5f * (e.y - o.x);
-        m = sqrtf(xr * xr + xi * xi);
+    for (int t = 0; t < 9; ++t) {
+      const int k = t < 8 ? lane + 32 * t : 256;
+      float m0 = 0.f, m1 = 0.f;
+      if (t < 8 || lane == 0) {
+        const float2 zk = buf[pad(k)];
+        const float2 zr = buf[pad((NC - k) & (NC - 1))];
+        const float2 e = make_float2(zk.x + zr.x, zk.y - zr.y);
+        const float2 wo = cmul(s_w1024[k], make_float2(zk.x - zr.x, zk.y + zr.y));
+        const float xr = e.x + wo.y, xi = e.y - wo.x, yr = e.x - wo.y, yi = e.y + wo.x;
+        m0 = sqrt_approx(0.25f * (xr * xr + xi * xi));
+        m1 = sqrt_approx(0.25f * (yr * yr + yi * yi));
       }
-      mag[i] = m;
+      ma[t] = m0;
+      if (t < 8) mb[t] = m1;
     }
     __syncwarp();
-    float* magbuf = reinterpret_cast<float*>(buf);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) magbuf[lane + 32 * i] = mag[i];
-    if (lane == 0) magbuf[512] = mag[16];
-    __syncwarp();
-    // ---- sparse mel rows + log-clamp
-    for (int m = lane; m < tb.n_mels; m += 32) {
-      const int st = tb.row_start[m], ln = tb.row_len[m];
-      const float* w = tb.mel_w + tb.row_off[m];
-      float acc = 0.f;
-      for (int i = 0; i < ln; ++i) acc = fmaf(__ldg(w + i), magbuf[st + i], acc);
-      s_mel[warp][m] = normalize ? logf(fmaxf(acc, 1e-5f)) : acc;
+    for (int t = 0; t < 8; ++t) {
+      magbuf[lane + 32 * t] = ma[t];
+      magbuf[NC - lane - 32 * t] = mb[t];
     }
-  } else if (lane == 0) {
-    s_dst[warp] = -1;
-  }
-  __syncthreads();
-  // ---- store: consecutive threads -> consecutive frames of the same mel row
-  for (int idx = tid; idx < tb.n_mels * WARPS; idx += WARPS * 32) {
-    const int w = idx % WARPS, m = idx / WARPS;
-    const int64_t d = s_dst[w];
-    if (d >= 0) out[d + (int64_t)m * s_frames[w]] = s_mel[w][m];
+    if (lane == 0) magbuf[256] = ma[8];
+    __syncwarp();
+    // ---- sparse mel: partial sums of the 8-tap virtual rows, then one lane per mel row adds its partials
+    for (int vr = lane; vr < tb.nvrp; vr += 32) {
+      const float* mg = magbuf + s_vrs[vr];
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < VL; ++i) acc = fmaf(s_vrw[i * tb.nvrp + vr], mg[i], acc);
+      part[vr] = acc;
+    }
+    __syncwarp();
+    float* dst = out + (int64_t)tb.n_mels * f_first + f;
+    for (int m = lane; m < tb.n_mels; m += 32) {
+      const int first = s_rfirst[m], cnt = s_rcnt[m];
+      float acc = 0.f;
+      for (int i = 0; i < cnt; ++i) acc += part[first + i];
+      dst[(int64_t)m * nframes] = normalize ? logf(fmaxf(acc, 1e-5f)) : acc;
+    }
+    __syncwarp();
   }
 }
 
@@ -204,6 +277,7 @@ struct ftb_mel_handle {
   int device = 0;
   std::vector<void*> owned;
   std::vector<float> fb_host;  // dense (n_mels, 513)
+  int smem = 0;                // dynamic shared memory of the kernel (tables + per-warp buffers)
   MelTables tb;
   ~ftb_mel_handle() {
     for (void* p : owned) cudaFree(p);
@@ -274,33 +348,56 @@ extern "C" int ftb_mel_create(const ftb_mel_config* cfg, int device, ftb_mel_han
     const double PI = 3.14159265358979323846;
     std::vector<float> win(mel::NFFT);
     for (int n = 0; n < mel::NFFT; ++n) win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / mel::NFFT));
-    std::vector<float2> w512(mel::NC), w1024(mel::NBINS);
-    for (int m = 0; m < mel::NC; ++m) w512[m] = make_float2((float)std::cos(2 * PI * m / 512), (float)-std::sin(2 * PI * m / 512));
-    for (int k = 0; k < mel::NBINS; ++k)
+    std::vector<float2> tw8(8 * 9, make_float2(1.f, 0.f)), tw64(7 * 64), w1024(257), win2(mel::NC);
+    for (int m = 0; m < mel::NC; ++m) win2[m] = make_float2(win[2 * m], win[2 * m + 1]);
+    for (int k = 0; k < 8; ++k)
+      for (int r = 0; r < 8; ++r)
+        tw8[k * 9 + r] = make_float2((float)std::cos(2 * PI * r * k / 64), (float)-std::sin(2 * PI * r * k / 64));
+    for (int r = 1; r < 8; ++r)
+      for (int k = 0; k < 64; ++k)
+        tw64[(r - 1) * 64 + k] = make_float2((float)std::cos(2 * PI * r * k / 512), (float)-std::sin(2 * PI * r * k / 512));
+    for (int k = 0; k < 257; ++k)
       w1024[k] = make_float2((float)std::cos(2 * PI * k / 1024), (float)-std::sin(2 * PI * k / 1024));
     h->fb_host = mel_filterbank(cfg->sample_rate, cfg->n_fft, cfg->num_mels, cfg->fmin, cfg->fmax);
-    std::vector<float> packed;
-    std::vector<int> start(cfg->num_mels), len(cfg->num_mels), off(cfg->num_mels);
+    // virtual rows: the support of every mel row cut into pieces of VL taps
+    std::vector<int> vstart, rfirst(cfg->num_mels), rcnt(cfg->num_mels);
+    std::vector<std::vector<float>> vtaps;
     for (int m = 0; m < cfg->num_mels; ++m) {
       const float* row = h->fb_host.data() + (size_t)m * mel::NBINS;
       int a = 0, b = mel::NBINS;
       while (a < mel::NBINS && row[a] == 0.f) ++a;
       while (b > a && row[b - 1] == 0.f) --b;
-      start[m] = a < mel::NBINS ? a : 0;
-      len[m] = b - a;
-      off[m] = (int)packed.size();
-      for (int k = a; k < b; ++k) packed.push_back(row[k]);
+      rfirst[m] = (int)vstart.size();
+      for (int p0 = a; p0 < b; p0 += mel::VL) {
+        const int st0 = std::min(p0, mel::NBINS - mel::VL);  // keep start + VL inside the spectrum
+        std::vector<float> taps(mel::VL, 0.f);
+        for (int k = p0; k < std::min(b, p0 + mel::VL); ++k) taps[k - st0] = row[k];
+        vstart.push_back(st0);
+        vtaps.push_back(taps);
+      }
+      rcnt[m] = (int)vstart.size() - rfirst[m];
     }
-    FTB_TRY(upload(h, win, &h->tb.window));
-    FTB_TRY(upload(h, w512, &h->tb.w512));
+    const int nvr = (int)vstart.size(), nvrp = std::max(32, (nvr + 31) / 32 * 32);
+    FTB_REQUIRE(nvrp <= mel::MAX_VR, FTB_ERR_UNSUPPORTED, "ftb_mel_create: %d virtual mel rows exceed the kernel's %d",
+                nvrp, mel::MAX_VR);
+    vstart.resize(nvrp, 0);
+    std::vector<float> vrw((size_t)mel::VL * nvrp, 0.f);
+    for (int v = 0; v < nvr; ++v)
+      for (int i = 0; i < mel::VL; ++i) vrw[(size_t)i * nvrp + v] = vtaps[v][i];
+    FTB_TRY(upload(h, win2, &h->tb.window));
+    FTB_TRY(upload(h, tw8, &h->tb.tw8));
+    FTB_TRY(upload(h, tw64, &h->tb.tw64));
     FTB_TRY(upload(h, w1024, &h->tb.w1024));
-    FTB_TRY(upload(h, packed, &h->tb.mel_w));
-    FTB_TRY(upload(h, start, &h->tb.row_start));
-    FTB_TRY(upload(h, len, &h->tb.row_len));
-    FTB_TRY(upload(h, off, &h->tb.row_off));
+    FTB_TRY(upload(h, vrw, &h->tb.vr_w));
+    FTB_TRY(upload(h, vstart, &h->tb.vr_start));
+    FTB_TRY(upload(h, rfirst, &h->tb.row_first));
+    FTB_TRY(upload(h, rcnt, &h->tb.row_cnt));
     h->tb.n_mels = cfg->num_mels;
-    h->tb.nnz = (int)packed.size();
+    h->tb.nvrp = nvrp;
     h->tb.hop = cfg->hop_length;
+    h->smem = (72 + 448 + 258 + mel::NC + mel::WARPS * mel::NCP) * (int)sizeof(float2) +
+              (mel::VL * nvrp + nvrp + 2 * cfg->num_mels) * 4;
+    FTB_CHECK_CUDA(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
     return FTB_OK;
   };
   const int st = build();
@@ -325,11 +422,12 @@ extern "C" int ftb_mel_run(ftb_mel_handle* h, const float* audio, const int64_t*
                            void* stream) {
   FTB_REQUIRE(h && audio && clip_offsets && frame_offsets && out && n_clips > 0 && total_frames > 0, FTB_ERR_INVALID,
               "ftb_mel_run: bad arguments");
-  const int64_t blocks = (total_frames + mel::WARPS - 1) / mel::WARPS;
+  const int64_t per_cta = (int64_t)mel::WARPS * mel::GROUPS;
+  const int64_t blocks = (total_frames + per_cta - 1) / per_cta;
   FTB_REQUIRE(blocks < 2147483647LL, FTB_ERR_INVALID, "ftb_mel_run: too many frames for one launch");
   ProfScope prof(FAM_STFT_MEL, 0.0, (double)total_frames * (h->cfg.hop_length * 4.0 + h->cfg.num_mels * 4.0),
                  (cudaStream_t)stream);
-  stft_mel_kernel<<<(unsigned)blocks, mel::WARPS * 32, 0, (cudaStream_t)stream>>>(audio, clip_offsets, frame_offsets,
+  stft_mel_kernel<<<(unsigned)blocks, mel::WARPS * 32, h->smem, (cudaStream_t)stream>>>(audio, clip_offsets, frame_offsets,
                                                                                    n_clips, total_frames, out, normalize,
                                                                                    h->tb);
   FTB_CHECK_LAUNCH();
