@@ -84,46 +84,88 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  An NVML thread polls every few ms (the timed
+    region of the default run is ~100 ms, far shorter than one `nvidia-smi -lms` period); if NVML is not importable
+    the `nvidia-smi` loop is the fallback."""
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, uuid: str):
-        self.tmp = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
-        self.proc = None
+    def __init__(self, uuid: str, period_s: float = 0.004):
+        import threading
+        self.samples, self.reasons, self.sm_max, self.power = [], set(), None, []
+        self.proc = self.tmp = self.thread = None
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', uuid, f'--query-gpu={self.FIELDS}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.tmp,
-                                         stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            masks = (('hw_slowdown', pynvml.nvmlClocksEventReasonHwSlowdown),
+                     ('hw_thermal_slowdown', pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                     ('sw_thermal_slowdown', pynvml.nvmlClocksEventReasonSwThermalSlowdown),
+                     ('sw_power_cap', pynvml.nvmlClocksEventReasonSwPowerCap))
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for name, m in masks:
+                            if r & m:
+                                self.reasons.add(name)
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+                    except Exception:
+                        pass
+                    self._stop.wait(period_s)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.source = 'nvml thread'
         except Exception:
-            self.proc = None
+            self.thread = None
+            self.source = 'nvidia-smi -lms 20'
+            self.tmp = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+            try:
+                self.proc = subprocess.Popen(['nvidia-smi', '-i', uuid, f'--query-gpu={self.FIELDS}',
+                                              '--format=csv,noheader,nounits', '-lms', '20'], stdout=self.tmp,
+                                             stderr=subprocess.DEVNULL)
+            except Exception:
+                self.proc = None
 
     def stop(self):
-        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.tmp.flush()
-        rows = [r.split(',') for r in Path(self.tmp.name).read_text().strip().splitlines() if r.count(',') >= 6]
-        os.unlink(self.tmp.name)
-        sm, reasons = [], set()
-        for r in rows:
+        out = {'sm_mhz': None, 'sm_max_mhz': self.sm_max, 'reasons': [], 'samples': 0, 'source': self.source}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        elif self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(r[0]))
-                out['sm_max_mhz'] = float(r[1])
-            except ValueError:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
-                if v.strip().lower().startswith('active'):
-                    reasons.add(name)
-        if sm:
-            out['sm_mhz'] = statistics.median(sm)
-            out['samples'] = len(sm)
-        out['reasons'] = sorted(reasons)
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.tmp.flush()
+            rows = [r.split(',') for r in Path(self.tmp.name).read_text().strip().splitlines() if r.count(',') >= 6]
+            os.unlink(self.tmp.name)
+            for r in rows:
+                try:
+                    self.samples.append(float(r[0]))
+                    self.sm_max = float(r[1])
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.strip().lower().startswith('active'):
+                        self.reasons.add(name)
+            out['sm_max_mhz'] = self.sm_max
+        if self.samples:
+            out['sm_mhz'] = statistics.median(self.samples)
+            out['samples'] = len(self.samples)
+        if self.power:
+            out['power_w_max'] = max(self.power)
+        out['reasons'] = sorted(self.reasons)
         return out
 
 

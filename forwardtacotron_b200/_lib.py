@@ -16,6 +16,7 @@ _LIB_PATH = Path(__file__).resolve().parent / 'csrc' / 'libftb200.so'
 FTB_F32, FTB_I64, FTB_BF16, FTB_I32 = 0, 1, 2, 3
 FTB_OPT_OVERLAP_PRENET = 1
 FTB_OPT_SERIALIZE = 2
+FTB_OPT_DUR_SIMT = 3
 FTB_TUNE_LSTM_MIN_CHUNK = 1
 
 

@@ -132,6 +132,29 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, void* __res
   }
 }
 
+// (N, Cin, k) f32 -> (Npad, 6, k, Cin_pad) bf16: the K axis of the split-precision GEMM (conv_gemm_tc.cu, split_in).
+// w = hi + mid + lo (three bf16 parts = the fp32 value); segment s holds the part that multiplies activation part
+// {lo, hi, mid, mid, hi, hi}[s]:  {hi, lo, mid, hi, mid, hi}[s].
+__global__ void pack_conv_weight_split3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int Cin,
+                                               int k, int Npad, int Cin_pad) {
+  const int64_t per_n = (int64_t)k * Cin_pad, total = (int64_t)Npad * per_n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cin_pad);
+    const int j = (int)((i / Cin_pad) % k);
+    const int n = (int)(i / per_n);
+    const float v = (n < N && c < Cin) ? w[((int64_t)n * Cin + c) * k + j] : 0.f;
+    __nv_bfloat16 part[3];
+    part[0] = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(part[0]);
+    part[1] = __float2bfloat16_rn(r1);
+    part[2] = __float2bfloat16_rn(r1 - __bfloat162float(part[1]));
+    const int wpart[6] = {0, 2, 1, 0, 1, 0};
+    __nv_bfloat16* o = out + (int64_t)n * 6 * per_n + (int64_t)j * Cin_pad + c;
+#pragma unroll
+    for (int s = 0; s < 6; ++s) o[s * per_n] = part[wpart[s]];
+  }
+}
+
 int conv_gemm_f32(const float* x, const float* w, const ftb_conv_desc& d, cudaStream_t s) {
   FTB_REQUIRE(x && w, FTB_ERR_INVALID, "conv_gemm_f32: null operand");
   FTB_REQUIRE(d.B > 0 && d.S > 0 && d.N > 0 && d.ktaps > 0, FTB_ERR_INVALID, "conv_gemm_f32: bad shape");
@@ -169,6 +192,12 @@ extern "C" int ftb_pack_conv_weight(const float* w, void* out, int N, int Cin, i
   FTB_REQUIRE(w && out && N > 0 && Cin > 0 && k > 0 && Npad >= N && Cin_pad >= Cin, FTB_ERR_INVALID,
               "ftb_pack_conv_weight: bad arguments");
   const int64_t total = (int64_t)Npad * k * Cin_pad;
+  if (out_bf16 == 3) {
+    pack_conv_weight_split3_kernel<<<(int)std::min<int64_t>(cdiv(total, 256), 4096), 256, 0, (cudaStream_t)stream>>>(
+        w, (__nv_bfloat16*)out, N, Cin, k, Npad, Cin_pad);
+    FTB_CHECK_LAUNCH();
+    return FTB_OK;
+  }
   pack_conv_weight_kernel<<<(int)std::min<int64_t>(cdiv(total, 256), 4096), 256, 0, (cudaStream_t)stream>>>(
       w, out, N, Cin, k, Npad, Cin_pad, out_bf16);
   FTB_CHECK_LAUNCH();

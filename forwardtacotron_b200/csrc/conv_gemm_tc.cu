@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "epilogue.cuh"
@@ -33,6 +34,7 @@ namespace tc {
 constexpr int BM = 128, BK = 64, STAGES = 4, BN_MAX = 256, MAXP = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN_MAX * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;  // 16K + 32K
 constexpr int EPI_WARPS = 8, STG_LD = 33;
+constexpr int SPLIT_BN = 128;  // split-precision mode: tile width (two 32-column chunks per epilogue warp stay in registers)
 constexpr int SMEM_TILES = STAGES * STAGE_BYTES;                  // 196608
 constexpr int SMEM_STAGING = EPI_WARPS * 32 * STG_LD * 4;         // 33792
 constexpr int SMEM_BYTES = SMEM_TILES + SMEM_STAGING + 1024 /*alignment slack*/ + 256 /*barriers*/;
@@ -132,6 +134,9 @@ struct alignas(64) TcArgs {
   TcProb prob[tc::MAXP];
   int nprob, B, S, Cin, cblocks;
   int m_tiles, m_stride, box_rows, bn, total_tiles, pool, highway, fp16;
+  int split_in;   // A holds 3 bf16 parts [hi | mid | lo] of an fp32 tensor; K loop = 6 part products (see conv_gemm_group)
+  int split_d;    // split-precision mode: k-blocks per TMEM accumulation unit
+  int split_out;  // > 0: the 16-bit output is written as 3 parts, split_out channels apart
   int ldo, ldr, n_total;  // n_total: N of the (B,N,S) transposed output
   float out_scale;
   float* out_f32;
@@ -184,6 +189,20 @@ __device__ __forceinline__ void epi_rows(const float* sp, int nrows, const EpiCo
     const float v = epi_affine(e, sp[rr * tc::STG_LD]) * e.out_scale;
     if (OUT & 1) *o32 = v, o32 += ldo;
     if (OUT & 2) *o16 = cvt16(v, e.fp16), o16 += ldo;
+  }
+}
+// fp32 value -> three bf16 parts hi + mid + lo (8 + 8 + 8 significand bits: the fp32 value exactly), `cs` channels
+// apart: the operand format of the split-precision GEMMs of the duration predictor.
+__device__ __forceinline__ void epi_rows_split3(const float* sp, int nrows, const EpiCol& e, __nv_bfloat16* o16, int64_t ldo, int cs) {
+#pragma unroll 4
+  for (int rr = 0; rr < nrows; ++rr) {
+    const float v = epi_affine(e, sp[rr * tc::STG_LD]) * e.out_scale;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    o16[0] = hi, o16[cs] = mid, o16[2 * cs] = lo;
+    o16 += ldo;
   }
 }
 // Residual variant (a few launches per step).  The residual loads of 8 rows are issued together before they are
@@ -270,29 +289,63 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const TileCoord c = decode_tile(a, tile);
         const TcProb& P = a.prob[c.p];
-        int j = 0, cb = 0;
+        // K order = (part product, tap, 64-channel block); the packed weights follow it, so their K offset is kb * BK.
+        // split_in: product `seg` reads activation part (amap >> 4 seg) & 15 -- smallest products first:
+        // lo.hi, hi.lo, mid.mid, mid.hi, hi.mid, hi.hi  (weights packed as hi, lo, mid, hi, mid, hi)
+        const uint32_t amap = a.split_in ? 0x001102u : 0u;
+        int j = 0, cb = 0, seg = 0;
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
           const uint32_t st = it % STAGES;
           if (it >= STAGES) mbar_wait(empty0 + 8 * st, ((it / STAGES) - 1) & 1);
           const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
           mbar_expect_tx(full0 + 8 * st, tx);
-          tma_load_3d(sa, &a.map_a, full0 + 8 * st, cb * BK, c.t0 + j - P.pad_left, c.b);
-          tma_load_2d(sb, &P.map_w, full0 + 8 * st, j * a.Cin + cb * BK, c.n0);
-          if (++cb == a.cblocks) cb = 0, ++j;
+          const int acb = cb + (int)((amap >> (4 * seg)) & 15u) * a.cblocks;
+          tma_load_3d(sa, &a.map_a, full0 + 8 * st, acb * BK, c.t0 + j - P.pad_left, c.b);
+          tma_load_2d(sb, &P.map_w, full0 + 8 * st, kb * BK, c.n0);
+          if (++cb == a.cblocks) {
+            cb = 0;
+            if (++j == P.ktaps) j = 0, ++seg;
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
-      uint32_t it = 0, tl = 0;
+      uint32_t it = 0, tl = 0, un = 0;  // un: accumulation units issued (split-precision mode)
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tl) {
         const TileCoord c = decode_tile(a, tile);
         const TcProb& P = a.prob[c.p];
+        const uint32_t idesc = P.idesc;
+        if (a.split_in) {
+          // Split-precision mode: the tensor core adds into the fp32 accumulator with truncation, a bias that grows with
+          // the length of the accumulation chain (measured: 80 K-steps put the duration predictor 5x further from an
+          // fp64 evaluation than the fp32 SIMT kernel).  So the chain is cut every split_d k-blocks: each short partial
+          // sum goes to the epilogue warps through the two TMEM buffers and is added there in fp32 registers
+          // (round-to-nearest) while the next partial accumulates.
+          for (int kb = 0; kb < P.nkb; ++un) {
+            const uint32_t ub = un & 1;
+            if (un >= 2) mbar_wait(tempty0 + 8 * ub, ((un >> 1) - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_unit = tmem_base + ub * BN_MAX;
+            const int kend = min(P.nkb, kb + a.split_d);
+            for (bool first = true; kb < kend; ++kb, ++it, first = false) {
+              const uint32_t st = it % STAGES;
+              mbar_wait(full0 + 8 * st, (it / STAGES) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(d_unit, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (!first || k > 0) ? 1u : 0u);
+              umma_commit(empty0 + 8 * st);
+            }
+            umma_commit(tfull0 + 8 * ub);
+          }
+          continue;
+        }
         const uint32_t buf = tl & 1;
         if (tl >= 2) mbar_wait(tempty0 + 8 * buf, ((tl >> 1) - 1) & 1);  // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + buf * BN_MAX;
-        const uint32_t idesc = P.idesc;
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
           const uint32_t st = it % STAGES;
           mbar_wait(full0 + 8 * st, (it / STAGES) & 1);
@@ -316,7 +369,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
     const int64_t ldo = a.ldo, ldr = a.ldr;
     const float out_scale = a.out_scale;
     const int S = a.S;
-    uint32_t tl = 0;
+    uint32_t tl = 0, un = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tl) {
       const TileCoord c = decode_tile(a, tile);
       const TcProb& P = a.prob[c.p];
@@ -328,6 +381,56 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
       const int trow0 = c.t0 + q * 32;                 // time index of this warp's first accumulator row
       const int nrows = max(0, min(32, S - trow0));    // rows of this quarter inside the utterance
       const int64_t mrow0 = (int64_t)c.b * S + trow0;  // flattened (b, t) row of accumulator row 0 of the quarter
+      if (a.split_in) {
+        // split-precision mode (see the MMA issuer): add the short partial sums in registers, then a plain epilogue
+        float acc[2][32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int k = 0; k < 32; ++k) acc[i][k] = 0.f;
+        const int nunits = (P.nkb + a.split_d - 1) / a.split_d;
+        for (int u = 0; u < nunits; ++u, ++un) {
+          const uint32_t ub = un & 1;
+          mbar_wait(tfull0 + 8 * ub, (un >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t r[2][32];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (half + 2 * i < nchunks) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ub * BN_MAX + (half + 2 * i) * 32, r[i]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) mbar_arrive(tempty0 + 8 * ub);  // the buffer is free as soon as it sits in registers
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (half + 2 * i < nchunks) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) acc[i][k] += __uint_as_float(r[i][k]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int ch = half + 2 * i;
+          if (ch >= nchunks) continue;
+          const int n = c.n0 + ch * 32 + lane;
+          const bool nok = n < pN;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) stg[lane * STG_LD + k] = acc[i][k];
+          __syncwarp();
+          EpiCol e;
+          e.bias = (nok && P.bias) ? __ldg(P.bias + n) : 0.f;
+          e.scale = (nok && P.scale) ? __ldg(P.scale + n) : 1.f;
+          e.shift = (nok && P.shift) ? __ldg(P.shift + n) : 0.f;
+          e.relu_lo = relu_lo;
+          e.out_scale = out_scale;
+          e.fp16 = false;
+          const int64_t ooff = mrow0 * ldo + P.n_offset + n;
+          const int nr = nok ? nrows : 0;
+          if (a.split_out) epi_rows_split3(stg + lane, nr, e, a.out_bf16 + ooff, ldo, a.split_out);
+          else epi_rows<1>(stg + lane, nr, e, a.out_f32 + ooff, nullptr, ldo);
+          __syncwarp();
+        }
+        continue;
+      }
       mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       bool released = false;
@@ -500,13 +603,24 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.Cin = Cin;
   a.cblocks = Cin / BK;
   a.pool = o.pool ? 1 : 0;
+  a.split_in = o.split_in ? 1 : 0;
+  a.split_out = o.split_out;
+  static const int split_d = getenv("FTB_SPLIT_D") ? std::max(1, atoi(getenv("FTB_SPLIT_D"))) : 2;
+  a.split_d = split_d;
+  FTB_REQUIRE(!(o.split_in || o.split_out) || (!o.fp16 && !o.pool && !o.highway && !o.res_f32 && !o.res_bf16 && !o.out_t),
+              FTB_ERR_INVALID, "conv_gemm_bf16: split-precision mode is plain bf16, row-major, no residual");
+  FTB_REQUIRE(!o.split_out || (o.split_in && o.out_bf16 && !o.out_f32), FTB_ERR_INVALID,
+              "conv_gemm_bf16: split output is 16-bit only and needs split input");
+  FTB_REQUIRE(!o.split_in || o.split_out || (o.out_f32 && !o.out_bf16), FTB_ERR_INVALID,
+              "conv_gemm_bf16: split-precision mode writes either fp32 or three bf16 parts");
+  FTB_REQUIRE(!o.split_in || lda >= 3 * Cin, FTB_ERR_INVALID, "conv_gemm_bf16: split input needs lda >= 3 Cin");
   a.highway = o.highway ? 1 : 0;
   a.fp16 = o.fp16 ? 1 : 0;
 
   a.m_stride = o.pool ? BM - 1 : BM;
   a.m_tiles = cdiv(S, a.m_stride);
   a.box_rows = BM;  // the box may exceed the tensor: rows outside [0,S) are zero-filled (conv padding, pool halo)
-  a.bn = tc_tile_n(items[0].N);
+  a.bn = o.split_in ? SPLIT_BN : tc_tile_n(items[0].N);
   a.ldo = o.ldo;
   a.ldr = o.ldr;
   a.out_scale = o.out_scale == 0.f ? 1.f : o.out_scale;
@@ -519,7 +633,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   FTB_REQUIRE(!o.out_t || n_items == 1, FTB_ERR_INVALID, "conv_gemm_bf16: transposed output needs a single problem");
   FTB_REQUIRE(!(o.out_t && o.fp16 && o.res_bf16), FTB_ERR_INVALID, "conv_gemm_bf16: fp16 residual with transposed output");
   {
-    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)S, (cuuint64_t)B};
+    cuuint64_t dims[3] = {(cuuint64_t)(o.split_in ? 3 * Cin : Cin), (cuuint64_t)S, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)lda * 2, (cuuint64_t)S * lda * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)a.box_rows, 1};
     FTB_TRY(make_map(&a.map_a, x, 3, dims, strides, box));
@@ -533,8 +647,8 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
     const TcItem& it = items[order[i]];
     TcProb& P = a.prob[i];
     FTB_REQUIRE(it.w && it.N > 0 && it.ktaps > 0 && ((uintptr_t)it.w & 15) == 0, FTB_ERR_INVALID, "conv_gemm_bf16: bad problem");
-    FTB_REQUIRE(tc_tile_n(it.N) == a.bn, FTB_ERR_INVALID, "conv_gemm_group: mixed tile widths");
-    const int ktot = it.ktaps * Cin;
+    FTB_REQUIRE(o.split_in || tc_tile_n(it.N) == a.bn, FTB_ERR_INVALID, "conv_gemm_group: mixed tile widths");
+    const int ktot = (o.split_in ? 6 : 1) * it.ktaps * Cin;
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)it.N};  // rows >= N of the last tile are zero-filled by TMA
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)a.bn};
@@ -549,7 +663,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
     P.n_offset = it.n_offset;
     P.relu = it.relu;
     P.n_tiles = cdiv(it.N, a.bn);
-    P.nkb = it.ktaps * a.cblocks;
+    P.nkb = (o.split_in ? 6 : 1) * it.ktaps * a.cblocks;
     P.tile_begin = tiles;
     P.idesc = idesc_16(it.N >= a.bn ? a.bn : (int)align_up(it.N, 16), o.fp16);
     tiles += P.n_tiles * a.m_tiles * B;

@@ -19,6 +19,24 @@ __global__ void embed_kernel(const int64_t* __restrict__ tok, const float* __res
   }
 }
 
+// embedding rows as three bf16 parts [hi | mid | lo] (rows, 3C): operand of the split-precision duration predictor
+__global__ void embed_split3_kernel(const int64_t* __restrict__ tok, const float* __restrict__ table,
+                                    __nv_bfloat16* __restrict__ out, int64_t rows, int C, int num_chars) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i % C);
+    int64_t id = tok[r];
+    id = id < 0 ? 0 : (id >= num_chars ? num_chars - 1 : id);
+    const float v = table[id * C + c];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    __nv_bfloat16* o = out + r * 3 * C + c;
+    o[0] = hi, o[C] = mid, o[2 * C] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+  }
+}
+
 // ---- MaxPool1d(2,1,1)[:S] along t on channel-last data, in place (common_layers.py:73,100) --
 // out[t] = max(in[t-1], in[t]), out[0] = in[0].  One thread per (b, 8-channel group) walks t
 // downward so the in-place update never reads an overwritten value.
@@ -195,6 +213,12 @@ int embed(const int64_t* tok, const float* table, T* out, int64_t rows, int C, i
           cudaStream_t s) {
   ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   embed_kernel<T><<<ew_blocks(rows * C), 256, 0, s>>>(tok, table, out, rows, C, ldo, num_chars);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+int embed_split3(const int64_t* tok, const float* table, __nv_bfloat16* out, int64_t rows, int C, int num_chars, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
+  embed_split3_kernel<<<ew_blocks(rows * C), 256, 0, s>>>(tok, table, out, rows, C, num_chars);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }

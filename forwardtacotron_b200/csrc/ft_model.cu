@@ -23,6 +23,7 @@ struct SeriesW {  // SeriesPredictor, models/forward_tacotron.py:14-55
   const float* lin_w = nullptr;
   const float* lin_b = nullptr;
   bool f32_only = false;
+  bool tc_split = false;  // f32_only predictor whose GEMMs run split-precision on the tensor cores (fp32-grade)
 };
 
 struct CbhgW {  // CBHG, models/common_layers.py:55-119
@@ -53,6 +54,7 @@ struct ftb_ft_handle : ftb::ModelBase {
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   int opt_overlap_prenet = 0, opt_serialize = 0;
+  int opt_dur_simt = getenv("FTB_DUR_SIMT") ? atoi(getenv("FTB_DUR_SIMT")) : 0;  // 1: duration predictor on the fp32 SIMT kernel
   char* pre_buf = nullptr;
   int64_t pre_cap = 0;
   const int64_t* pre_tok = nullptr;
@@ -78,13 +80,17 @@ static int build_series(ftb_ft_handle* h, SeriesW& P, const std::string& p, int 
   P.H = H;
   P.f32_only = f32_only;
   const bool w16 = h->bf16_mode() && !f32_only, w32 = !w16;
+  // the fp32-exact predictor of a 16-bit mode: split-precision tensor-core GEMMs (fp32 SIMT stays packed as the
+  // FTB_OPT_DUR_SIMT / all-fp32 path)
+  const bool split = f32_only && h->bf16_mode() && C % 64 == 0 && E % 64 == 0;
+  P.tc_split = split;
   FTB_TRY(h->get(p + ".embedding.weight", {h->cfg.num_chars, E}, &P.emb));
   for (int i = 0; i < 3; ++i) {
     const std::string c = p + ".convs." + std::to_string(i);
-    FTB_TRY(h->make_conv(P.conv[i], c + ".conv.weight", C, i ? C : E, 5, 2, true, c + ".bnorm", "", w32, w16));
+    FTB_TRY(h->make_conv(P.conv[i], c + ".conv.weight", C, i ? C : E, 5, 2, true, c + ".bnorm", "", w32, w16, split));
   }
   FTB_REQUIRE(H == 64 || H == 128, FTB_ERR_UNSUPPORTED, "%s.rnn: hidden size %d not built (64, 128)", p.c_str(), H);
-  FTB_TRY(h->make_rnn(P.rnn, p + ".rnn", C, H, false, w32, w16));
+  FTB_TRY(h->make_rnn(P.rnn, p + ".rnn", C, H, false, w32, w16, split));
   FTB_TRY(h->get(p + ".lin.weight", {1, 2 * H}, &P.lin_w));
   FTB_TRY(h->get(p + ".lin.bias", {1}, &P.lin_b));
   return FTB_OK;
@@ -164,9 +170,10 @@ template <typename T>
 static SeriesBufs<T> plan_series(Arena& A, const SeriesW& P, int B, int Tn) {
   SeriesBufs<T> w;
   const int64_t M = (int64_t)B * Tn;
-  w.emb = A.take<T>(M * P.E);
-  w.a = A.take<T>(M * P.C);
-  w.b = A.take<T>(M * P.C);
+  const int64_t grow = (P.tc_split && sizeof(T) == 4) ? 2 : 1;  // split parts: 3 x bf16 = 6 bytes per element
+  w.emb = A.take<T>(M * P.E * grow);
+  w.a = A.take<T>(M * P.C * grow);
+  w.b = A.take<T>(M * P.C * grow);
   w.xg = A.take<float>(M * 6 * P.H);
   w.ro = A.take<float>(M * 2 * P.H);
   return w;
@@ -201,6 +208,19 @@ static int run_series(ftb_ft_handle* h, SeriesW& P, const int64_t* tok, int B, i
   SeriesBufs<T> w = plan_series<T>(A, P, B, Tn);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for SeriesPredictor");
   const int64_t M = (int64_t)B * Tn;
+  if (std::is_same<T, float>::value && P.tc_split && !h->opt_dur_simt) {
+    bf16 *e3 = (bf16*)w.emb, *a3 = (bf16*)w.a, *b3 = (bf16*)w.b;
+    FTB_TRY(embed_split3(tok, P.emb, e3, M, P.E, h->cfg.num_chars, s));
+    FTB_TRY(h->gemm_split(P.conv[0], e3, B, Tn, nullptr, 0, a3, s));
+    FTB_TRY(h->gemm_split(P.conv[1], a3, B, Tn, nullptr, 0, b3, s));
+    FTB_TRY(h->gemm_split(P.conv[2], b3, B, Tn, nullptr, 0, a3, s));
+    FTB_TRY(h->gemm_split(P.rnn.in, a3, B, Tn, w.xg, 6 * P.H, nullptr, s));
+    FTB_TRY(rnn_bidir(w.xg, P.rnn.w_hh, P.rnn.b_hn, w.ro, B, Tn, P.H, 0, 0, s));
+    FTB_TRY(head1<float>(w.ro, P.lin_w, P.lin_b, alpha, out, M, 2 * P.H, s));
+    h->launches += 3;
+    A.reset(mark);
+    return FTB_OK;
+  }
   FTB_TRY(embed<T>(tok, P.emb, w.emb, M, P.E, P.E, h->cfg.num_chars, s));
   FTB_TRY(h->gemm<T>(P.conv[0], w.emb, P.E, B, Tn, act_out(w.a, P.C), nullptr, 0, 1.f, s));
   FTB_TRY(h->gemm<T>(P.conv[1], w.a, P.C, B, Tn, act_out(w.b, P.C), nullptr, 0, 1.f, s));
@@ -454,6 +474,10 @@ extern "C" int ftb_ft_set_option(ftb_ft_handle* h, int option, int value) {
   if (option == FTB_OPT_OVERLAP_PRENET) {
     h->opt_overlap_prenet = value != 0;
     if (!value) h->pre_valid = false;
+    return FTB_OK;
+  }
+  if (option == FTB_OPT_DUR_SIMT) {
+    h->opt_dur_simt = value != 0;
     return FTB_OK;
   }
   if (option == FTB_OPT_SERIALIZE) {

@@ -26,6 +26,9 @@ struct TcOut {
   float out_scale = 1.f;
   bool pool = false;
   bool fp16 = false;     // the 16-bit operands / outputs / residual are IEEE half instead of bfloat16
+  bool split_in = false;  // x is (B,S,3*Cin): bf16 parts hi | mid | lo of an fp32 tensor, weights packed by pack mode 3:
+                          // 6 part products with fp32 accumulation = fp32-grade result on the tensor cores
+  int split_out = 0;      // > 0: write the 16-bit output as 3 parts, split_out channels apart (ldo >= 3 * split_out)
   bool highway = false;  // N = 2C interleaved [32 x1 | 32 x2] groups -> y (C) = sigmoid(x2) relu(x1) + (1 - sigmoid(x2)) res_bf16
 };
 int tc_tile_n(int N);
@@ -43,6 +46,7 @@ int attention(const T* qkv, const int64_t* tokens_for_mask, T* ctx, int B, int S
 // elementwise.cu
 template <typename T>
 int embed(const int64_t* tok, const float* table, T* out, int64_t rows, int C, int ldo, int num_chars, cudaStream_t s);
+int embed_split3(const int64_t* tok, const float* table, __nv_bfloat16* out, int64_t rows, int C, int num_chars, cudaStream_t s);
 template <typename T>
 int maxpool_inplace(T* x, int B, int S, int C, cudaStream_t s);
 template <typename T>

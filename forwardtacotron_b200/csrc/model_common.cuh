@@ -16,6 +16,7 @@ struct Layer {
   int N = 0, Cin = 0, CinP = 0, k = 1, pad = 0, relu = 0;
   float* w32 = nullptr;
   bf16* w16 = nullptr;
+  bf16* w16s = nullptr;  // split-precision copy (ftb_pack_conv_weight mode 3): (N, 6, k, CinP) bf16
   float* bias = nullptr;
   float* scale = nullptr;
   float* shift = nullptr;
@@ -82,7 +83,7 @@ struct ModelBase {
 
   // conv weight (N,Cin,k) [+ BatchNorm `bn` prefix] [+ bias] -> Layer
   int make_conv(Layer& L, const std::string& wname, int N, int Cin, int k, int pad, bool relu, const std::string& bn,
-                const std::string& bias, bool want32, bool want16) {
+                const std::string& bias, bool want32, bool want16, bool want_split = false) {
     L.N = N;
     L.Cin = Cin;
     L.CinP = (int)align_up(Cin, 64);
@@ -104,6 +105,11 @@ struct ModelBase {
       L.w16 = dalloc<bf16>(n);
       FTB_REQUIRE(L.w16, FTB_ERR_CUDA, "out of device memory packing %s", wname.c_str());
       FTB_TRY(ftb_pack_conv_weight(w, L.w16, N, Cin, k, N, L.CinP, pack16, prep));
+    }
+    if (want_split) {
+      L.w16s = dalloc<bf16>(6 * n);
+      FTB_REQUIRE(L.w16s, FTB_ERR_CUDA, "out of device memory packing %s", wname.c_str());
+      FTB_TRY(ftb_pack_conv_weight(w, L.w16s, N, Cin, k, N, L.CinP, 3, prep));
     }
     if (!bn.empty()) {
       const float *g, *b, *m, *v;
@@ -127,7 +133,7 @@ struct ModelBase {
   }
 
   // torch.nn.GRU / nn.LSTM (1 layer, bidirectional) under prefix p -> Rnn
-  int make_rnn(Rnn& R, const std::string& p, int in, int H, bool lstm, bool want32, bool want16) {
+  int make_rnn(Rnn& R, const std::string& p, int in, int H, bool lstm, bool want32, bool want16, bool want_split = false) {
     const int G = lstm ? 4 : 3;
     R.H = H;
     R.lstm = lstm;
@@ -139,6 +145,8 @@ struct ModelBase {
     const int64_t per_dir = (int64_t)G * H * L.CinP;
     if (want32) L.w32 = dalloc<float>(2 * per_dir);
     if (want16) L.w16 = dalloc<bf16>(2 * per_dir);
+    if (want_split) L.w16s = dalloc<bf16>(12 * per_dir);
+    FTB_REQUIRE(!want_split || L.w16s, FTB_ERR_CUDA, "out of device memory packing %s", p.c_str());
     L.bias = dalloc<float>(2 * G * H);
     R.w_hh = dalloc<float>((int64_t)2 * G * H * H);
     R.b_hn = lstm ? nullptr : dalloc<float>(2 * H);
@@ -153,6 +161,7 @@ struct ModelBase {
       FTB_TRY(get(p + ".bias_hh_l0" + sfx, {G * H}, &b_hh));
       if (want32) FTB_TRY(ftb_pack_conv_weight(w_ih, L.w32 + d * per_dir, G * H, in, 1, G * H, L.CinP, 0, prep));
       if (want16) FTB_TRY(ftb_pack_conv_weight(w_ih, L.w16 + d * per_dir, G * H, in, 1, G * H, L.CinP, pack16, prep));
+      if (want_split) FTB_TRY(ftb_pack_conv_weight(w_ih, L.w16s + 6 * d * per_dir, G * H, in, 1, G * H, L.CinP, 3, prep));
       // b_hh folds into the input projection for every gate except the GRU n gate
       FTB_TRY(rnn_bias(b_ih, b_hh, L.bias + d * G * H, G * H, lstm ? G * H : 2 * H, prep));
       FTB_TRY(copy_f32(w_hh, R.w_hh + (int64_t)d * G * H * H, (int64_t)G * H * H, prep));
@@ -215,6 +224,35 @@ struct ModelBase {
     to.out_scale = out_scale;
     to.fp16 = std::is_same<T, f16>::value;
     return conv_gemm_group((const bf16*)x, lda, B, S, L.CinP, &it, 1, to, s);
+  }
+
+  // fp32-grade conv / linear on the tensor cores (duration predictor): x holds the three bf16 parts of an fp32
+  // activation, (B,S,3*CinP); the result goes out either as fp32 (out32, ld = ldo) or again as three parts
+  // (out_split, (B,S,3*N)).  6 part products accumulate in fp32 in TMEM, smallest first (conv_gemm_tc.cu).
+  int gemm_split(const Layer& L, const bf16* x, int B, int S, float* out32, int ldo, bf16* out_split, cudaStream_t s) {
+    FTB_REQUIRE(L.w16s, FTB_ERR_INVALID, "layer has no split-precision weights packed");
+    TcItem it;
+    it.w = L.w16s;
+    it.N = L.N;
+    it.ktaps = L.k;
+    it.pad_left = L.pad;
+    it.relu = L.relu;
+    it.bias = L.bias;
+    it.scale = L.scale;
+    it.shift = L.shift;
+    TcOut o;
+    o.split_in = true;
+    if (out_split) {
+      o.out_bf16 = out_split;
+      o.ldo = 3 * L.N;
+      o.split_out = L.N;
+    } else {
+      o.out_f32 = out32;
+      o.ldo = ldo;
+    }
+    ++launches;
+    ProfScope prof(FAM_GEMM_TC, 2.0 * B * S * (double)L.N * L.k * L.Cin, 0.0, s);
+    return conv_gemm_group(x, 3 * L.CinP, B, S, L.CinP, &it, 1, o, s);
   }
 
   // One highway layer on the tensor cores: L packs W1/W2 interleaved in groups of 32 rows (pack_highway), the

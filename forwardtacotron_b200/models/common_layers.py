@@ -183,6 +183,17 @@ class NativeModel(nn.Module):
             _lib.check(lib.ftb_tune(_lib.FTB_TUNE_LSTM_MIN_CHUNK, 32))
         return out
 
+    def lane_streams(self, device, n: int):
+        """``n`` long-lived CUDA streams for batches in flight.  Lanes are keyed by stream, so callers that overlap
+        batches must reuse these instead of creating streams per call (each new stream would cost a packed weight
+        copy and a workspace)."""
+        device = torch.device(device)
+        pool = self.__dict__.setdefault('_stream_pool', {})
+        have = pool.setdefault(device.index or 0, [])
+        while len(have) < n:
+            have.append(torch.cuda.Stream(device))
+        return have[:n]
+
     def _get_workspace(self, nbytes: int, device: torch.device) -> torch.Tensor:
         lane = self._lanes[self._lane_key(device)]
         ws = lane['ws']

@@ -143,7 +143,11 @@ def synthesize_corpus(model, utterances: Sequence[Sequence[int]], alpha: float =
     mine = shard_for_rank(bucket_by_length(utterances, max_tokens, max_batch), rank, world)
     on_gpu = torch.device(device).type == 'cuda'
     n_streams = max(1, min(int(in_flight), len(mine))) if on_gpu else 1
-    streams = [torch.cuda.Stream(device) for _ in range(n_streams)] if n_streams > 1 else [None]
+    if n_streams > 1:  # the model's own long-lived streams: one native lane (packed weights, workspace) per stream
+        streams = (model.lane_streams(device, n_streams) if hasattr(model, 'lane_streams')
+                   else [torch.cuda.Stream(device) for _ in range(n_streams)])
+    else:
+        streams = [None]
     if n_streams > 1:
         here = torch.cuda.current_stream(device)
         for s in streams:

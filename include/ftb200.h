@@ -146,7 +146,8 @@ int ftb_conv_bank_bf16(const void* x, const void* const* w_packed, const ftb_con
  * this returns how many waits gave up since the library was loaded (0 in a healthy run). */
 int ftb_tc_timeout_count(void);
 /* Pack a reference-layout conv weight (N, Cin, k) f32 into (Npad, k*Cin_pad) K-major
- * f32 (out_bf16 = 0), bf16 (1) or IEEE half (2), zero padded. */
+ * f32 (out_bf16 = 0), bf16 (1) or IEEE half (2), zero padded.  Mode 3: (Npad, 6, k, Cin_pad) bf16, the K axis of the
+ * split-precision GEMM (three bf16 parts per weight, arranged for the six part products). */
 int ftb_pack_conv_weight(const float* w, void* out, int N, int Cin, int k, int Npad, int Cin_pad,
                          int out_bf16, void* stream);
 
@@ -224,6 +225,11 @@ int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, int T, float 
 /* FTB_OPT_SERIALIZE (default 0): run every launch on the caller's stream, one after the other (no side streams, no
  * prenet prefetch).  For profiling: per-launch CUDA-event timings are kernel durations only when nothing overlaps. */
 #define FTB_OPT_SERIALIZE 2
+/* FTB_OPT_DUR_SIMT (default 0; env FTB_DUR_SIMT): in the 16-bit modes the duration predictor -- whose rounded output
+ * must be bit-exact -- runs its convs / GRU input projection as split-precision tensor-core GEMMs: every fp32 operand
+ * is carried as three bf16 parts (hi + mid + lo = the fp32 value), six part products accumulate in fp32.  1 = use the
+ * fp32 SIMT GEMM instead (the all-fp32 gemm_mode 1 always does). */
+#define FTB_OPT_DUR_SIMT 3
 int ftb_ft_set_option(ftb_ft_handle* h, int option, int value);
 
 /* Between the stages the Python callbacks pitch_function / energy_function run

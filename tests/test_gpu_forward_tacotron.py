@@ -184,3 +184,40 @@ def test_concurrent_streams_match_single_stream():
     for a, b in zip(ref, outs):
         for k in ('mel', 'mel_post', 'dur', 'mel_len'):
             assert torch.equal(a[k], b[k]), k
+
+
+def _dur_truth_fp64(sd, x):
+    """The reference's duration predictor (forward_tacotron.py:44-55) evaluated in float64."""
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    p = 'dur_pred'
+    v = sd64[p + '.embedding.weight'][x].transpose(1, 2)
+    for i in range(3):
+        v = mo.conv_relu_bn(sd64, f'{p}.convs.{i}', v, relu=True)
+    v = mo.rnn_explicit(sd64, p + '.rnn', v.transpose(1, 2), 'gru')
+    return (v @ sd64[p + '.lin.weight'].T + sd64[p + '.lin.bias']).squeeze(-1)
+
+
+def test_duration_predictor_split_precision_is_fp32_grade():
+    """The duration predictor's GEMMs run on the tensor cores with every fp32 operand carried as three bf16 parts
+    (FTB_OPT_DUR_SIMT = 0, the default).  Against a float64 evaluation of the reference algorithm it must be no
+    further off than fp32 arithmetic itself is: the fp32 SIMT kernel and the fp32 CPU oracle are the yardsticks."""
+    from forwardtacotron_b200 import _lib
+    model, _ = cuda_model('forward_tacotron', 0)
+    sd = cpu_state_dict(model)
+    x = synth.synthetic_tokens(24, 160, seed=9)
+    truth = _dur_truth_fp64(sd, x)
+    cpu32 = mo.ft_series_predictor(sd, 'dur_pred', x).squeeze(-1)
+    h = model._get_handle(torch.device('cuda', 0))
+    got = {}
+    try:
+        for name, simt in (('split', 0), ('simt', 1)):
+            _lib.check(_lib.lib().ftb_ft_set_option(h, _lib.FTB_OPT_DUR_SIMT, simt))
+            got[name] = model.run_series_predictor('dur_pred', x.cuda()).squeeze(-1).cpu()
+    finally:
+        _lib.check(_lib.lib().ftb_ft_set_option(h, _lib.FTB_OPT_DUR_SIMT, 0))
+    e = {k: (v.double() - truth).abs() for k, v in dict(got, cpu32=cpu32).items()}
+    print({k: (float(v.max()), float(v.mean())) for k, v in e.items()})
+    assert float(e['split'].mean()) <= 1.5 * float(e['cpu32'].mean()) and float(e['split'].max()) <= 2e-5
+    assert not torch.equal(got['split'], got['simt'])            # the two paths really are different kernels
+    flips = rounded(got['split']) != rounded(cpu32)
+    assert bool((near_tie_mask(cpu32) | ~flips).all()) and int(flips.sum()) <= 1
