@@ -228,6 +228,37 @@ __device__ __forceinline__ void epi_rows_res(const float* sp, int nrows, const E
     }
   }
 }
+// Residual rows of one 32 x 32 chunk (lane = column), loaded ahead of use: the epilogue issues them BEFORE it waits
+// for the accumulator (and for the following chunk before it works on the current one), so their L2 / HBM latency
+// hides behind the MMAs instead of stalling every chunk.
+template <int RES /*1 f32, 2 16-bit*/>
+__device__ __forceinline__ void load_res_rows(float (&res)[32], const float* r32, const __nv_bfloat16* r16, int64_t ldr,
+                                              int nrows, bool fp16) {
+  if (RES == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) res[j] = j < nrows ? __ldg(r32 + j * ldr) : 0.f;
+  } else {
+    unsigned short raw[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) raw[j] = j < nrows ? __ldg(reinterpret_cast<const unsigned short*>(r16) + j * ldr) : (unsigned short)0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const __nv_bfloat16 b = __ushort_as_bfloat16(raw[j]);
+      res[j] = ld16(b, fp16);
+    }
+  }
+}
+__device__ __forceinline__ void epi_rows_preres(const float* sp, int nrows, const EpiCol& e, float* o32, __nv_bfloat16* o16,
+                                                bool has_o32, bool has_o16, int64_t ldo, const float (&res)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < nrows) {
+      const float v = (epi_affine(e, sp[j * tc::STG_LD]) + res[j]) * e.out_scale;
+      if (has_o32) o32[j * ldo] = v;
+      if (has_o16) o16[j * ldo] = cvt16(v, e.fp16);
+    }
+  }
+}
 template <int OUT>
 __device__ __forceinline__ void epi_rows_pool(const float* sp, int nrows, const EpiCol& e, float prev, bool first_is_halo,
                                               int trow0, float* o32, __nv_bfloat16* o16, int64_t ldo) {
@@ -244,7 +275,12 @@ __device__ __forceinline__ void epi_rows_pool(const float* sp, int nrows, const 
   }
 }
 
+// MODE: 0 generic epilogue (bias / ReLU / BN affine / residual / pool / transposed output), 1 highway, 2 split
+// precision.  Separate instantiations because the kernel sits at its register cap (10 warps -> 3 per scheduler ->
+// 168 registers per thread): every mode only carries its own epilogue state.
+template <int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcArgs a) {
+  constexpr bool HIGHWAY = MODE == 1, SPLIT = MODE == 2;
   using namespace tc;
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B tiles need 1024-byte alignment (offset arithmetic keeps the pointer in the shared space)
@@ -292,7 +328,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         // K order = (part product, tap, 64-channel block); the packed weights follow it, so their K offset is kb * BK.
         // split_in: product `seg` reads activation part (amap >> 4 seg) & 15 -- smallest products first:
         // lo.hi, hi.lo, mid.mid, mid.hi, hi.mid, hi.hi  (weights packed as hi, lo, mid, hi, mid, hi)
-        const uint32_t amap = a.split_in ? 0x001102u : 0u;
+        const uint32_t amap = SPLIT ? 0x001102u : 0u;
         int j = 0, cb = 0, seg = 0;
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
           const uint32_t st = it % STAGES;
@@ -316,7 +352,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         const TileCoord c = decode_tile(a, tile);
         const TcProb& P = a.prob[c.p];
         const uint32_t idesc = P.idesc;
-        if (a.split_in) {
+        if (SPLIT) {
           // Split-precision mode: the tensor core adds into the fp32 accumulator with truncation, a bias that grows with
           // the length of the accumulation chain (measured: 80 K-steps put the duration predictor 5x further from an
           // fp64 evaluation than the fp32 SIMT kernel).  So the chain is cut every split_d k-blocks: each short partial
@@ -381,7 +417,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
       const int trow0 = c.t0 + q * 32;                 // time index of this warp's first accumulator row
       const int nrows = max(0, min(32, S - trow0));    // rows of this quarter inside the utterance
       const int64_t mrow0 = (int64_t)c.b * S + trow0;  // flattened (b, t) row of accumulator row 0 of the quarter
-      if (a.split_in) {
+      if (SPLIT) {
         // split-precision mode (see the MMA issuer): add the short partial sums in registers, then a plain epilogue
         float acc[2][32];
 #pragma unroll
@@ -393,19 +429,24 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
           const uint32_t ub = un & 1;
           mbar_wait(tfull0 + 8 * ub, (un >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          uint32_t r[2][32];
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
-            if (half + 2 * i < nchunks) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ub * BN_MAX + (half + 2 * i) * 32, r[i]);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if (lane == 0) mbar_arrive(tempty0 + 8 * ub);  // the buffer is free as soon as it sits in registers
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
+          for (int i = 0; i < 2; ++i) {
             if (half + 2 * i < nchunks) {
+              uint32_t r[32];
+              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ub * BN_MAX + (half + 2 * i) * 32, r);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              if (i == 1 || half + 2 >= nchunks) {  // last read of this unit: the buffer is free once it sits in registers
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) mbar_arrive(tempty0 + 8 * ub);
+              }
 #pragma unroll
-              for (int k = 0; k < 32; ++k) acc[i][k] += __uint_as_float(r[i][k]);
+              for (int k = 0; k < 32; ++k) acc[i][k] += __uint_as_float(r[k]);
             }
+          }
+          if (half >= nchunks) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) mbar_arrive(tempty0 + 8 * ub);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -431,10 +472,32 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         }
         continue;
       }
+      // operands of the epilogue that do not depend on the accumulator are fetched while the MMAs still run
+      uint4 xin_next[4];
+      float res_next[32];
+      const bool pre_res = (has_r16 || has_r32) && row_major && !pool && !HIGHWAY;
+#define FTB_LOAD_HW_RES(pr)                                                                                             \
+  if (lane < nrows) {                                                                                                   \
+    const uint4* xr = reinterpret_cast<const uint4*>(a.res_bf16 + (mrow0 + lane) * ldr + (c.n0 >> 1) + (pr) * 32);      \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) xin_next[i] = __ldg(xr + i);                                          \
+  }
+#define FTB_LOAD_RES(ch)                                                                                                \
+  {                                                                                                                     \
+    const int n_ = c.n0 + (ch) * 32 + lane;                                                                             \
+    const int nr_ = (n_ < pN) ? nrows : 0;                                                                              \
+    if (has_r16) load_res_rows<2>(res_next, nullptr, a.res_bf16 + mrow0 * ldr + n_, ldr, nr_, a.fp16 != 0);             \
+    else load_res_rows<1>(res_next, a.res_f32 + mrow0 * ldr + n_, nullptr, ldr, nr_, false);                            \
+  }
+      if (HIGHWAY) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xin_next[i] = make_uint4(0, 0, 0, 0);
+        if (half < (nchunks >> 1)) FTB_LOAD_HW_RES(half)
+      }
+      if (pre_res && half < nchunks) FTB_LOAD_RES(half)
       mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       bool released = false;
-      if (a.highway) {
+      if (HIGHWAY) {
         // Highway layer (models/common_layers.py:30-35): columns come in groups of 64 = [32 x (W1 x + b1) | 32 x (W2 x + b2)]
         // of the SAME 32 channels (weights interleaved at pack time); y = g relu(x1) + (1 - g) x, g = sigmoid(x2),
         // is formed in the accumulator layout (thread = row), then transposed for the coalesced bf16 store.
@@ -451,12 +514,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
             released = true;
           }
           const int nb1 = c.n0 + pr * 64, oc0 = (c.n0 >> 1) + pr * 32;  // GEMM column of x1[0], output channel 0 of the pair
-          uint4 xin[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-          if (lane < nrows) {
-            const uint4* xr = reinterpret_cast<const uint4*>(a.res_bf16 + (mrow0 + lane) * ldr + oc0);
+          uint4 xin[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) xin[i] = __ldg(xr + i);
-          }
+          for (int i = 0; i < 4; ++i) xin[i] = xin_next[i];
+          if (pr + 2 < npairs) FTB_LOAD_HW_RES(pr + 2)  // in flight during this pair's gate maths
           const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xin);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -473,7 +534,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
           __syncwarp();
         }
       }
-      for (int ch = half; ch < (a.highway ? 0 : nchunks); ch += 2) {
+      for (int ch = half; ch < (HIGHWAY ? 0 : nchunks); ch += 2) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX + ch * 32, r);
         const int nb = c.n0 + ch * 32;  // first output column of the chunk
@@ -517,9 +578,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
           __nv_bfloat16* o16 = a.out_bf16 + ooff;
           const float* sp = stg + lane;
           if (!pool) {
-            if (has_r16) epi_rows_res<2>(sp, nr, e, o32, o16, has_o32, has_o16, ldo, nullptr, a.res_bf16 + mrow0 * ldr + n, ldr);
-            else if (has_r32) epi_rows_res<1>(sp, nr, e, o32, o16, has_o32, has_o16, ldo, a.res_f32 + mrow0 * ldr + n, nullptr, ldr);
-            else if (has_o16 && !has_o32) epi_rows<2>(sp, nr, e, o32, o16, ldo);
+            if (pre_res) {
+              epi_rows_preres(sp, nr, e, o32, o16, has_o32, has_o16, ldo, res_next);
+              if (ch + 2 < nchunks) FTB_LOAD_RES(ch + 2)  // (no second register set: the kernel sits at the 168-register cap)
+            } else if (has_o16 && !has_o32) epi_rows<2>(sp, nr, e, o32, o16, ldo);
             else if (has_o32 && !has_o16) epi_rows<1>(sp, nr, e, o32, o16, ldo);
             else epi_rows<3>(sp, nr, e, o32, o16, ldo);
           } else {  // out[t] = max(v[t-1], v[t]); tile row 0 is the halo row t0 = first output row - 1
@@ -671,11 +733,15 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.total_tiles = tiles;
   static bool configured = false;
   if (!configured) {
-    FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   const int grid = std::min(tiles, sm_count());
-  conv_gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(a);
+  if (o.highway) conv_gemm_tc_kernel<1><<<grid, THREADS, SMEM_BYTES, s>>>(a);
+  else if (o.split_in) conv_gemm_tc_kernel<2><<<grid, THREADS, SMEM_BYTES, s>>>(a);
+  else conv_gemm_tc_kernel<0><<<grid, THREADS, SMEM_BYTES, s>>>(a);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }

@@ -20,6 +20,7 @@
 // 128 x 512 tile by a <= 32-column operand and is bound by latency, not MMA throughput.
 #include <cooperative_groups.h>
 
+#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -369,6 +370,10 @@ static int launch_rnn_cluster(const float* xg, const float* w_hh, const float* b
 
 // Utterances per cluster: the smallest chunk whose cluster count still fits on the GPU in ONE wave
 // (the clusters are independent, so a second wave would double the latency of the whole recurrence).
+// FTB_TUNE_GRU_MIN_CHUNK raises the smallest chunk: fewer clusters hold fewer SMs for the whole recurrence at a
+// somewhat longer step (mma.sync cost grows with the column count) -- the throughput setting when several
+// batches are in flight (include/ftb200.h).
+std::atomic<int> g_gru_min_chunk{getenv("FTB_GRU_MIN_CHUNK") ? atoi(getenv("FTB_GRU_MIN_CHUNK")) : 8};
 template <int G, int H, int CL>
 static int dispatch_bc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
                        cudaStream_t s) {
@@ -376,7 +381,9 @@ static int dispatch_bc(const float* xg, const float* w_hh, const float* b_hn, vo
   FTB_TRY((launch_rnn_cluster<G, H, CL, 8>(nullptr, nullptr, nullptr, nullptr, B, S, 0, s, &m8)));
   FTB_TRY((launch_rnn_cluster<G, H, CL, 16>(nullptr, nullptr, nullptr, nullptr, B, S, 0, s, &m16)));
   FTB_TRY((launch_rnn_cluster<G, H, CL, 24>(nullptr, nullptr, nullptr, nullptr, B, S, 0, s, &m24)));
-  const int bc = 2 * cdiv(B, 8) <= m8 ? 8 : 2 * cdiv(B, 16) <= m16 ? 16 : 2 * cdiv(B, 24) <= m24 ? 24 : 32;
+  const int mc = g_gru_min_chunk.load(std::memory_order_relaxed);
+  const int bc = (mc <= 8 && 2 * cdiv(B, 8) <= m8) ? 8 : (mc <= 16 && 2 * cdiv(B, 16) <= m16) ? 16
+               : (mc <= 24 && 2 * cdiv(B, 24) <= m24) ? 24 : 32;
   // IEEE-half activations (output type 2) take IEEE-half recurrent operands as well: same kernel, f16 mma
 #define FTB_RNN_BC(N)                                                                                         \
   case N:                                                                                                     \
@@ -397,7 +404,12 @@ static int dispatch_bc(const float* xg, const float* w_hh, const float* b_hn, vo
 int rnn_gru256_mma(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
                    cudaStream_t s) {
   FTB_REQUIRE(b_hn, FTB_ERR_INVALID, "rnn_cluster: GRU needs b_hn");
-  return dispatch_bc<3, 256, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
+  // Cluster of 4 (each CTA: 192 gate rows = 12 warps x 64 registers of A fragments) rather than 8: the hand-off to 3
+  // instead of 7 peers shortens the step more than the doubled mma.sync work per SM lengthens it (cfg2: 1.32 vs
+  // 1.41 ms for both CBHG GRUs) and the recurrence holds 64 instead of 128 SMs (FTB_GRU_CL=8 selects the old shape).
+  static const int cl = getenv("FTB_GRU_CL") ? atoi(getenv("FTB_GRU_CL")) : 4;
+  if (cl == 8) return dispatch_bc<3, 256, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
+  return dispatch_bc<3, 256, 4>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
 }
 
 }  // namespace ftb

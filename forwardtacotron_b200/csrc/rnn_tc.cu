@@ -484,7 +484,14 @@ int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out
 
 }  // namespace ftb
 
+namespace ftb {
+extern std::atomic<int> g_gru_min_chunk;  // rnn_mma.cu
+}
 extern "C" int ftb_tune(int key, int value) {
+  if (key == FTB_TUNE_GRU_MIN_CHUNK && value >= 8 && value <= 32) {
+    ftb::g_gru_min_chunk.store(value);
+    return FTB_OK;
+  }
   if (key == FTB_TUNE_LSTM_MIN_CHUNK && value >= 8 && value <= 32) {
     ftb::g_lstm_min_chunk.store(value);
     return FTB_OK;

@@ -83,6 +83,9 @@ int ftb_ipc_release(void* dev_ptr, int owner);
  * cluster takes.  8 = lowest latency of one call (as many clusters as fit in a wave); 32 = throughput mode for
  * several generate() calls in flight on different streams (fewer SMs pinned by the latency-bound recurrence). */
 #define FTB_TUNE_LSTM_MIN_CHUNK 1
+/* FTB_TUNE_GRU_MIN_CHUNK (8..32, default 8): the same for the CBHG GRU clusters (8 CTAs each): 8 utterances per
+ * cluster = 16 clusters / 128 SMs for a batch of 64; 16 halves the SMs held for a ~30 % longer step. */
+#define FTB_TUNE_GRU_MIN_CHUNK 2
 int ftb_tune(int key, int value);
 /* Number of SMs / compute capability of `device`; fails on anything but sm_100. */
 int ftb_device_check(int device, int* sm_count, int* cc_major, int* cc_minor);
