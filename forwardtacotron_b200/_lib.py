@@ -103,6 +103,7 @@ SIGNATURES = {
     'ftb_ft_set_option': (_I, [_P, _I, _I]),
     'ftb_ft_predict': (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _L, _P]),
     'ftb_ft_synthesize': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _L, _P]),
+    'ftb_ft_synthesize_packed': (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _L, _P]),
     'ftb_ft_series_predictor': (_I, [_P, _I, _P, _I, _I, _F, _P, _P, _L, _P]),
     'ftb_ft_cbhg': (_I, [_P, _I, _P, _I, _I, _P, _P, _L, _P]),
     'ftb_ft_last_launch_count': (_I, [_P]),

@@ -270,7 +270,7 @@ static int run_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn, T* x0
 template <typename T>
 static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* cum, const float* pitch,
                           const float* energy, int B, int Tn, int L, float* mel, float* mel_post, Arena& A,
-                          cudaStream_t s) {
+                          cudaStream_t s, const int32_t* mel_lens = nullptr, float pad_value = 0.f) {
   const ftb_ft_config& c = h->cfg;
   const int E = c.embed_dims, D = 2 * c.prenet_dims, RH = c.rnn_dims, NM = c.n_mels;
   const int melP = (int)align_up(NM, 64);
@@ -295,7 +295,12 @@ static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* c
                       c.energy_strength, B, Tn, D, s));
   FTB_TRY(ftb_length_expand(enc, cum, up, B, Tn, L, D, (int)sizeof(T), s));
   FTB_TRY(h->gemm<T>(h->lstm.in, up, D, B, L, act_out(xg, 8 * RH), nullptr, 0, 1.f, s));
-  FTB_TRY(rnn_bidir(xg, h->lstm.w_hh, nullptr, dec, B, L, RH, 1, out_kind<T>(), s));
+  if (mel_lens) {  // packed sequences (teacher-forced forward in eval mode)
+    ProfScope prof(FAM_RNN_LSTM, 2.0 * 2 * B * L * 4.0 * RH * RH, 0.0, s);
+    FTB_TRY(lstm512_packed(xg, h->lstm.w_hh, dec, mel_lens, pad_value, B, L, out_kind<T>(), s));
+  } else {
+    FTB_TRY(rnn_bidir(xg, h->lstm.w_hh, nullptr, dec, B, L, RH, 1, out_kind<T>(), s));
+  }
   if (melP != NM) FTB_CHECK_CUDA(cudaMemsetAsync(mel_cl, 0, (size_t)ML * melP * sizeof(T), s));
   Out o = act_out(mel_cl, melP);
   o.t = mel;  // 'mel' (B,80,L) and the channel-last copy the postnet reads, from one epilogue
@@ -539,6 +544,23 @@ extern "C" int ftb_ft_synthesize(ftb_ft_handle* h, const int64_t* tokens, const 
     return h->is_fp16() ? run_synthesize<f16>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, (cudaStream_t)stream)
                         : run_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, (cudaStream_t)stream);
   return run_synthesize<float>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, (cudaStream_t)stream);
+}
+
+extern "C" int ftb_ft_synthesize_packed(ftb_ft_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
+                                        const float* energy, const int32_t* mel_lens, float pad_value, int B, int T, int L,
+                                        float* mel, float* mel_post, void* workspace, int64_t workspace_bytes,
+                                        void* stream) {
+  FTB_REQUIRE(h && tokens && cum && pitch && energy && mel_lens && mel && mel_post && workspace, FTB_ERR_INVALID,
+              "ftb_ft_synthesize_packed: bad arguments");
+  FTB_REQUIRE(B > 0 && T > 0 && L > 0, FTB_ERR_INVALID, "ftb_ft_synthesize_packed: bad sizes B=%d T=%d L=%d", B, T, L);
+  h->launches = 0;
+  h->pre_valid = false;
+  Arena A(workspace, workspace_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->bf16_mode())
+    return h->is_fp16() ? run_synthesize<f16>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, s, mel_lens, pad_value)
+                        : run_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, s, mel_lens, pad_value);
+  return run_synthesize<float>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, s, mel_lens, pad_value);
 }
 
 extern "C" int ftb_ft_cbhg(ftb_ft_handle* h, int which, const float* x, int B, int S, float* out, void* workspace,

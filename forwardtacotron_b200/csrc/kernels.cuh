@@ -39,6 +39,10 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
 int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
               int out_bf16, cudaStream_t s);
 
+// rnn_tc.cu: decoder LSTM (H=512) over packed sequences -- state zero and output pad_value wherever t >= lens[b]
+int lstm512_packed(const float* xg, const float* w_hh, void* out, const int* lens, float pad_value, int B, int S,
+                   int out_bf16, cudaStream_t s);
+
 // attention.cu : softmax(q k^T / sqrt(hd) + key_pad_mask) v on packed qkv (B,S,3E)
 template <typename T>
 int attention(const T* qkv, const int64_t* tokens_for_mask, T* ctx, int B, int S, int E, int heads, cudaStream_t s);

@@ -182,6 +182,60 @@ class ForwardTacotron(NativeModel):
             finally:
                 _lib.check(lib.ftb_ft_set_option(h, _lib.FTB_OPT_OVERLAP_PRENET, 0))
 
+    def generate_jit(self, x: torch.Tensor, alpha: float = 1.0, beta: float = 1.0) -> Dict[str, torch.Tensor]:
+        """The TorchScript-exported entry point of the reference (models/forward_tacotron.py:270-284): ``generate``
+        with the pitch scaled by ``beta`` and no callbacks.  (It does not switch to eval mode there either.)"""
+        with torch.no_grad():
+            dur_hat, pitch_hat, energy_hat = self.predict(x, alpha)
+            return self.synthesize(x, dur_hat, pitch_hat * beta, energy_hat)
+
+    def forward(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Teacher-forced forward in EVAL mode (models/forward_tacotron.py:184-242) -- the ground-truth-aligned
+        feature dump of train_forward.py:33-52.  ``batch``: x (B,T) int64, mel (B,n_mels,Lm), mel_len (B,), dur (B,T),
+        pitch (B,T), energy (B,T).  Durations / pitch / energy of the batch drive the synthesis, the decoder LSTM runs
+        over packed sequences (rows stop at ``mel_len``, padded with ``padding_value``), the outputs are cut / padded
+        to ``mel.size(2)``; 'dur' / 'pitch' / 'energy' are the raw predictor outputs (no fallback).  Training mode
+        (dropout, BatchNorm statistics, autograd) is outside the path this package implements."""
+        if self.training:
+            raise NotImplementedError('training-mode forward() is outside the hot path this package implements '
+                                      '(SURVEY 8f-4); call .eval() for the teacher-forced inference pass')
+        with torch.no_grad():
+            x = self._check_tokens(batch['x'])
+            lib, dev = _lib.lib(), x.device
+            B, T = x.shape
+            mel_lens = batch['mel_len'].to(device=dev, dtype=torch.int32).contiguous()
+            dur = batch['dur']
+            if dur.dtype != torch.float32 or not dur.is_contiguous() or dur.device != dev:
+                dur = dur.to(device=dev, dtype=torch.float32).contiguous()
+            dur_hat = self.run_series_predictor('dur_pred', x).squeeze(-1)
+            pitch_hat = self.run_series_predictor('pitch_pred', x).transpose(1, 2)
+            energy_hat = self.run_series_predictor('energy_pred', x).transpose(1, 2)
+            pitch = batch['pitch'].to(device=dev, dtype=torch.float32).reshape(B, T).contiguous()
+            energy = batch['energy'].to(device=dev, dtype=torch.float32).reshape(B, T).contiguous()
+            cum, total = LengthRegulator.plan(dur)           # clamps dur in place like the reference's lr()
+            stats = torch.stack([total.max().to(torch.int64), mel_lens.max().to(torch.int64)]).tolist()  # one D2H
+            L_lr, L = int(stats[0]), int(stats[1])
+            if L <= 0 or L > L_lr:
+                raise RuntimeError(f'mel_len (max {L}) must be positive and not exceed the expanded length {L_lr} '
+                                   '(pack_padded_sequence would raise)')
+            h = self._get_handle(dev)
+            ws = self._workspace_for(h, B, T, L, dev)
+            n_mels = self._dims['n_mels']
+            mel = torch.empty((B, n_mels, L), dtype=torch.float32, device=dev)
+            mel_post = torch.empty((B, n_mels, L), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.ftb_ft_synthesize_packed(h, _lib.ptr(x), _lib.ptr(cum), _lib.ptr(pitch), _lib.ptr(energy),
+                                                        _lib.ptr(mel_lens), float(self.padding_value), B, T, L,
+                                                        _lib.ptr(mel), _lib.ptr(mel_post), _lib.ptr(ws), ws.numel(),
+                                                        _lib.current_stream(dev)))
+            max_len = int(batch['mel'].size(2))
+            return {'mel': self._pad(mel, max_len), 'mel_post': self._pad(mel_post, max_len),
+                    'dur': dur_hat, 'pitch': pitch_hat, 'energy': energy_hat}
+
+    def _pad(self, x: torch.Tensor, max_len: int) -> torch.Tensor:
+        x = x[:, :, :max_len]
+        return torch.nn.functional.pad(x, [0, max_len - x.size(2), 0, 0], 'constant', self.padding_value)
+
     def last_launch_count(self) -> int:
         return int(_lib.lib().ftb_ft_last_launch_count(self._handle)) if self._handle is not None else 0
 

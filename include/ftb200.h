@@ -244,6 +244,15 @@ int ftb_ft_synthesize(ftb_ft_handle* h, const int64_t* tokens, const int32_t* cu
                       const float* energy, int B, int T, int L, float* mel, float* mel_post, void* workspace,
                       int64_t workspace_bytes, void* stream);
 
+/* Stage B of the teacher-forced forward() in eval mode (models/forward_tacotron.py:203-242; the GTA feature dump of
+ * train_forward.py:33-52): as ftb_ft_synthesize, but the decoder LSTM runs over PACKED sequences -- row b stops at
+ * mel_lens[b] (int32, device; pack_padded_sequence), the reverse direction starts at its last valid frame, and the
+ * LSTM output beyond it is pad_value (pad_packed_sequence, padding_value = -11.5129).  lin and the postnet then run
+ * over the padded rows exactly as the reference does.  L = max(mel_lens) <= the expanded length. */
+int ftb_ft_synthesize_packed(ftb_ft_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
+                             const float* energy, const int32_t* mel_lens, float pad_value, int B, int T, int L,
+                             float* mel, float* mel_post, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Sub-module entry points (row a3 / a4 of the scope table; used by the mirrored
  * SeriesPredictor / CBHG modules and their parity tests).
  * which: 0 dur_pred, 1 pitch_pred, 2 energy_pred.  out (B,T) f32 (no fallback). */

@@ -189,6 +189,38 @@ def ft_generate(sd: SD, tokens: torch.Tensor, alpha: float = 1.0,
                              pitch_strength, energy_strength)
 
 
+def ft_forward(sd: SD, batch: Dict[str, torch.Tensor], pitch_strength: float = 1.0, energy_strength: float = 1.0,
+               padding_value: float = -11.5129) -> Dict[str, torch.Tensor]:
+    """Teacher-forced ``forward`` in eval mode, models/forward_tacotron.py:184-242 (the GTA dump of
+    train_forward.py:33-52).  The packed-sequence LSTM (:224-230) is restated row by row: row b runs the bidirectional
+    LSTM over its first ``mel_len[b]`` frames only, the rest of the row is ``padding_value``; the result is cut to
+    ``max(mel_len)`` frames (pad_packed_sequence), ``lin`` / postnet / ``post_proj`` see the padded rows, and both
+    outputs are cut / padded to ``mel.size(2)`` (:238-239, ``_pad`` :332-335).  ``batch['dur']`` is clamped in place."""
+    with torch.no_grad():
+        x, mel_lens = batch['x'], batch['mel_len']
+        dur_hat = ft_series_predictor(sd, 'dur_pred', x).squeeze(-1)
+        pitch_hat = ft_series_predictor(sd, 'pitch_pred', x).transpose(1, 2)
+        energy_hat = ft_series_predictor(sd, 'energy_pred', x).transpose(1, 2)
+        enc = cbhg(sd, 'prenet', sd['embedding.weight'][x].transpose(1, 2))
+        enc = enc + cond_proj(sd, 'pitch_proj', batch['pitch'].unsqueeze(1)) * pitch_strength
+        enc = enc + cond_proj(sd, 'energy_proj', batch['energy'].unsqueeze(1)) * energy_strength
+        up = length_regulate(enc, batch['dur'])
+        L = int(mel_lens.max())
+        dec = up.new_full((up.shape[0], L, 2 * sd['lstm.weight_hh_l0'].shape[1]), padding_value)
+        for b in range(up.shape[0]):
+            n = int(mel_lens[b])
+            dec[b, :n] = rnn(sd, 'lstm', up[b:b + 1, :n], 'lstm')[0]
+        mel = (dec @ sd['lin.weight'].T + sd['lin.bias']).transpose(1, 2)
+        post = cbhg(sd, 'postnet', mel)
+        mel_post = (post @ sd['post_proj.weight'].T).transpose(1, 2)
+        max_len = batch['mel'].size(2)
+
+        def pad(t):
+            t = t[:, :, :max_len]
+            return F.pad(t, [0, max_len - t.size(2), 0, 0], 'constant', padding_value)
+        return {'mel': pad(mel), 'mel_post': pad(mel_post), 'dur': dur_hat, 'pitch': pitch_hat, 'energy': energy_hat}
+
+
 # --------------------------------------------------------------------------
 # FastPitch
 # --------------------------------------------------------------------------

@@ -221,3 +221,73 @@ def test_duration_predictor_split_precision_is_fp32_grade():
     assert not torch.equal(got['split'], got['simt'])            # the two paths really are different kernels
     flips = rounded(got['split']) != rounded(cpu32)
     assert bool((near_tie_mask(cpu32) | ~flips).all()) and int(flips.sum()) <= 1
+
+
+def _forward_batch(g, device):
+    B = g['x'].shape[0]
+    return {'x': g['x'].to(device), 'dur': g['dur_in'].clone().to(device), 'mel_len': g['mel_len'].to(device),
+            'pitch': g['pitch_in'].to(device), 'energy': g['energy_in'].to(device),
+            'mel': torch.zeros(B, 80, int(g['mel_frames']), device=device)}
+
+
+@pytest.mark.parametrize('gemm_mode', [1, 0, 2])
+def test_teacher_forced_forward_against_reference_fixture(gemm_mode):
+    """forward() in eval mode = the GTA feature dump (train_forward.py:33-52): packed-sequence decoder LSTM, outputs
+    padded with padding_value; fixture frozen from the reference's own forward()."""
+    g = load('ft_forward_b3_t30')
+    model, _ = cuda_model('forward_tacotron', gemm_mode)
+    model.eval()
+    out = model(_forward_batch(g, 'cuda'))
+    assert set(out) == {'mel', 'mel_post', 'dur', 'pitch', 'energy'}
+    assert_close(out['dur'], g['dur'], 1e-4, 1e-5, 'dur_hat')
+    lens = g['mel_len'].tolist()
+    for k in ('mel', 'mel_post'):
+        assert out[k].shape == g[k].shape
+        got, want = out[k].cpu(), g[k]
+        for b, n in enumerate(lens):   # what the GTA dump keeps: mel[:, :mel_len] (train_forward.py:47)
+            assert_close(got[b, :, :n], want[b, :, :n], what=f'{k}[{b}] valid frames')
+        # rows past mel_len carry lin / postnet of the padding value (magnitude ~10^1): relative check
+        rel = float((got - want).abs().max() / want.abs().max())
+        assert rel < (1e-4 if gemm_mode == 1 else 2e-2), (k, rel)
+        n = max(lens)
+        assert torch.all(got[:, :, n:] == -11.5129)          # _pad up to mel.size(2)
+    if gemm_mode == 1:
+        assert_close(out['mel'], g['mel'], what='mel (all frames, fp32 mode)')
+
+
+def test_forward_requires_eval_and_generate_jit_matches_generate():
+    model, _ = cuda_model('forward_tacotron', 0)
+    g = load('ft_forward_b3_t30')
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(_forward_batch(g, 'cuda'))
+    model.eval()
+    x = synth.synthetic_tokens(3, 40, seed=4).cuda()
+    a = model.generate_jit(x, alpha=1.1, beta=0.9)             # models/forward_tacotron.py:270-284
+    b = model.generate(x, alpha=1.1, pitch_function=lambda p: p * 0.9)
+    for k in ('mel', 'mel_post', 'dur', 'pitch', 'energy'):
+        assert torch.equal(a[k], b[k]), k
+    sd = cpu_state_dict(model)
+    want = mo.ft_generate(sd, x.cpu(), alpha=1.1, pitch_function=lambda p: p * 0.9)
+    assert torch.equal(rounded(a['dur']), rounded(want['dur']))
+    assert_close(a['mel_post'], want['mel_post'], what='generate_jit mel_post')
+
+
+def test_packed_forward_many_rows():
+    """More rows than one LSTM cluster sub-chunk holds (B = 40, ragged lengths) against the oracle."""
+    model, _ = cuda_model('forward_tacotron', 0)
+    model.eval()
+    gen = torch.Generator().manual_seed(5)
+    B, T = 40, 24
+    dur = torch.randint(1, 7, (B, T), generator=gen).float()
+    dur[torch.arange(B), torch.randint(0, T, (B,), generator=gen)] = 0.0
+    for b in range(0, B, 3):
+        dur[b, T // 3:] = 0.0
+    batch = {'x': torch.randint(1, 135, (B, T), generator=gen), 'dur': dur, 'mel_len': (dur + 0.5).long().sum(1),
+             'pitch': torch.randn(B, T, generator=gen), 'energy': torch.randn(B, T, generator=gen)}
+    batch['mel'] = torch.zeros(B, 80, int(batch['mel_len'].max()))
+    want = mo.ft_forward(cpu_state_dict(model), {k: v.clone() for k, v in batch.items()}, model.pitch_strength,
+                         model.energy_strength)
+    out = model({k: v.cuda() for k, v in batch.items()})
+    for b, n in enumerate(batch['mel_len'].tolist()):
+        assert_close(out['mel_post'][b, :, :n], want['mel_post'][b, :, :n], what=f'mel_post[{b}]')

@@ -76,3 +76,20 @@ def test_fastpitch_max_len_raises():
     model, _ = synth.synthetic_model('fast_pitch')
     with pytest.raises(RuntimeError, match='must match the size'):
         mo.forward_transformer(model.state_dict(), 'prenet', torch.zeros(1, 5001, 256), 2)
+
+
+def _forward_batch(g):
+    return {'x': g['x'], 'dur': g['dur_in'].clone(), 'mel_len': g['mel_len'], 'pitch': g['pitch_in'],
+            'energy': g['energy_in'], 'mel': torch.zeros(g['x'].shape[0], 80, int(g['mel_frames']))}
+
+
+def test_forward_fixture():
+    """Teacher-forced forward() in eval mode (GTA features): the oracle against the reference's own output
+    (oracle/make_golden_forward.py), including the packed-sequence padding."""
+    g = load('ft_forward_b3_t30')
+    model, _ = synth.synthetic_model('forward_tacotron')
+    out = mo.ft_forward(model.state_dict(), _forward_batch(g), model.pitch_strength, model.energy_strength)
+    for k in ('mel', 'mel_post', 'dur', 'pitch', 'energy'):
+        assert out[k].shape == g[k].shape and float((out[k] - g[k]).abs().max()) < 2e-5, k
+    n = int(g['mel_len'].max())
+    assert torch.all(out['mel'][:, :, n:] == -11.5129) and torch.all(out['mel_post'][:, :, n:] == -11.5129)
