@@ -1,10 +1,11 @@
 // Bidirectional GRU recurrence for small hidden sizes (H = 64 / 128: the three
 // SeriesPredictors, models/forward_tacotron.py:39,53), exact fp32.
 //
-// One CTA per (utterance, direction); the whole W_hh (3H x H fp32, <= 196 KB)
-// stays in shared memory for all S steps, so there is no inter-CTA traffic and
-// no grid synchronisation: a step is one smem mat-vec, two block barriers and
-// the gate maths.  Latency-bound by design (SURVEY 8d "recurrences").
+// One CTA per (utterance, direction), one thread per gate row; the thread keeps ITS ROW of W_hh (H fp32 values) in
+// registers for all S steps, so a step reads only h from shared memory (H/4 broadcast 16-byte loads per thread; with
+// the row in shared memory as well the step was bound by 2H shared loads per thread: 1.7 us at H = 128).  No
+// inter-CTA traffic, no grid synchronisation: a step is one mat-vec, two block barriers and the gate maths.
+// Latency-bound by design (SURVEY 8d "recurrences").
 #include "common.cuh"
 
 namespace ftb {
@@ -14,52 +15,73 @@ __global__ void __launch_bounds__(3 * H) gru_small_kernel(const float* __restric
                                                           const float* __restrict__ w_hh,  // (2,3H,H)
                                                           const float* __restrict__ b_hn,  // (2,H)
                                                           void* __restrict__ out, int S, int out_bf16) {
-  extern __shared__ float smem[];
-  constexpr int G = 3 * H, LD = H + 1;
-  float* W = smem;            // [G][LD]
-  float* h = W + G * LD;      // [H]
-  float* gh = h + H;          // [G]
+  constexpr int G = 3 * H;
+  __shared__ __align__(16) float h[H];
+  __shared__ float gh[G];
   const int b = blockIdx.x, dir = blockIdx.y, tid = threadIdx.x;
 
-  const float* wsrc = w_hh + (int64_t)dir * G * H;
-  for (int i = tid; i < G * H; i += G) W[(i / H) * LD + (i % H)] = wsrc[i];
+  float w[H];  // this thread's gate row
+  {
+    const float4* wsrc = reinterpret_cast<const float4*>(w_hh + ((int64_t)dir * G + tid) * H);
+#pragma unroll
+    for (int k = 0; k < H / 4; ++k) {
+      const float4 v = __ldg(wsrc + k);
+      w[4 * k] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+    }
+  }
   if (tid < H) h[tid] = 0.f;
   const float bn = tid >= 2 * H ? b_hn[dir * H + tid - 2 * H] : 0.f;
   const float* xrow = xg + (((int64_t)b * S) * 2 + dir) * G;  // + t*2*G
   const int64_t xstride = 2 * G;
-  float xr = 0.f, xz = 0.f, xn = 0.f;
-  if (tid < H) {
+  // Input pre-activations: thread tid < H (r row of unit tid) carries x_r and x_n of its unit, thread H + u (z row)
+  // carries x_z, so the r and z sigmoids of a unit run on two threads side by side.  The values of the current and
+  // the next step sit in registers; the loads for step s + 2 are issued at the top of step s (a step is shorter
+  // than an L2 round trip, so one step of look-ahead left the load latency exposed).
+  const int gate = tid / H, u = tid - gate * H;  // 0 r, 1 z, 2 n
+  const float* xa = xrow + (gate == 1 ? H + u : u);        // x_r (gate 0) or x_z (gate 1)
+  const float* xb = xrow + 2 * H + u;                      // x_n (gate 0 only)
+  float xa0 = 0.f, xb0 = 0.f, xa1 = 0.f, xb1 = 0.f;
+  if (gate < 2) {
     const int t0 = dir ? S - 1 : 0;
-    xr = xrow[t0 * xstride + tid];
-    xz = xrow[t0 * xstride + H + tid];
-    xn = xrow[t0 * xstride + 2 * H + tid];
+    xa0 = xa[t0 * xstride];
+    if (gate == 0) xb0 = xb[t0 * xstride];
+    if (S > 1) {
+      const int t1 = dir ? S - 2 : 1;
+      xa1 = xa[t1 * xstride];
+      if (gate == 0) xb1 = xb[t1 * xstride];
+    }
   }
   __syncthreads();
 
-  const float* wr = W + tid * LD;
   for (int s = 0; s < S; ++s) {
     const int t = dir ? S - 1 - s : s;
-    float nr = 0.f, nz = 0.f, nn = 0.f;
-    if (tid < H && s + 1 < S) {  // prefetch next step's input pre-activations
-      const int tn = dir ? t - 1 : t + 1;
-      nr = xrow[tn * xstride + tid];
-      nz = xrow[tn * xstride + H + tid];
-      nn = xrow[tn * xstride + 2 * H + tid];
+    float xa2 = 0.f, xb2 = 0.f;
+    if (gate < 2 && s + 2 < S) {
+      const int tn = dir ? t - 2 : t + 2;
+      xa2 = xa[tn * xstride];
+      if (gate == 0) xb2 = xb[tn * xstride];
     }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
+#pragma unroll
     for (int k = 0; k < H; k += 4) {
-      a0 = fmaf(wr[k], h[k], a0);
-      a1 = fmaf(wr[k + 1], h[k + 1], a1);
-      a2 = fmaf(wr[k + 2], h[k + 2], a2);
-      a3 = fmaf(wr[k + 3], h[k + 3], a3);
+      const float4 hv = *reinterpret_cast<const float4*>(h + k);
+      a0 = fmaf(w[k], hv.x, a0);
+      a1 = fmaf(w[k + 1], hv.y, a1);
+      a2 = fmaf(w[k + 2], hv.z, a2);
+      a3 = fmaf(w[k + 3], hv.w, a3);
     }
-    gh[tid] = (a0 + a1) + (a2 + a3) + bn;
+    const float acc = (a0 + a1) + (a2 + a3) + bn;
+    float r = 0.f;
+    if (gate == 0)
+      r = 1.f / (1.f + expf(-(xa0 + acc)));
+    else if (gate == 1)
+      gh[tid] = 1.f / (1.f + expf(-(xa0 + acc)));  // z
+    else
+      gh[tid] = acc;                                // W_hn h + b_hn
     __syncthreads();
-    if (tid < H) {
-      const float r = 1.f / (1.f + expf(-(xr + gh[tid])));
-      const float z = 1.f / (1.f + expf(-(xz + gh[H + tid])));
-      const float n = tanhf(xn + r * gh[2 * H + tid]);
+    if (gate == 0) {
+      const float z = gh[H + tid];
+      const float n = tanhf(xb0 + r * gh[2 * H + tid]);
       const float hn = (1.f - z) * n + z * h[tid];
       h[tid] = hn;
       const int64_t o = ((int64_t)b * S + t) * (2 * H) + dir * H + tid;
@@ -69,10 +91,9 @@ __global__ void __launch_bounds__(3 * H) gru_small_kernel(const float* __restric
         ((__nv_bfloat16*)out)[o] = __float2bfloat16_rn(hn);
       else
         ((float*)out)[o] = hn;
-      xr = nr;
-      xz = nz;
-      xn = nn;
     }
+    xa0 = xa1, xb0 = xb1;
+    xa1 = xa2, xb1 = xb2;
     __syncthreads();
   }
 }
@@ -81,13 +102,7 @@ template <int H>
 static int launch_gru_small(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S,
                             int out_bf16, cudaStream_t s) {
   constexpr int G = 3 * H;
-  const size_t smem = sizeof(float) * (G * (H + 1) + H + G);
-  static bool attr_set = false;
-  if (!attr_set) {
-    FTB_CHECK_CUDA(cudaFuncSetAttribute(gru_small_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  gru_small_kernel<H><<<dim3(B, 2), G, smem, s>>>(xg, w_hh, b_hn, out, S, out_bf16);
+  gru_small_kernel<H><<<dim3(B, 2), G, 0, s>>>(xg, w_hh, b_hn, out, S, out_bf16);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }

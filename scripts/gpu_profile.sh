@@ -4,7 +4,7 @@
 # usage: bash scripts/gpu_profile.sh [tag]
 set -u
 mkdir -p gpurun_out
-TAG=${1:-v3}
+TAG=${1:-v4}
 CMD="python bench.py --steps 1 --warmup 3 --no-extras --in-flight 1"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum,launch__grid_size,sm__inst_executed_pipe_tensor.sum --clock-control none -c 4000 --csv \
@@ -14,14 +14,18 @@ cap() {  # name kernel-regex skip count
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -o gpurun_out/prof_$1_$TAG -f $CMD > gpurun_out/ncu_$1_$TAG.log 2>&1
   echo "$1 capture rc=$?"
 }
-# per generate: 29 conv_gemm_tc launches: 8 stage A, 9 prenet (bank first), LSTM in-proj (#17), lin, 9 postnet (bank #19,
-# proj1 #20), post_proj; warm-up = 3 generates
+# Launch order of one generate() (serialised under ncu): dur_pred 4 x conv_gemm_tc_kernel<2>; pitch / energy 4 + 4 x <0>;
+# prenet: bank, proj1, proj2, pre_highway (<0>), 4 x highway (<1>), GRU in-proj (<0>); LSTM in-proj (<0>); rnn_tc;
+# lin; postnet: bank, proj1, proj2, pre_highway, 4 x <1>, GRU in-proj; post_proj.  => 21 x <0>, 8 x <1>, 4 x <2>,
+# 2 x rnn_cluster_kernel, 3 x gru_small_kernel per generate; warm-up = 3 generates.
 cap lstm rnn_tc_kernel 3 1
 cap gru rnn_cluster_kernel 7 1
-cap gemm conv_gemm_tc_kernel 104 4
-cap f32gemm conv_gemm_f32_kernel 13 1
+cap grusmall gru_small_kernel 9 3
+cap gemm "conv_gemm_tc_kernel<0>" 71 13
+cap highway "conv_gemm_tc_kernel<1>" 28 1
+cap split "conv_gemm_tc_kernel<2>" 13 2
 CMD="python bench.py --stft-only"
 $CMD > gpurun_out/plain_stft.log 2>&1 && cap stft stft_mel 3 1
 CMD="python scripts/fp_profile.py"
 $CMD > gpurun_out/plain_fp.log 2>&1 && cap attn attention_tc_kernel 30 1
-ls -la gpurun_out
+ls -la gpurun_out | head -40
