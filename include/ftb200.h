@@ -83,8 +83,8 @@ int ftb_ipc_release(void* dev_ptr, int owner);
  * cluster takes.  8 = lowest latency of one call (as many clusters as fit in a wave); 32 = throughput mode for
  * several generate() calls in flight on different streams (fewer SMs pinned by the latency-bound recurrence). */
 #define FTB_TUNE_LSTM_MIN_CHUNK 1
-/* FTB_TUNE_GRU_MIN_CHUNK (8..32, default 8): the same for the CBHG GRU clusters (8 CTAs each): 8 utterances per
- * cluster = 16 clusters / 128 SMs for a batch of 64; 16 halves the SMs held for a ~30 % longer step. */
+/* FTB_TUNE_GRU_MIN_CHUNK (8..32, default 8): the same for the CBHG GRU clusters (4 CTAs each): 8 utterances per
+ * cluster = 16 clusters / 64 SMs for a batch of 64; 16 halves the SMs held for a ~40 % longer step. */
 #define FTB_TUNE_GRU_MIN_CHUNK 2
 int ftb_tune(int key, int value);
 /* Number of SMs / compute capability of `device`; fails on anything but sm_100. */
@@ -160,9 +160,10 @@ int ftb_pack_conv_weight(const float* w, void* out, int N, int Cin, int k, int N
  * folded: all LSTM gates, GRU r and z); w_hh (2,G*H,H) f32 in torch gate order;
  * b_hn (2,H) f32 is the GRU n-gate hidden bias (NULL for LSTM).
  * out (B,S,2H): f32 when out_bf16 == 0, bf16 when 1, IEEE half when 2.
- * H in {64,128}: one-CTA-per-row fp32 kernel (W_hh in shared memory, exact fp32).
- * H in {256,512}: thread-block-cluster kernel, W_hh resident in registers as
- * bf16 MMA fragments, hidden state exchanged through distributed shared memory. */
+ * H in {64,128}: one CTA per (row, direction), one thread per gate row with its W_hh row in registers, exact fp32.
+ * H = 256 (GRU): cluster of 4 CTAs, W_hh resident in registers as 16-bit mma.sync fragments.
+ * H = 512 (LSTM): cluster of 16 CTAs, W_hh resident in shared memory as the tcgen05 A operand.
+ * Both exchange the hidden state through distributed shared memory. */
 int ftb_rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H,
                   int is_lstm, int out_bf16, void* stream);
 

@@ -21,9 +21,13 @@ cap() {  # name kernel-regex skip count
 cap lstm rnn_tc_kernel 3 1
 cap gru rnn_cluster_kernel 7 1
 cap grusmall gru_small_kernel 9 3
-cap gemm "conv_gemm_tc_kernel<0>" 71 13
-cap highway "conv_gemm_tc_kernel<1>" 28 1
-cap split "conv_gemm_tc_kernel<2>" 13 2
+capm() {  # as cap, matching the MANGLED name (template arguments are not part of ncu's default function name)
+  ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:$2 -s $3 -c $4 -o gpurun_out/prof_$1_$TAG -f $CMD > gpurun_out/ncu_$1_$TAG.log 2>&1
+  echo "$1 capture rc=$?"
+}
+capm gemm conv_gemm_tc_kernelILi0E 71 13
+capm highway conv_gemm_tc_kernelILi1E 28 1
+capm split conv_gemm_tc_kernelILi2E 13 2
 CMD="python bench.py --stft-only"
 $CMD > gpurun_out/plain_stft.log 2>&1 && cap stft stft_mel 3 1
 CMD="python scripts/fp_profile.py"
