@@ -455,6 +455,8 @@ def run_ours(args):
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': roofline_of(top, pk),
+            # the same figure for every kernel family that has algorithmic work attached (the dominant one above)
+            'rooflines': [roofline_of(f, pk) for f in fams if f['flops_per_step'] > 0 or f['bytes_per_step'] > 0],
             'kernels': kernels,
             'kernels_note': f'share = fraction of the serialised step ({serial_ms:.3f} ms kernel time); the timed steps '
                             f'overlap stage A / prenet on side streams and keep {S} batches in flight',

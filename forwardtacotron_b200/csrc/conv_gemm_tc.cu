@@ -135,7 +135,8 @@ struct alignas(64) TcArgs {
   int nprob, B, S, Cin, cblocks;
   int m_tiles, m_stride, box_rows, bn, total_tiles, pool, highway, fp16;
   int split_in;   // A holds 3 bf16 parts [hi | mid | lo] of an fp32 tensor; K loop = 6 part products (see conv_gemm_group)
-  int split_d;    // split-precision mode: k-blocks per TMEM accumulation unit
+  int split_d;    // split-precision mode: k-blocks per TMEM accumulation unit inside the hi.hi product ...
+  int split_ds;   // ... and inside the five small products (their truncation error is 2^-8 of the result's)
   int split_out;  // > 0: the 16-bit output is written as 3 parts, split_out channels apart
   int ldo, ldr, n_total;  // n_total: N of the (B,N,S) transposed output
   float out_scale;
@@ -275,6 +276,15 @@ __device__ __forceinline__ void epi_rows_pool(const float* sp, int nrows, const 
   }
 }
 
+// Split-precision mode: end of the accumulation unit that starts at k-block kb.  The last sixth of the K loop is the
+// hi.hi product (units of d k-blocks); the five small products before it take units of ds k-blocks: their sums are
+// <= 2^-8 of the result, so the truncation of a longer chain stays far below one ulp of it, and the TMEM read of a
+// drain (128 x 128 fp32 at ~64 B/clk = 1 k clk) then hides behind the unit's MMAs.  Units never straddle the boundary.
+__device__ __forceinline__ int split_unit_end(int kb, int nkb, int d, int ds) {
+  const int hi0 = nkb - nkb / 6;
+  return kb < hi0 ? min(hi0, kb + ds) : min(nkb, kb + d);
+}
+
 // MODE: 0 generic epilogue (bias / ReLU / BN affine / residual / pool / transposed output), 1 highway, 2 split
 // precision.  Separate instantiations because the kernel sits at its register cap (10 warps -> 3 per scheduler ->
 // 168 registers per thread): every mode only carries its own epilogue state.
@@ -355,7 +365,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         if (SPLIT) {
           // Split-precision mode: the tensor core adds into the fp32 accumulator with truncation, a bias that grows with
           // the length of the accumulation chain (measured: 80 K-steps put the duration predictor 5x further from an
-          // fp64 evaluation than the fp32 SIMT kernel).  So the chain is cut every split_d k-blocks: each short partial
+          // fp64 evaluation than the fp32 SIMT kernel).  So the chain is cut into units (split_unit_end): each short partial
           // sum goes to the epilogue warps through the two TMEM buffers and is added there in fp32 registers
           // (round-to-nearest) while the next partial accumulates.
           for (int kb = 0; kb < P.nkb; ++un) {
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
             if (un >= 2) mbar_wait(tempty0 + 8 * ub, ((un >> 1) - 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_unit = tmem_base + ub * BN_MAX;
-            const int kend = min(P.nkb, kb + a.split_d);
+            const int kend = split_unit_end(kb, P.nkb, a.split_d, a.split_ds);
             for (bool first = true; kb < kend; ++kb, ++it, first = false) {
               const uint32_t st = it % STAGES;
               mbar_wait(full0 + 8 * st, (it / STAGES) & 1);
@@ -424,8 +434,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int k = 0; k < 32; ++k) acc[i][k] = 0.f;
-        const int nunits = (P.nkb + a.split_d - 1) / a.split_d;
-        for (int u = 0; u < nunits; ++u, ++un) {
+        for (int kb = 0; kb < P.nkb; kb = split_unit_end(kb, P.nkb, a.split_d, a.split_ds), ++un) {
           const uint32_t ub = un & 1;
           mbar_wait(tfull0 + 8 * ub, (un >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -669,6 +678,8 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.split_out = o.split_out;
   static const int split_d = getenv("FTB_SPLIT_D") ? std::max(1, atoi(getenv("FTB_SPLIT_D"))) : 2;
   a.split_d = split_d;
+  static const int split_ds = getenv("FTB_SPLIT_DS") ? std::max(1, atoi(getenv("FTB_SPLIT_DS"))) : 20;
+  a.split_ds = split_ds;
   FTB_REQUIRE(!(o.split_in || o.split_out) || (!o.fp16 && !o.pool && !o.highway && !o.res_f32 && !o.res_bf16 && !o.out_t),
               FTB_ERR_INVALID, "conv_gemm_bf16: split-precision mode is plain bf16, row-major, no residual");
   FTB_REQUIRE(!o.split_out || (o.split_in && o.out_bf16 && !o.out_f32), FTB_ERR_INVALID,
