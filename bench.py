@@ -224,7 +224,18 @@ def stft_extra(torch, dev, pk):
     ms = e0.elapsed_time(e1) / reps
     secs = a.numel() / 22050.0
     nbytes = a.numel() * 4 + out.numel() * 4
+    # The kernel is bound by instruction issue, not by HBM: the fp32 FFT + split + sparse mel cost
+    # WARP_INSTR_PER_FRAME warp instructions per frame (smsp__inst_executed.sum / frames of profiles/r01_stft_v4.txt),
+    # against 4 issue slots per SM and clock.
+    WARP_INSTR_PER_FRAME = 1499.0
+    frames = out.numel() / 80
+    props = torch.cuda.get_device_properties(dev)
+    issue_peak = props.multi_processor_count * 4 * 1.965e9
+    issue = {'bound': 'issue', 'achieved': frames * WARP_INSTR_PER_FRAME / (ms / 1e3) / 1e9, 'peak': issue_peak / 1e9,
+             'unit': 'G warp-instr/s', 'frac': frames * WARP_INSTR_PER_FRAME / (ms / 1e3) / issue_peak,
+             'note': 'warp instructions per frame from the committed ncu capture; peak = SMs x 4 schedulers x 1965 MHz'}
     return {'metric': 'stft_mel_audio_seconds_per_s', 'value': secs / (ms / 1e3), 'unit': 'audio-s/s',
+            'issue_roofline': issue,
             'ms_per_step': ms, 'clips': n_clips, 'audio_seconds': secs,
             'workload': 'DSP.wav_to_mel, 22.05 kHz clips of 2-10 s (noise, sines, silence), n_fft 1024 / hop 256 / 80 mels',
             'roofline': {'kernel': 'stft_mel', 'bound': 'hbm', 'achieved': nbytes / (ms / 1e3) / 1e9,

@@ -99,7 +99,7 @@ __device__ __forceinline__ int find_clip(const int64_t* __restrict__ frame_off, 
   return lo;
 }
 
-__global__ void __launch_bounds__(mel::WARPS * 32, 4)
+__global__ void __launch_bounds__(mel::WARPS * 32, 3)
     stft_mel_kernel(const float* __restrict__ audio, const int64_t* __restrict__ clip_off,
                     const int64_t* __restrict__ frame_off, int n_clips, int64_t total_frames, float* __restrict__ out,
                     int normalize, const MelTables tb) {
