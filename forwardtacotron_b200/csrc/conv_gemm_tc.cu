@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
           const int64_t ooff = mrow0 * ldo + P.n_offset + n;
           const int nr = nok ? nrows : 0;
           if (a.split_out) epi_rows_split3(stg + lane, nr, e, a.out_bf16 + ooff, ldo, a.split_out);
+          else if (a.res_f32) epi_rows_res<1>(stg + lane, nr, e, a.out_f32 + ooff, nullptr, true, false, ldo, a.res_f32 + mrow0 * ldr + n, nullptr, ldr);
           else epi_rows<1>(stg + lane, nr, e, a.out_f32 + ooff, nullptr, ldo);
           __syncwarp();
         }
@@ -680,8 +681,8 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.split_d = split_d;
   static const int split_ds = getenv("FTB_SPLIT_DS") ? std::max(1, atoi(getenv("FTB_SPLIT_DS"))) : 20;
   a.split_ds = split_ds;
-  FTB_REQUIRE(!(o.split_in || o.split_out) || (!o.fp16 && !o.pool && !o.highway && !o.res_f32 && !o.res_bf16 && !o.out_t),
-              FTB_ERR_INVALID, "conv_gemm_bf16: split-precision mode is plain bf16, row-major, no residual");
+  FTB_REQUIRE(!(o.split_in || o.split_out) || (!o.fp16 && !o.pool && !o.highway && !o.res_bf16 && !o.out_t && !(o.res_f32 && o.split_out)),
+              FTB_ERR_INVALID, "conv_gemm_bf16: split-precision mode is plain bf16, row-major; fp32 residual with fp32 output only");
   FTB_REQUIRE(!o.split_out || (o.split_in && o.out_bf16 && !o.out_f32), FTB_ERR_INVALID,
               "conv_gemm_bf16: split output is 16-bit only and needs split input");
   FTB_REQUIRE(!o.split_in || o.split_out || (o.out_f32 && !o.out_bf16), FTB_ERR_INVALID,

@@ -216,6 +216,26 @@ int embed(const int64_t* tok, const float* table, T* out, int64_t rows, int C, i
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }
+// fp32 (rows, C) -> three bf16 parts [hi | mid | lo] (rows, 3C): operand of a split-precision GEMM
+__global__ void split3_rows_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t rows, int C) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i % C);
+    const float v = in[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    __nv_bfloat16* o = out + r * 3 * C + c;
+    o[0] = hi, o[C] = mid, o[2 * C] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+  }
+}
+int split3_rows(const float* in, __nv_bfloat16* out, int64_t rows, int C, cudaStream_t s) {
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
+  split3_rows_kernel<<<ew_blocks(rows * C), 256, 0, s>>>(in, out, rows, C);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
 int embed_split3(const int64_t* tok, const float* table, __nv_bfloat16* out, int64_t rows, int C, int num_chars, cudaStream_t s) {
   ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
   embed_split3_kernel<<<ew_blocks(rows * C), 256, 0, s>>>(tok, table, out, rows, C, num_chars);

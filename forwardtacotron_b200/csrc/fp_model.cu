@@ -21,6 +21,7 @@ struct TransformerW {  // ForwardTransformer, models/fast_pitch.py:95-130
   std::vector<FftBlockW> layers;
   const float *nw = nullptr, *nb = nullptr;
   bool f32_only = false;
+  bool tc_split = false;  // f32_only stack whose GEMMs run split-precision on the tensor cores
 };
 struct FpSeriesW {  // SeriesPredictor, models/fast_pitch.py:133-160
   const float* emb = nullptr;
@@ -65,6 +66,11 @@ static int build_transformer(ftb_fp_handle* h, TransformerW& W, const std::strin
   W.heads = heads;
   W.f32_only = f32_only;
   const bool w16 = h->half_mode() && !f32_only, w32 = !w16;
+  // the fp32-exact stack of a 16-bit mode (duration predictor): split-precision tensor-core GEMMs; the fp32 SIMT
+  // weights stay packed as the FTB_DUR_SIMT=1 path
+  const bool split = f32_only && h->half_mode() && E % 64 == 0 && dfft % 64 == 0 &&
+                     !(getenv("FTB_DUR_SIMT") && atoi(getenv("FTB_DUR_SIMT")));
+  W.tc_split = split;
   FTB_REQUIRE(heads > 0 && E % heads == 0 && (E / heads == 64 || E / heads == 128), FTB_ERR_UNSUPPORTED,
               "%s: head dim %d not built (64, 128)", p.c_str(), heads ? E / heads : 0);
   FTB_REQUIRE(E % 64 == 0 && dfft % 64 == 0 && E <= 1024, FTB_ERR_UNSUPPORTED, "%s: d_model/d_fft must be multiples of 64",
@@ -81,11 +87,11 @@ static int build_transformer(ftb_fp_handle* h, TransformerW& W, const std::strin
     const std::string q = p + ".layers." + std::to_string(i);
     FftBlockW& L = W.layers[i];
     FTB_TRY(h->make_conv(L.qkv, q + ".self_attn.in_proj_weight", 3 * E, E, 1, 0, false, "", q + ".self_attn.in_proj_bias",
-                         w32, w16));
+                         w32, w16, split));
     FTB_TRY(h->make_conv(L.out_proj, q + ".self_attn.out_proj.weight", E, E, 1, 0, false, "",
-                         q + ".self_attn.out_proj.bias", w32, w16));
-    FTB_TRY(h->make_conv(L.conv1, q + ".conv1.weight", dfft, E, k1, k1 / 2, true, "", q + ".conv1.bias", w32, w16));
-    FTB_TRY(h->make_conv(L.conv2, q + ".conv2.weight", E, dfft, k2, k2 / 2, false, "", q + ".conv2.bias", w32, w16));
+                         q + ".self_attn.out_proj.bias", w32, w16, split));
+    FTB_TRY(h->make_conv(L.conv1, q + ".conv1.weight", dfft, E, k1, k1 / 2, true, "", q + ".conv1.bias", w32, w16, split));
+    FTB_TRY(h->make_conv(L.conv2, q + ".conv2.weight", E, dfft, k2, k2 / 2, false, "", q + ".conv2.bias", w32, w16, split));
     FTB_TRY(h->get(q + ".norm1.weight", {E}, &L.n1w));
     FTB_TRY(h->get(q + ".norm1.bias", {E}, &L.n1b));
     FTB_TRY(h->get(q + ".norm2.weight", {E}, &L.n2w));
@@ -151,6 +157,53 @@ static int run_transformer(ftb_fp_handle* h, TransformerW& W, T* x, float* x32_b
   return FTB_OK;
 }
 
+// The fp32 stack with split-precision tensor-core GEMMs: x32 (B,S,E) fp32 is transformed in place.  Every GEMM
+// operand is the three-bf16-part copy of an fp32 tensor (split3_rows / the split epilogue); attention, LayerNorm,
+// residual stream and biases stay fp32.
+struct TrSplitBufs {
+  bf16 *xs, *ctxs, *f1s;
+  float *qkv, *ctx, *a32;
+};
+static TrSplitBufs plan_tr_split(Arena& A, const TransformerW& W, int B, int S) {
+  TrSplitBufs w;
+  const int64_t M = (int64_t)B * S;
+  w.xs = A.take<bf16>(M * 3 * W.E);
+  w.ctxs = A.take<bf16>(M * 3 * W.E);
+  w.f1s = A.take<bf16>(M * 3 * W.dfft);
+  w.qkv = A.take<float>(M * 3 * W.E);
+  w.ctx = A.take<float>(M * W.E);
+  w.a32 = A.take<float>(M * W.E);
+  return w;
+}
+static int run_transformer_split(ftb_fp_handle* h, TransformerW& W, float* x32, int B, int S, Arena& A, cudaStream_t s) {
+  FTB_REQUIRE(S <= W.max_len, FTB_ERR_INVALID, "The size of tensor a (%d) must match the size of tensor b (%d) at "
+              "non-singleton dimension 0", S, W.max_len);
+  const int64_t mark = A.mark();
+  TrSplitBufs w = plan_tr_split(A, W, B, S);
+  FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for ForwardTransformer");
+  const int64_t M = (int64_t)B * S;
+  const int E = W.E;
+  FTB_TRY(posenc_add<float>(x32, W.pe, W.scale, B, S, E, s));
+  FTB_TRY(split3_rows(x32, w.xs, M, E, s));
+  for (FftBlockW& L : W.layers) {
+    FTB_TRY(h->gemm_split(L.qkv, w.xs, B, S, w.qkv, 3 * E, nullptr, s));
+    FTB_TRY(attention<float>(w.qkv, nullptr, w.ctx, B, S, E, W.heads, s));
+    FTB_TRY(split3_rows(w.ctx, w.ctxs, M, E, s));
+    FTB_TRY(h->gemm_split(L.out_proj, w.ctxs, B, S, w.a32, E, nullptr, s, x32, E));  // + bias + residual
+    FTB_TRY(layernorm(w.a32, L.n1w, L.n1b, x32, nullptr, 0, M, E, s));
+    FTB_TRY(split3_rows(x32, w.xs, M, E, s));
+    FTB_TRY(h->gemm_split(L.conv1, w.xs, B, S, nullptr, 0, w.f1s, s));                // + bias, ReLU -> three parts
+    FTB_TRY(h->gemm_split(L.conv2, w.f1s, B, S, w.a32, E, nullptr, s, x32, E));      // + bias + residual
+    FTB_TRY(layernorm(w.a32, L.n2w, L.n2b, x32, nullptr, 0, M, E, s));
+    FTB_TRY(split3_rows(x32, w.xs, M, E, s));
+    h->launches += 6;
+  }
+  FTB_TRY(layernorm(x32, W.nw, W.nb, x32, nullptr, 0, M, E, s));
+  h->launches += 3;
+  A.reset(mark);
+  return FTB_OK;
+}
+
 template <typename T>
 static int run_fp_series(ftb_fp_handle* h, FpSeriesW& P, const int64_t* tok, int B, int Tn, float alpha, float* out,
                          Arena& A, cudaStream_t s) {
@@ -160,7 +213,10 @@ static int run_fp_series(ftb_fp_handle* h, FpSeriesW& P, const int64_t* tok, int
   float* x32 = std::is_same<T, float>::value ? (float*)x : A.take<float>(M * P.tr.E);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for SeriesPredictor");
   FTB_TRY(embed<T>(tok, P.emb, x, M, P.tr.E, P.tr.E, h->cfg.num_chars, s));
-  FTB_TRY(run_transformer<T>(h, P.tr, x, x32, nullptr, B, Tn, A, s));
+  if (std::is_same<T, float>::value && P.tr.tc_split)
+    FTB_TRY(run_transformer_split(h, P.tr, x32, B, Tn, A, s));
+  else
+    FTB_TRY(run_transformer<T>(h, P.tr, x, x32, nullptr, B, Tn, A, s));
   FTB_TRY(head1<float>(x32, P.lin_w, P.lin_b, alpha, out, M, P.tr.E, s));  // head reads the fp32 stream
   h->launches += 2;
   A.reset(mark);
@@ -195,7 +251,10 @@ static int64_t fp_series_bytes(const ftb_fp_handle* h, int i, int B, int Tn) {
   Arena A(nullptr, 0);
   if (h->series[i].tr.f32_only || !h->half_mode()) {
     A.take<float>((int64_t)B * Tn * h->series[i].tr.E);
-    plan_tr<float>(A, h->series[i].tr, B, Tn);
+    if (h->series[i].tr.tc_split)
+      plan_tr_split(A, h->series[i].tr, B, Tn);
+    else
+      plan_tr<float>(A, h->series[i].tr, B, Tn);
   } else {
     A.take<T>((int64_t)B * Tn * h->series[i].tr.E);
     A.take<float>((int64_t)B * Tn * h->series[i].tr.E);

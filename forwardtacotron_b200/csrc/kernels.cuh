@@ -50,6 +50,7 @@ int attention(const T* qkv, const int64_t* tokens_for_mask, T* ctx, int B, int S
 // elementwise.cu
 template <typename T>
 int embed(const int64_t* tok, const float* table, T* out, int64_t rows, int C, int ldo, int num_chars, cudaStream_t s);
+int split3_rows(const float* in, __nv_bfloat16* out, int64_t rows, int C, cudaStream_t s);
 int embed_split3(const int64_t* tok, const float* table, __nv_bfloat16* out, int64_t rows, int C, int num_chars, cudaStream_t s);
 template <typename T>
 int maxpool_inplace(T* x, int B, int S, int C, cudaStream_t s);

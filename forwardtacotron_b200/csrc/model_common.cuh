@@ -229,7 +229,8 @@ struct ModelBase {
   // fp32-grade conv / linear on the tensor cores (duration predictor): x holds the three bf16 parts of an fp32
   // activation, (B,S,3*CinP); the result goes out either as fp32 (out32, ld = ldo) or again as three parts
   // (out_split, (B,S,3*N)).  6 part products accumulate in fp32 in TMEM, smallest first (conv_gemm_tc.cu).
-  int gemm_split(const Layer& L, const bf16* x, int B, int S, float* out32, int ldo, bf16* out_split, cudaStream_t s) {
+  int gemm_split(const Layer& L, const bf16* x, int B, int S, float* out32, int ldo, bf16* out_split, cudaStream_t s,
+                 const float* residual32 = nullptr, int ldr = 0) {
     FTB_REQUIRE(L.w16s, FTB_ERR_INVALID, "layer has no split-precision weights packed");
     TcItem it;
     it.w = L.w16s;
@@ -249,6 +250,8 @@ struct ModelBase {
     } else {
       o.out_f32 = out32;
       o.ldo = ldo;
+      o.res_f32 = residual32;
+      o.ldr = ldr;
     }
     ++launches;
     ProfScope prof(FAM_GEMM_TC, 2.0 * B * S * (double)L.N * L.k * L.Cin, 0.0, s);
