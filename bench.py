@@ -198,8 +198,14 @@ def roofline_of(fam, pk):
         return {'kernel': fam['name'], 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s',
                 'frac': ach / pk['hbm'], 'traffic': ncu.get(fam['name']), 'peak_source': pk['src']}
     ach = fam['flops_per_step'] / sec / 1e12
-    return {'kernel': fam['name'], 'bound': 'tensor', 'achieved': ach, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
-            'frac': ach / pk['tensor'], 'traffic': ncu.get(fam['name']), 'peak_source': pk['src'] + ' (sustained bf16)'}
+    out = {'kernel': fam['name'], 'bound': 'tensor', 'achieved': ach, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
+           'frac': ach / pk['tensor'], 'traffic': ncu.get(fam['name']), 'peak_source': pk['src'] + ' (sustained bf16)'}
+    if fam['name'].startswith('rnn_'):
+        out['note'] = ('recurrence: a chain of dependent time steps (T or L per launch), bound by the per-step latency '
+                       '(DSMEM hand-off + dependent MMA chain + gate maths, DESIGN.md 4), not by the tensor pipe; '
+                       + ('exact-fp32 SIMT kernel, listed against the tensor peak only for scale'
+                          if fam['name'] == 'rnn_gru_small' else 'the fraction is reported for completeness'))
+    return out
 
 
 def stft_extra(torch, dev, pk):
