@@ -306,14 +306,14 @@ def gather_extra(torch, dist, model, dev, world):
 
 
 def long_article_extra(torch, dev):
-    """BASELINE.json configs[4] at 1/4 of its utterance count: ForwardTacotron on 64 x 2000-phoneme utterances,
-    length-bucketed into batches of 32 (utils/batching.synthesize_corpus, batches in flight on separate streams),
-    alpha sweep 0.8 / 1.0 / 1.2.  Wall clock including the host-side bucketing and the per-row slicing."""
+    """BASELINE.json configs[4]: ForwardTacotron on 256 x 2000-phoneme utterances, length-bucketed into batches of 32
+    (utils/batching.synthesize_corpus, batches in flight on separate streams), alpha sweep 0.8 / 1.0 / 1.2.
+    Wall clock including the host-side bucketing and the per-row slicing."""
     from forwardtacotron_b200.utils import batching, synth
     model, _ = synth.synthetic_model('forward_tacotron')
     model = model.to(dev)
     g = torch.Generator().manual_seed(11)
-    utts = [torch.randint(1, 135, (int(n),), generator=g).tolist() for n in torch.randint(1900, 2001, (64,), generator=g)]
+    utts = [torch.randint(1, 135, (int(n),), generator=g).tolist() for n in torch.randint(1900, 2001, (256,), generator=g)]
     res = {}
     # warm-up at the LONGEST setting (alpha 0.8): lanes and packed weights are created and the workspaces sized once
     batching.synthesize_corpus(model, utts, alpha=0.8, max_tokens=65536, in_flight=2)
@@ -325,7 +325,7 @@ def long_article_extra(torch, dev):
         dt = time.perf_counter() - t0
         frames = sum(int(m.shape[1]) for m in mels)
         res[f'alpha_{alpha}'] = {'frames': frames, 'ms': dt * 1e3, 'frames_per_s': frames / dt}
-    return {'metric': 'mel_frames_per_s', 'unit': 'frames/s', 'utterances': 64, 'phonemes_per_utterance': '1900-2000',
+    return {'metric': 'mel_frames_per_s', 'unit': 'frames/s', 'utterances': 256, 'phonemes_per_utterance': '1900-2000',
             'batching': 'length-bucketed, 32 utterances per batch, 2 batches in flight', **res}
 
 
