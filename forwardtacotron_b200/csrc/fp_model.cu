@@ -175,7 +175,8 @@ static TrSplitBufs plan_tr_split(Arena& A, const TransformerW& W, int B, int S) 
   w.a32 = A.take<float>(M * W.E);
   return w;
 }
-static int run_transformer_split(ftb_fp_handle* h, TransformerW& W, float* x32, int B, int S, Arena& A, cudaStream_t s) {
+static int run_transformer_split(ftb_fp_handle* h, TransformerW& W, float* x32, const int64_t* mask_tokens, int B, int S,
+                                 Arena& A, cudaStream_t s) {
   FTB_REQUIRE(S <= W.max_len, FTB_ERR_INVALID, "The size of tensor a (%d) must match the size of tensor b (%d) at "
               "non-singleton dimension 0", S, W.max_len);
   const int64_t mark = A.mark();
@@ -187,7 +188,7 @@ static int run_transformer_split(ftb_fp_handle* h, TransformerW& W, float* x32, 
   FTB_TRY(split3_rows(x32, w.xs, M, E, s));
   for (FftBlockW& L : W.layers) {
     FTB_TRY(h->gemm_split(L.qkv, w.xs, B, S, w.qkv, 3 * E, nullptr, s));
-    FTB_TRY(attention<float>(w.qkv, nullptr, w.ctx, B, S, E, W.heads, s));
+    FTB_TRY(attention<float>(w.qkv, mask_tokens, w.ctx, B, S, E, W.heads, s));
     FTB_TRY(split3_rows(w.ctx, w.ctxs, M, E, s));
     FTB_TRY(h->gemm_split(L.out_proj, w.ctxs, B, S, w.a32, E, nullptr, s, x32, E));  // + bias + residual
     FTB_TRY(layernorm(w.a32, L.n1w, L.n1b, x32, nullptr, 0, M, E, s));
@@ -206,7 +207,8 @@ static int run_transformer_split(ftb_fp_handle* h, TransformerW& W, float* x32, 
 
 template <typename T>
 static int run_fp_series(ftb_fp_handle* h, FpSeriesW& P, const int64_t* tok, int B, int Tn, float alpha, float* out,
-                         Arena& A, cudaStream_t s) {
+                         Arena& A, cudaStream_t s, bool masked = false) {
+  const int64_t* mask = masked ? tok : nullptr;  // forward(): src_pad_mask = (x == 0), models/fast_pitch.py:255-258
   const int64_t mark = A.mark();
   const int64_t M = (int64_t)B * Tn;
   T* x = A.take<T>(M * P.tr.E);
@@ -214,9 +216,9 @@ static int run_fp_series(ftb_fp_handle* h, FpSeriesW& P, const int64_t* tok, int
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for SeriesPredictor");
   FTB_TRY(embed<T>(tok, P.emb, x, M, P.tr.E, P.tr.E, h->cfg.num_chars, s));
   if (std::is_same<T, float>::value && P.tr.tc_split)
-    FTB_TRY(run_transformer_split(h, P.tr, x32, B, Tn, A, s));
+    FTB_TRY(run_transformer_split(h, P.tr, x32, mask, B, Tn, A, s));
   else
-    FTB_TRY(run_transformer<T>(h, P.tr, x, x32, nullptr, B, Tn, A, s));
+    FTB_TRY(run_transformer<T>(h, P.tr, x, x32, mask, B, Tn, A, s));
   FTB_TRY(head1<float>(x32, P.lin_w, P.lin_b, alpha, out, M, P.tr.E, s));  // head reads the fp32 stream
   h->launches += 2;
   A.reset(mark);
@@ -225,7 +227,8 @@ static int run_fp_series(ftb_fp_handle* h, FpSeriesW& P, const int64_t* tok, int
 
 template <typename T>
 static int run_fp_synthesize(ftb_fp_handle* h, const int64_t* tok, const int32_t* cum, const float* pitch,
-                             const float* energy, int B, int Tn, int L, float* mel, Arena& A, cudaStream_t s) {
+                             const float* energy, int B, int Tn, int L, float* mel, Arena& A, cudaStream_t s,
+                             const int64_t* post_mask = nullptr) {
   const ftb_fp_config& c = h->cfg;
   const int E = c.d_model;
   const int64_t MT = (int64_t)B * Tn, ML = (int64_t)B * L;
@@ -238,7 +241,7 @@ static int run_fp_synthesize(ftb_fp_handle* h, const int64_t* tok, const int32_t
   FTB_TRY(cond_add<T>(x, pitch, energy, h->pitch_w, h->pitch_b, h->energy_w, h->energy_b, c.pitch_strength,
                       c.energy_strength, B, Tn, E, s));
   FTB_TRY(ftb_length_expand(x, cum, up, B, Tn, L, E, (int)sizeof(T), s));
-  FTB_TRY(run_transformer<T>(h, h->postnet, up, x32, nullptr, B, L, A, s));
+  FTB_TRY(run_transformer<T>(h, h->postnet, up, x32, post_mask, B, L, A, s));
   Out o;
   o.t = mel;
   FTB_TRY(h->gemm<T>(h->lin, up, E, B, L, o, nullptr, 0, 1.f, s));
@@ -395,6 +398,31 @@ extern "C" int ftb_fp_synthesize(ftb_fp_handle* h, const int64_t* tokens, const 
     return h->is_fp16() ? run_fp_synthesize<f16>(h, tokens, cum, pitch, energy, B, T, L, mel, A, (cudaStream_t)stream)
                         : run_fp_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, A, (cudaStream_t)stream);
   return run_fp_synthesize<float>(h, tokens, cum, pitch, energy, B, T, L, mel, A, (cudaStream_t)stream);
+}
+
+extern "C" int ftb_fp_forward_eval(ftb_fp_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
+                                   const float* energy, const int64_t* frame_mask, int B, int T, int L, float* dur_hat,
+                                   float* pitch_hat, float* energy_hat, float* mel, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+  FTB_REQUIRE(h && tokens && cum && pitch && energy && frame_mask && dur_hat && pitch_hat && energy_hat && mel && workspace,
+              FTB_ERR_INVALID, "ftb_fp_forward_eval: bad arguments");
+  FTB_REQUIRE(B > 0 && T > 0 && L > 0, FTB_ERR_INVALID, "ftb_fp_forward_eval: bad sizes B=%d T=%d L=%d", B, T, L);
+  h->launches = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* outs[3] = {dur_hat, pitch_hat, energy_hat};
+  for (int i = 0; i < 3; ++i) {  // the predictors with the token padding mask, no fallback (models/fast_pitch.py:255-258)
+    Arena A(workspace, workspace_bytes);
+    if (h->series[i].tr.f32_only || !h->half_mode())
+      FTB_TRY(run_fp_series<float>(h, h->series[i], tokens, B, T, 1.f, outs[i], A, s, true));
+    else
+      FTB_TRY(h->is_fp16() ? run_fp_series<f16>(h, h->series[i], tokens, B, T, 1.f, outs[i], A, s, true)
+                           : run_fp_series<bf16>(h, h->series[i], tokens, B, T, 1.f, outs[i], A, s, true));
+  }
+  Arena A(workspace, workspace_bytes);
+  if (h->half_mode())
+    return h->is_fp16() ? run_fp_synthesize<f16>(h, tokens, cum, pitch, energy, B, T, L, mel, A, s, frame_mask)
+                        : run_fp_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, A, s, frame_mask);
+  return run_fp_synthesize<float>(h, tokens, cum, pitch, energy, B, T, L, mel, A, s, frame_mask);
 }
 
 extern "C" int ftb_fp_last_launch_count(const ftb_fp_handle* h) { return h ? h->launches : -1; }

@@ -193,6 +193,47 @@ class FastPitch(NativeModel):
             energy_hat = energy_function(energy_hat)
             return self.synthesize(x, dur_hat, pitch_hat, energy_hat, mel_post_alloc)
 
+    def forward(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Teacher-forced forward in EVAL mode (models/fast_pitch.py:243-283): predictors and prenet with the token
+        padding mask, durations / pitch / energy of the batch drive the synthesis, the postnet masks the frames past
+        ``mel_len`` as keys, outputs cut / padded to ``mel.size(2)`` with ``padding_value``; 'mel_post' is 'mel'.
+        Training mode is outside the path this package implements."""
+        if self.training:
+            raise NotImplementedError('training-mode forward() is outside the hot path this package implements '
+                                      '(SURVEY 8f-4); call .eval() for the teacher-forced inference pass')
+        with torch.no_grad():
+            x = self._check_tokens(batch['x'])
+            lib, dev = _lib.lib(), x.device
+            B, T = x.shape
+            self._check_len(T)
+            dur = batch['dur']
+            if dur.dtype != torch.float32 or not dur.is_contiguous() or dur.device != dev:
+                dur = dur.to(device=dev, dtype=torch.float32).contiguous()
+            pitch = batch['pitch'].to(device=dev, dtype=torch.float32).reshape(B, T).contiguous()
+            energy = batch['energy'].to(device=dev, dtype=torch.float32).reshape(B, T).contiguous()
+            cum, total = LengthRegulator.plan(dur)
+            L = int(total.max().item())
+            if L <= 0:
+                raise RuntimeError('all rounded durations are zero: nothing to synthesize')
+            self._check_len(L)
+            mel_lens = batch['mel_len'].to(dev)
+            frame_mask = (torch.arange(L, device=dev)[None, :] < mel_lens[:, None]).to(torch.int64).contiguous()
+            h = self._get_handle(dev)
+            ws = self._workspace_for(h, B, T, L, dev)
+            dur_hat = torch.empty((B, T), dtype=torch.float32, device=dev)
+            pitch_hat = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
+            energy_hat = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
+            mel = torch.empty((B, self._dims['n_mels'], L), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.ftb_fp_forward_eval(h, _lib.ptr(x), _lib.ptr(cum), _lib.ptr(pitch), _lib.ptr(energy),
+                                                   _lib.ptr(frame_mask), B, T, L, _lib.ptr(dur_hat), _lib.ptr(pitch_hat),
+                                                   _lib.ptr(energy_hat), _lib.ptr(mel), _lib.ptr(ws), ws.numel(),
+                                                   _lib.current_stream(dev)))
+            max_len = int(batch['mel'].size(2))
+            mel = mel[:, :, :max_len]
+            mel = torch.nn.functional.pad(mel, [0, max_len - mel.size(2), 0, 0], 'constant', self.padding_value)
+            return {'mel': mel, 'mel_post': mel, 'dur': dur_hat, 'pitch': pitch_hat, 'energy': energy_hat}
+
     def last_launch_count(self) -> int:
         return int(_lib.lib().ftb_fp_last_launch_count(self._handle)) if self._handle is not None else 0
 

@@ -291,6 +291,15 @@ int ftb_fp_predict(ftb_fp_handle* h, const int64_t* tokens, int B, int T, float 
 int ftb_fp_synthesize(ftb_fp_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
                       const float* energy, int B, int T, int L, float* mel, void* workspace,
                       int64_t workspace_bytes, void* stream);
+
+/* FastPitch.forward in eval mode (models/fast_pitch.py:243-283; the teacher-forced pass): the three predictors with the
+ * token padding mask (keys with id 0 ignored) and no fallback -> dur_hat / pitch_hat / energy_hat (B,T); then stage B
+ * with the batch's durations (cum from ftb_length_plan), pitch and energy, the prenet masked by the tokens and the
+ * postnet by frame_mask: (B,L) int64, 0 = padded frame (t >= mel_len[b], make_mel_len_mask :47-51).  mel (B,n_mels,L). */
+int ftb_fp_forward_eval(ftb_fp_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
+                        const float* energy, const int64_t* frame_mask, int B, int T, int L, float* dur_hat,
+                        float* pitch_hat, float* energy_hat, float* mel, void* workspace, int64_t workspace_bytes,
+                        void* stream);
 int ftb_fp_last_launch_count(const ftb_fp_handle* h);
 
 #ifdef __cplusplus

@@ -1,5 +1,6 @@
-"""Pins oracle.model_oracle.ft_forward (teacher-forced forward in eval mode, the GTA feature path) against the REAL
-reference and freezes tests/golden/ft_forward_b3_t30.npz.  Runs in the build container only (/root/reference).
+"""Pins oracle.model_oracle.ft_forward / fp_forward (teacher-forced forward in eval mode, the GTA feature path) against
+the REAL reference and freezes tests/golden/ft_forward_b3_t30.npz and fp_forward_b3_t30.npz.  Runs in the build container
+only (/root/reference).
 
     python oracle/make_golden_forward.py
 """
@@ -64,6 +65,27 @@ def main():
                         mel=r['mel'].numpy(), mel_post=r['mel_post'].numpy(), dur=r['dur'].numpy(),
                         pitch=r['pitch'].numpy(), energy=r['energy'].numpy())
     print('ft_forward_b3_t30', errs, 'mel', tuple(r['mel'].shape), 'mel_len', batch['mel_len'].tolist())
+
+    # ---- FastPitch: token padding mask on predictors / prenet, mel-length key mask on the postnet
+    from models.fast_pitch import FastPitch as RefFP  # type: ignore
+    model, cfg = synth.synthetic_model('fast_pitch')
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    ref = RefFP.from_config(copy.deepcopy(cfg))
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    batch = synthetic_batch(seed=22)
+    batch['x'][1, 30 // 2:] = 0        # padded tokens (their durations are already 0): exercises the token mask
+    with torch.no_grad():
+        r = ref({k: v.clone() for k, v in batch.items()})
+    o = mo.fp_forward(sd, {k: v.clone() for k, v in batch.items()}, ref.pitch_strength, ref.energy_strength)
+    errs = {k: float((r[k] - o[k]).abs().max()) for k in ('mel', 'mel_post', 'dur', 'pitch', 'energy')}
+    assert r['mel'].shape == o['mel'].shape and max(errs.values()) < 2e-5, errs
+    np.savez_compressed(GOLD / 'fp_forward_b3_t30.npz', x=batch['x'].numpy(), dur_in=batch['dur'].numpy(),
+                        mel_len=batch['mel_len'].numpy(), mel_frames=np.int64(batch['mel'].size(2)),
+                        pitch_in=batch['pitch'].numpy(), energy_in=batch['energy'].numpy(),
+                        mel=r['mel'].numpy(), mel_post=r['mel_post'].numpy(), dur=r['dur'].numpy(),
+                        pitch=r['pitch'].numpy(), energy=r['energy'].numpy())
+    print('fp_forward_b3_t30', errs, 'mel', tuple(r['mel'].shape), 'mel_len', batch['mel_len'].tolist())
 
 
 if __name__ == '__main__':

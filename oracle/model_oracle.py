@@ -292,6 +292,33 @@ def fp_synthesize(sd: SD, tokens, dur, pitch, energy, pitch_strength=1.0, energy
     return {'mel': mel, 'mel_post': mel, 'dur': dur, 'pitch': pitch, 'energy': energy}
 
 
+def fp_forward(sd: SD, batch: Dict[str, torch.Tensor], pitch_strength=1.0, energy_strength=1.0,
+               heads=(2, 2, 2, 2, 2), padding_value: float = -11.5129) -> Dict[str, torch.Tensor]:
+    """Teacher-forced ``FastPitch.forward`` in eval mode, models/fast_pitch.py:243-283: predictors and prenet with the
+    token padding mask (:255-261), batch durations / pitch / energy, postnet with the mel-length key mask (:274-278),
+    outputs cut / padded to ``mel.size(2)`` (:283-284).  ``batch['dur']`` is clamped in place."""
+    with torch.no_grad():
+        x, mel_lens = batch['x'], batch['mel_len']
+        tok_mask = x == 0
+
+        def series(p, hd):
+            t = forward_transformer(sd, p + '.transformer', sd[p + '.embedding.weight'][x], hd, key_pad=tok_mask)
+            return t @ sd[p + '.lin.weight'].T + sd[p + '.lin.bias']
+        dur_hat = series('dur_pred', heads[0]).squeeze(-1)
+        pitch_hat = series('pitch_pred', heads[1]).transpose(1, 2)
+        energy_hat = series('energy_pred', heads[2]).transpose(1, 2)
+        h = forward_transformer(sd, 'prenet', sd['embedding.weight'][x], heads[3], key_pad=tok_mask)
+        h = h + cond_proj(sd, 'pitch_proj', batch['pitch'].unsqueeze(1)) * pitch_strength
+        h = h + cond_proj(sd, 'energy_proj', batch['energy'].unsqueeze(1)) * energy_strength
+        h = length_regulate(h, batch['dur'])
+        len_mask = torch.arange(h.shape[1])[None, :] >= mel_lens[:, None]
+        h = forward_transformer(sd, 'postnet', h, heads[4], key_pad=len_mask)
+        mel = (h @ sd['lin.weight'].T + sd['lin.bias']).transpose(1, 2)
+        max_len = batch['mel'].size(2)
+        mel = F.pad(mel[:, :, :max_len], [0, max_len - min(max_len, mel.size(2)), 0, 0], 'constant', padding_value)
+        return {'mel': mel, 'mel_post': mel, 'dur': dur_hat, 'pitch': pitch_hat, 'energy': energy_hat}
+
+
 def fp_generate(sd: SD, tokens, alpha: float = 1.0, pitch_function: Callable = _IDENT,
                 energy_function: Callable = _IDENT, pitch_strength=1.0, energy_strength=1.0,
                 heads=(2, 2, 2, 2, 2)) -> Dict[str, torch.Tensor]:

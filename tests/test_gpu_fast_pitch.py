@@ -4,7 +4,7 @@ import torch
 
 from oracle import model_oracle as mo
 
-from util import assert_close, cpu_state_dict, cuda_model, load, near_tie_mask, rounded
+from util import MAX_ABS, MEAN_ABS, assert_close, cpu_state_dict, cuda_model, load, near_tie_mask, rounded
 from forwardtacotron_b200.utils import synth
 
 pytestmark = pytest.mark.gpu
@@ -61,3 +61,28 @@ def test_bf16_tensor_core_mode_is_opt_in():
     assert torch.equal(rounded(out['dur']), rounded(g['dur']))
     mx, mn = assert_close(out['mel'], g['mel'], 5e-2, 5e-3, 'mel (bf16 GEMMs)')
     print('fp gemm_mode 2', mx, mn)
+
+
+@pytest.mark.parametrize('gemm_mode', [1, 0])
+def test_teacher_forced_forward_against_reference_fixture(gemm_mode):
+    """FastPitch.forward in eval mode (models/fast_pitch.py:243-283) against the reference's own output: masked
+    predictors / prenet, batch durations, postnet masked past mel_len, padded to mel.size(2)."""
+    g = load('fp_forward_b3_t30')
+    model, _ = cuda_model('fast_pitch', gemm_mode)
+    model.eval()
+    B = g['x'].shape[0]
+    batch = {'x': g['x'].cuda(), 'dur': g['dur_in'].clone().cuda(), 'mel_len': g['mel_len'].cuda(),
+             'pitch': g['pitch_in'].cuda(), 'energy': g['energy_in'].cuda(),
+             'mel': torch.zeros(B, 80, int(g['mel_frames']), device='cuda')}
+    out = model(batch)
+    assert out['mel_post'] is out['mel'] and out['mel'].shape == g['mel'].shape
+    tol = (1e-4, 1e-5) if gemm_mode == 1 else (MAX_ABS, MEAN_ABS)
+    assert_close(out['dur'], g['dur'], 1e-4, 1e-5, 'dur_hat')
+    assert_close(out['pitch'], g['pitch'], *tol, 'pitch_hat')
+    assert_close(out['energy'], g['energy'], *tol, 'energy_hat')
+    for b, n in enumerate(g['mel_len'].tolist()):     # the frames a GTA dump keeps
+        assert_close(out['mel'][b, :, :n], g['mel'][b, :, :n], *tol, f'mel[{b}] valid frames')
+    assert_close(out['mel'], g['mel'], 2 * tol[0], 2 * tol[1], 'mel (all frames)')
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(batch)

@@ -93,3 +93,14 @@ def test_forward_fixture():
         assert out[k].shape == g[k].shape and float((out[k] - g[k]).abs().max()) < 2e-5, k
     n = int(g['mel_len'].max())
     assert torch.all(out['mel'][:, :, n:] == -11.5129) and torch.all(out['mel_post'][:, :, n:] == -11.5129)
+
+
+def test_fastpitch_forward_fixture():
+    """FastPitch.forward in eval mode: token padding mask on predictors / prenet, mel-length key mask on the postnet."""
+    g = load('fp_forward_b3_t30')
+    model, _ = synth.synthetic_model('fast_pitch')
+    out = mo.fp_forward(model.state_dict(), _forward_batch(g), model.pitch_strength, model.energy_strength)
+    for k in ('mel', 'mel_post', 'dur', 'pitch', 'energy'):
+        assert out[k].shape == g[k].shape and float((out[k] - g[k]).abs().max()) < 2e-5, k
+    assert bool((g['x'] == 0).any())                                   # the fixture really has padded tokens
+    assert torch.all(out['mel'][:, :, int((g['dur_in'].clamp(min=0) + 0.5).long().sum(1).max()):] == -11.5129)
