@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Accuracy of the duration predictor paths against an fp64 evaluation of the reference algorithm:
 split-precision tensor-core GEMMs (default) vs the fp32 SIMT GEMM (FTB_OPT_DUR_SIMT) vs the fp32 CPU oracle.
-    python scripts/dur_split_check.py        (needs a B200)"""
+    python tests/dur_split_check.py        (needs a B200)"""
 import sys
 import time
 from pathlib import Path
