@@ -291,3 +291,29 @@ def test_packed_forward_many_rows():
     out = model({k: v.cuda() for k, v in batch.items()})
     for b, n in enumerate(batch['mel_len'].tolist()):
         assert_close(out['mel_post'][b, :, :n], want['mel_post'][b, :, :n], what=f'mel_post[{b}]')
+
+
+@pytest.mark.parametrize('B', [1, 5])
+def test_packed_forward_mel_len_shorter_than_expansion(B):
+    """mel_len may be shorter than the expanded length (pack_padded_sequence only reads the first mel_len frames): the
+    synthesis length is max(mel_len), not max(sum(dur)); also the single-utterance batch."""
+    model, _ = cuda_model('forward_tacotron', 0)
+    model.eval()
+    gen = torch.Generator().manual_seed(17 + B)
+    T = 14
+    dur = torch.randint(1, 6, (B, T), generator=gen).float()
+    total = (dur + 0.5).long().sum(1)
+    mel_len = (total - torch.arange(B) % 4 - 1).clamp(min=1)      # 1..4 frames short
+    batch = {'x': torch.randint(1, 135, (B, T), generator=gen), 'dur': dur, 'mel_len': mel_len,
+             'pitch': torch.randn(B, T, generator=gen), 'energy': torch.randn(B, T, generator=gen),
+             'mel': torch.zeros(B, 80, int(mel_len.max()))}
+    want = mo.ft_forward(cpu_state_dict(model), {k: v.clone() for k, v in batch.items()}, model.pitch_strength,
+                         model.energy_strength)
+    out = model({k: v.cuda() for k, v in batch.items()})
+    assert out['mel'].shape == want['mel'].shape == (B, 80, int(mel_len.max()))
+    for b, n in enumerate(mel_len.tolist()):
+        assert_close(out['mel'][b, :, :n], want['mel'][b, :, :n], what=f'mel[{b}]')
+        assert_close(out['mel_post'][b, :, :n], want['mel_post'][b, :, :n], what=f'mel_post[{b}]')
+    bad = dict(batch, mel_len=total + 1)
+    with pytest.raises(RuntimeError):
+        model({k: v.cuda() for k, v in bad.items()})
