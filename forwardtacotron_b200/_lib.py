@@ -86,13 +86,16 @@ SIGNATURES = {
     'ftb_device_check': (_I, [_I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     'ftb_length_plan': (_I, [_P, _P, _P, _I, _I, _P]),
     'ftb_length_expand': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'ftb_length_index': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'ftb_duration_fallback': (_I, [_P, _L, _P, _P]),
     'ftb_conv_gemm_f32': (_I, [_P, _P, C.POINTER(ConvDesc), _P]),
     'ftb_conv_gemm_bf16': (_I, [_P, _P, C.POINTER(ConvDesc), _P]),
     'ftb_conv_bank_bf16': (_I, [_P, C.POINTER(_P), C.POINTER(ConvDesc), _I, _I, _P]),
     'ftb_tc_timeout_count': (_I, []),
     'ftb_pack_conv_weight': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'ftb_linear_pair': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     'ftb_rnn_bidir': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'ftb_rnn_bidir_rows': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'ftb_mel_create': (_I, [C.POINTER(MelConfig), _I, C.POINTER(_P)]),
     'ftb_mel_destroy': (None, [_P]),
     'ftb_mel_run': (_I, [_P, _P, _P, _P, _I, _L, _P, _I, _P]),

@@ -134,6 +134,53 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// mbarrier wait of the pipelined kernels.  A wait that never completes is a protocol bug; it must neither hang the GPU
+// nor let the kernel run on with data that has not arrived.  So the spin is bounded (2^27 polls: seconds, far beyond
+// any legitimate wait -- polls only advance while the warp is scheduled, so time-slicing does not eat the budget) and
+// on expiry the kernel records the fact and TRAPS: the launch fails, the next CUDA call of the host returns an error
+// (FTB_ERR_CUDA / a torch exception) and no output of that launch is ever consumed silently.
+static __device__ int g_mbar_timeouts = 0;  // one copy per translation unit (no -rdc); summed by ftb_tc_timeout_count()
+#define FTB_DEFINE_TIMEOUT_READER(name)                                                           \
+  int name() {                                                                                    \
+    int v = -1;                                                                                   \
+    return cudaMemcpyFromSymbol(&v, g_mbar_timeouts, sizeof(int)) == cudaSuccess ? v : -1;        \
+  }
+__device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > (1u << 27)) {
+      atomicAdd(&g_mbar_timeouts, 1);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+// h -> out[o] as f32 (kind 0), bf16 (1) or IEEE half (2).  lo_off > 0 (16-bit kinds): the rounding remainder h - hi goes
+// to out[o + lo_off] in the same 16-bit type, so a consumer GEMM can use hi + lo (16 / 22 significand bits) -- the output
+// heads multiply this tensor by trained-magnitude weights and need more than a 16-bit activation.
+__device__ __forceinline__ void store_h(void* out, int64_t o, int lo_off, int kind, float h) {
+  if (kind == 2) {
+    const __half hi = __float2half_rn(h);
+    reinterpret_cast<__half*>(out)[o] = hi;
+    if (lo_off) reinterpret_cast<__half*>(out)[o + lo_off] = __float2half_rn(h - __half2float(hi));
+  } else if (kind) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(h);
+    reinterpret_cast<__nv_bfloat16*>(out)[o] = hi;
+    if (lo_off) reinterpret_cast<__nv_bfloat16*>(out)[o + lo_off] = __float2bfloat16_rn(h - __bfloat162float(hi));
+  } else {
+    reinterpret_cast<float*>(out)[o] = h;
+  }
+}
+
 template <typename T>
 struct ActIO;
 template <>

@@ -155,6 +155,25 @@ __global__ void pack_conv_weight_split3_kernel(const float* __restrict__ w, __nv
   }
 }
 
+// (N, Cin, k) f32 -> (Npad, 3, k, Cin_pad) 16-bit [hi | hi | lo]: the K axis of a GEMM whose activation comes as the
+// pair hi | lo (conv_gemm_tc.cu, hl_in): w = hi + lo up to 2^-22 (half) / 2^-16 (bf16) relative.
+template <typename T16>
+__global__ void pack_conv_weight_hl_kernel(const float* __restrict__ w, T16* __restrict__ out, int N, int Cin, int k,
+                                           int Npad, int Cin_pad) {
+  const int64_t per_n = (int64_t)k * Cin_pad, total = (int64_t)Npad * per_n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cin_pad);
+    const int j = (int)((i / Cin_pad) % k);
+    const int n = (int)(i / per_n);
+    const float v = (n < N && c < Cin) ? w[((int64_t)n * Cin + c) * k + j] : 0.f;
+    T16 hi, lo;
+    ActIO<T16>::store(&hi, v);
+    ActIO<T16>::store(&lo, v - ActIO<T16>::load(&hi));
+    T16* o = out + (int64_t)n * 3 * per_n + (int64_t)j * Cin_pad + c;
+    o[0] = hi, o[per_n] = hi, o[2 * per_n] = lo;
+  }
+}
+
 int conv_gemm_f32(const float* x, const float* w, const ftb_conv_desc& d, cudaStream_t s) {
   FTB_REQUIRE(x && w, FTB_ERR_INVALID, "conv_gemm_f32: null operand");
   FTB_REQUIRE(d.B > 0 && d.S > 0 && d.N > 0 && d.ktaps > 0, FTB_ERR_INVALID, "conv_gemm_f32: bad shape");
@@ -192,9 +211,16 @@ extern "C" int ftb_pack_conv_weight(const float* w, void* out, int N, int Cin, i
   FTB_REQUIRE(w && out && N > 0 && Cin > 0 && k > 0 && Npad >= N && Cin_pad >= Cin, FTB_ERR_INVALID,
               "ftb_pack_conv_weight: bad arguments");
   const int64_t total = (int64_t)Npad * k * Cin_pad;
+  FTB_REQUIRE(out_bf16 >= 0 && out_bf16 <= 5, FTB_ERR_INVALID, "ftb_pack_conv_weight: unknown output mode %d", out_bf16);
+  const int blocks = (int)std::min<int64_t>(cdiv(total, 256), 4096);
   if (out_bf16 == 3) {
-    pack_conv_weight_split3_kernel<<<(int)std::min<int64_t>(cdiv(total, 256), 4096), 256, 0, (cudaStream_t)stream>>>(
-        w, (__nv_bfloat16*)out, N, Cin, k, Npad, Cin_pad);
+    pack_conv_weight_split3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out, N, Cin, k, Npad, Cin_pad);
+    FTB_CHECK_LAUNCH();
+    return FTB_OK;
+  }
+  if (out_bf16 >= 4) {
+    if (out_bf16 == 4) pack_conv_weight_hl_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out, N, Cin, k, Npad, Cin_pad);
+    else pack_conv_weight_hl_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__half*)out, N, Cin, k, Npad, Cin_pad);
     FTB_CHECK_LAUNCH();
     return FTB_OK;
   }

@@ -40,7 +40,6 @@ constexpr int SMEM_STAGING = EPI_WARPS * 32 * STG_LD * 4;         // 33792
 constexpr int SMEM_BYTES = SMEM_TILES + SMEM_STAGING + 1024 /*alignment slack*/ + 256 /*barriers*/;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);                     // 320
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t SPIN_LIMIT = 1u << 22;  // bounded wait: a protocol bug must not hang the GPU
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16 (format 1) or fp16 (format 0), both
 // K-major, M=128, N=n
@@ -49,7 +48,6 @@ __host__ __device__ constexpr uint32_t idesc_16(int n, bool fp16) {
 }
 }  // namespace tc
 
-__device__ int g_tc_timeouts = 0;  // a barrier wait that gave up (never expected; prevents hangs)
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -61,23 +59,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > tc::SPIN_LIMIT) {
-      atomicAdd(&g_tc_timeouts, 1);
-      break;
-    }
-  }
-}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_or_trap(bar, parity); }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -135,6 +117,7 @@ struct alignas(64) TcArgs {
   int nprob, B, S, Cin, cblocks;
   int m_tiles, m_stride, box_rows, bn, total_tiles, pool, highway, fp16;
   int split_in;   // A holds 3 bf16 parts [hi | mid | lo] of an fp32 tensor; K loop = 6 part products (see conv_gemm_group)
+  uint32_t amap;  // K segment `seg` (one full pass over taps x channel blocks) reads activation part (amap >> 4 seg) & 15
   int split_d;    // split-precision mode: k-blocks per TMEM accumulation unit inside the hi.hi product ...
   int split_ds;   // ... and inside the five small products (their truncation error is 2^-8 of the result's)
   int split_out;  // > 0: the 16-bit output is written as 3 parts, split_out channels apart
@@ -338,7 +321,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         // K order = (part product, tap, 64-channel block); the packed weights follow it, so their K offset is kb * BK.
         // split_in: product `seg` reads activation part (amap >> 4 seg) & 15 -- smallest products first:
         // lo.hi, hi.lo, mid.mid, mid.hi, hi.mid, hi.hi  (weights packed as hi, lo, mid, hi, mid, hi)
-        const uint32_t amap = SPLIT ? 0x001102u : 0u;
+        // hl_in (heads): parts hi | lo, products hi.hi, lo.hi, hi.lo (weights packed as hi, hi, lo)
+        const uint32_t amap = a.amap;
         int j = 0, cb = 0, seg = 0;
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
           const uint32_t st = it % STAGES;
@@ -677,6 +661,10 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.pool = o.pool ? 1 : 0;
   a.split_in = o.split_in ? 1 : 0;
   a.split_out = o.split_out;
+  a.amap = o.split_in ? 0x001102u : o.hl_in ? 0x010u : 0u;
+  const int a_parts = o.split_in ? 3 : o.hl_in ? 2 : 1, nseg = o.split_in ? 6 : o.hl_in ? 3 : 1;
+  FTB_REQUIRE(!(o.hl_in && (o.split_in || o.split_out || o.pool || o.highway)), FTB_ERR_INVALID,
+              "conv_gemm_bf16: the hi/lo input goes with the generic epilogue only");
   static const int split_d = getenv("FTB_SPLIT_D") ? std::max(1, atoi(getenv("FTB_SPLIT_D"))) : 2;
   a.split_d = split_d;
   static const int split_ds = getenv("FTB_SPLIT_DS") ? std::max(1, atoi(getenv("FTB_SPLIT_DS"))) : 20;
@@ -687,7 +675,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
               "conv_gemm_bf16: split output is 16-bit only and needs split input");
   FTB_REQUIRE(!o.split_in || o.split_out || (o.out_f32 && !o.out_bf16), FTB_ERR_INVALID,
               "conv_gemm_bf16: split-precision mode writes either fp32 or three bf16 parts");
-  FTB_REQUIRE(!o.split_in || lda >= 3 * Cin, FTB_ERR_INVALID, "conv_gemm_bf16: split input needs lda >= 3 Cin");
+  FTB_REQUIRE(lda >= a_parts * Cin, FTB_ERR_INVALID, "conv_gemm_bf16: %d-part input needs lda >= %d Cin", a_parts, a_parts);
   a.highway = o.highway ? 1 : 0;
   a.fp16 = o.fp16 ? 1 : 0;
 
@@ -707,7 +695,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   FTB_REQUIRE(!o.out_t || n_items == 1, FTB_ERR_INVALID, "conv_gemm_bf16: transposed output needs a single problem");
   FTB_REQUIRE(!(o.out_t && o.fp16 && o.res_bf16), FTB_ERR_INVALID, "conv_gemm_bf16: fp16 residual with transposed output");
   {
-    cuuint64_t dims[3] = {(cuuint64_t)(o.split_in ? 3 * Cin : Cin), (cuuint64_t)S, (cuuint64_t)B};
+    cuuint64_t dims[3] = {(cuuint64_t)(a_parts * Cin), (cuuint64_t)S, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)lda * 2, (cuuint64_t)S * lda * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)a.box_rows, 1};
     FTB_TRY(make_map(&a.map_a, x, 3, dims, strides, box));
@@ -722,7 +710,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
     TcProb& P = a.prob[i];
     FTB_REQUIRE(it.w && it.N > 0 && it.ktaps > 0 && ((uintptr_t)it.w & 15) == 0, FTB_ERR_INVALID, "conv_gemm_bf16: bad problem");
     FTB_REQUIRE(o.split_in || tc_tile_n(it.N) == a.bn, FTB_ERR_INVALID, "conv_gemm_group: mixed tile widths");
-    const int ktot = (o.split_in ? 6 : 1) * it.ktaps * Cin;
+    const int ktot = nseg * it.ktaps * Cin;
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)it.N};  // rows >= N of the last tile are zero-filled by TMA
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)a.bn};
@@ -737,7 +725,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
     P.n_offset = it.n_offset;
     P.relu = it.relu;
     P.n_tiles = cdiv(it.N, a.bn);
-    P.nkb = (o.split_in ? 6 : 1) * it.ktaps * a.cblocks;
+    P.nkb = nseg * it.ktaps * a.cblocks;
     P.tile_begin = tiles;
     P.idesc = idesc_16(it.N >= a.bn ? a.bn : (int)align_up(it.N, 16), o.fp16);
     tiles += P.n_tiles * a.m_tiles * B;
@@ -823,8 +811,28 @@ extern "C" int ftb_conv_bank_bf16(const void* x, const void* const* w_packed, co
   return conv_gemm_group((const __nv_bfloat16*)x, d0.lda, d0.B, d0.S, d0.Cin, items.data(), n_convs, o, (cudaStream_t)stream);
 }
 
+extern "C" int ftb_linear_pair(const void* x_pair, const void* w_packed, int B, int S, int Cin, int N, const float* bias,
+                               float* out_f32, int ldo, int fp16, void* stream) {
+  FTB_REQUIRE(x_pair && w_packed && out_f32 && B > 0 && S > 0 && Cin > 0 && N > 0 && ldo >= N, FTB_ERR_INVALID,
+              "ftb_linear_pair: bad arguments");
+  TcItem it;
+  it.w = (const __nv_bfloat16*)w_packed;
+  it.N = N;
+  it.bias = bias;
+  TcOut o;
+  o.out_f32 = out_f32;
+  o.ldo = ldo;
+  o.fp16 = fp16 != 0;
+  o.hl_in = true;
+  return conv_gemm_group((const __nv_bfloat16*)x_pair, 2 * Cin, B, S, Cin, &it, 1, o, (cudaStream_t)stream);
+}
+
+namespace ftb {
+FTB_DEFINE_TIMEOUT_READER(gemm_tc_timeouts)
+int rnn_tc_timeouts();   // rnn_tc.cu
+int rnn_mma_timeouts();  // rnn_mma.cu
+}  // namespace ftb
 extern "C" int ftb_tc_timeout_count(void) {
-  int v = -1;
-  if (cudaMemcpyFromSymbol(&v, g_tc_timeouts, sizeof(int)) != cudaSuccess) return -1;
-  return v;
+  const int a = ftb::gemm_tc_timeouts(), b = ftb::rnn_tc_timeouts(), c = ftb::rnn_mma_timeouts();
+  return (a < 0 || b < 0 || c < 0) ? -1 : a + b + c;  // -1: the context is gone (a kernel trapped)
 }

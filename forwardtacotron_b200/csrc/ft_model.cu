@@ -4,9 +4,11 @@
 //   (host: pitch_function / energy_function callbacks, ftb_length_plan, D2H of frame counts)
 //   stage B  ftb_ft_synthesize : embedding -> CBHG prenet -> conditioning -> LengthRegulator ->
 //                                biLSTM -> lin -> CBHG postnet -> post_proj
-// Activation dtype T is bf16 (gemm_mode 0, tcgen05 GEMMs), IEEE half (gemm_mode 2: same kernels and rate, 11-bit
-// significand -- the choice for trained-magnitude mels) or float (gemm_mode 1, all-fp32 validation mode).
-// The duration predictor is always fp32 (bit-exact durations).
+// Activation dtype T is IEEE half (gemm_mode 0, the default: tcgen05 GEMMs with fp32 accumulation, 11-bit significand --
+// what the absolute mel tolerance needs at trained-checkpoint magnitude), bf16 (gemm_mode 2: same kernels
+// and rate, 8-bit significand) or float (gemm_mode 1, all-fp32 validation mode).
+// The duration predictor is always fp32-grade (bit-exact durations).  The two output heads (lin,
+// post_proj) read their recurrent input as a 16-bit pair hi + lo and carry their weights as hi + lo as well.
 #include "model_common.cuh"
 
 namespace ftb {
@@ -45,7 +47,7 @@ struct ftb_ft_handle : ftb::ModelBase {
   ftb::Rnn lstm;
   ftb::Layer lin, post_proj;
   bool bf16_mode() const { return cfg.gemm_mode == 0 || cfg.gemm_mode == 2; }  // a 16-bit tensor-core mode
-  bool is_fp16() const { return cfg.gemm_mode == 2; }
+  bool is_fp16() const { return cfg.gemm_mode == 0; }
 
   // Stage A runs its three independent predictors on three side streams, forked from and joined back into the
   // caller's stream with events.  With FTB_OPT_OVERLAP_PRENET the prenet CBHG of stage B (it depends on the
@@ -234,8 +236,10 @@ static int run_series(ftb_ft_handle* h, SeriesW& P, const int64_t* tok, int B, i
 }
 
 // x: (B,S,ldx) with ldx >= CinP of the bank convs and zero padding columns; out: (B,S,2*ch)
+// out_ld / out_lo: row stride of `out` and offset of the 16-bit remainder part (rnn_bidir); 0 = plain (B,S,2*ch)
 template <typename T>
-static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int S, T* out, Arena& A, cudaStream_t s) {
+static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int S, T* out, Arena& A, cudaStream_t s,
+                    int out_ld = 0, int out_lo = 0) {
   const int64_t mark = A.mark();
   CbhgBufs<T> w = plan_cbhg<T>(A, W, B, S);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for CBHG");
@@ -258,7 +262,7 @@ static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int 
     std::swap(cur, nxt);
   }
   FTB_TRY(h->gemm<T>(W.rnn.in, cur, W.ch, B, S, act_out(w.xg, 6 * W.ch), nullptr, 0, 1.f, s));
-  FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, out_kind<T>(), s));
+  FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, out_kind<T>(), s, nullptr, out_ld, out_lo));
   h->launches += 1;
   A.reset(mark);
   return FTB_OK;
@@ -275,13 +279,16 @@ static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* c
   const int E = c.embed_dims, D = 2 * c.prenet_dims, RH = c.rnn_dims, NM = c.n_mels;
   const int melP = (int)align_up(NM, 64);
   const int64_t MT = (int64_t)B * Tn, ML = (int64_t)B * L;
+  // 16-bit modes: the recurrences that feed the output heads write h as the pair hi | lo (rnn_bidir lo_off)
+  constexpr int HP = std::is_same<T, float>::value ? 1 : 2;
+  const int dec_ld = 2 * RH * HP, post_ld = 2 * c.postnet_dims * HP;
   T* x0 = A.take<T>(MT * E);
   T* enc = A.take<T>(MT * D);
-  T* up = A.take<T>(ML * D);
-  float* xg = A.take<float>(ML * 8 * RH);
-  T* dec = A.take<T>(ML * 2 * RH);
+  float* xg = A.take<float>((MT + 1) * 8 * RH);  // phoneme-rate LSTM input pre-activations + one bias-only row
+  int32_t* fidx = A.take<int32_t>(ML);
+  T* dec = A.take<T>(ML * dec_ld);
   T* mel_cl = A.take<T>(ML * melP);
-  T* post = A.take<T>(ML * 2 * c.postnet_dims);
+  T* post = A.take<T>(ML * post_ld);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for synthesize");
 
   if (h->pre_valid && h->pre_tok == tok && h->pre_B == B && h->pre_T == Tn) {
@@ -293,23 +300,30 @@ static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* c
   h->pre_valid = false;
   FTB_TRY(cond_add<T>(enc, pitch, energy, h->pitch_w, h->pitch_b, h->energy_w, h->energy_b, c.pitch_strength,
                       c.energy_strength, B, Tn, D, s));
-  FTB_TRY(ftb_length_expand(enc, cum, up, B, Tn, L, D, (int)sizeof(T), s));
-  FTB_TRY(h->gemm<T>(h->lstm.in, up, D, B, L, act_out(xg, 8 * RH), nullptr, 0, 1.f, s));
+  // LengthRegulator + LSTM input projection (forward_tacotron.py:317-321, common_layers.py:12-19), commuted:
+  // Linear(repeat(x)) == repeat(Linear(x)) row for row (same K order -> bit-identical), so the projection runs on the
+  // B*T phoneme rows instead of the B*L expanded rows (6x fewer at the calibrated durations) and the recurrence
+  // gathers its input row through the frame -> phoneme index.  A padded frame is a zero row: its projection is the
+  // bias, kept as row MT.
+  FTB_TRY(h->gemm<T>(h->lstm.in, enc, D, B, Tn, act_out(xg, 8 * RH), nullptr, 0, 1.f, s));
+  FTB_CHECK_CUDA(cudaMemcpyAsync(xg + MT * 8 * RH, h->lstm.in.bias, sizeof(float) * 8 * RH, cudaMemcpyDeviceToDevice, s));
+  FTB_TRY(length_index(cum, fidx, B, Tn, L, (int)MT, s));
   if (mel_lens) {  // packed sequences (teacher-forced forward in eval mode)
     ProfScope prof(FAM_RNN_LSTM, 2.0 * 2 * B * L * 4.0 * RH * RH, 0.0, s);
-    FTB_TRY(lstm512_packed(xg, h->lstm.w_hh, dec, mel_lens, pad_value, B, L, out_kind<T>(), s));
+    FTB_TRY(lstm512_packed(xg, h->lstm.w_hh, dec, mel_lens, pad_value, B, L, out_kind<T>(), s, fidx, dec_ld,
+                           HP == 2 ? 2 * RH : 0));
   } else {
-    FTB_TRY(rnn_bidir(xg, h->lstm.w_hh, nullptr, dec, B, L, RH, 1, out_kind<T>(), s));
+    FTB_TRY(rnn_bidir(xg, h->lstm.w_hh, nullptr, dec, B, L, RH, 1, out_kind<T>(), s, fidx, dec_ld, HP == 2 ? 2 * RH : 0));
   }
   if (melP != NM) FTB_CHECK_CUDA(cudaMemsetAsync(mel_cl, 0, (size_t)ML * melP * sizeof(T), s));
   Out o = act_out(mel_cl, melP);
   o.t = mel;  // 'mel' (B,80,L) and the channel-last copy the postnet reads, from one epilogue
-  FTB_TRY(h->gemm<T>(h->lin, dec, 2 * RH, B, L, o, nullptr, 0, 1.f, s));
-  FTB_TRY(run_cbhg<T>(h, h->postnet, mel_cl, melP, B, L, post, A, s));
+  FTB_TRY(h->gemm<T>(h->lin, dec, dec_ld, B, L, o, nullptr, 0, 1.f, s));
+  FTB_TRY(run_cbhg<T>(h, h->postnet, mel_cl, melP, B, L, post, A, s, post_ld, HP == 2 ? 2 * c.postnet_dims : 0));
   Out op;
   op.t = mel_post;
-  FTB_TRY(h->gemm<T>(h->post_proj, post, 2 * c.postnet_dims, B, L, op, nullptr, 0, 1.f, s));
-  h->launches += 4;
+  FTB_TRY(h->gemm<T>(h->post_proj, post, post_ld, B, L, op, nullptr, 0, 1.f, s));
+  h->launches += 5;
   return FTB_OK;
 }
 
@@ -363,13 +377,14 @@ static int64_t synth_bytes(const ftb_ft_handle* h, int B, int Tn, int L) {
   Arena A(nullptr, 0);
   const int D = 2 * c.prenet_dims, RH = c.rnn_dims, melP = (int)align_up(c.n_mels, 64);
   const int64_t MT = (int64_t)B * Tn, ML = (int64_t)B * L;
+  constexpr int HP = std::is_same<T, float>::value ? 1 : 2;
   A.take<T>(MT * c.embed_dims);
   A.take<T>(MT * D);
-  A.take<T>(ML * D);
-  A.take<float>(ML * 8 * RH);
-  A.take<T>(ML * 2 * RH);
+  A.take<float>((MT + 1) * 8 * RH);
+  A.take<int32_t>(ML);
+  A.take<T>(ML * 2 * RH * HP);
   A.take<T>(ML * melP);
-  A.take<T>(ML * 2 * c.postnet_dims);
+  A.take<T>(ML * 2 * c.postnet_dims * HP);
   const int64_t base = A.mark();
   plan_cbhg<T>(A, h->prenet, B, Tn);
   const int64_t pre = A.mark();
@@ -428,10 +443,11 @@ extern "C" int ftb_ft_create(const ftb_ft_config* cfg, const ftb_tensor* tensors
     FTB_TRY(h->get("energy_proj.bias", {D}, &h->energy_b));
     const bool w16 = h->bf16_mode(), w32 = !w16;
     FTB_TRY(h->make_rnn(h->lstm, "lstm", D, c.rnn_dims, true, w32, w16));
-    FTB_TRY(h->make_conv(h->lin, "lin.weight", c.n_mels, 2 * c.rnn_dims, 1, 0, false, "", "lin.bias", w32, w16));
+    // the heads multiply by trained-magnitude weights: two-part 16-bit operands (hi + lo) on both sides
+    FTB_TRY(h->make_conv(h->lin, "lin.weight", c.n_mels, 2 * c.rnn_dims, 1, 0, false, "", "lin.bias", w32, w16, false, true));
     FTB_TRY(build_cbhg(h, h->postnet, "postnet", c.postnet_k, c.n_mels, c.postnet_dims, c.postnet_dims, c.n_mels,
                        c.postnet_num_highways));
-    FTB_TRY(h->make_conv(h->post_proj, "post_proj.weight", c.n_mels, 2 * c.postnet_dims, 1, 0, false, "", "", w32, w16));
+    FTB_TRY(h->make_conv(h->post_proj, "post_proj.weight", c.n_mels, 2 * c.postnet_dims, 1, 0, false, "", "", w32, w16, false, true));
     FTB_CHECK_CUDA(cudaStreamSynchronize(h->prep));
     for (int i = 0; i < 4; ++i) {
       FTB_CHECK_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));

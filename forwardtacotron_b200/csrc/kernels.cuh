@@ -29,6 +29,8 @@ struct TcOut {
   bool split_in = false;  // x is (B,S,3*Cin): bf16 parts hi | mid | lo of an fp32 tensor, weights packed by pack mode 3:
                           // 6 part products with fp32 accumulation = fp32-grade result on the tensor cores
   int split_out = 0;      // > 0: write the 16-bit output as 3 parts, split_out channels apart (ldo >= 3 * split_out)
+  bool hl_in = false;     // x is (B,S,2*Cin): 16-bit parts hi | lo (rnn_bidir lo_off), weights packed by pack mode 4 / 5
+                          // as [hi | hi | lo] along K: hi.hi + lo.hi + hi.lo = a 22-bit (half) / 16-bit (bf16) operand pair
   bool highway = false;  // N = 2C interleaved [32 x1 | 32 x2] groups -> y (C) = sigmoid(x2) relu(x1) + (1 - sigmoid(x2)) res_bf16
 };
 int tc_tile_n(int N);
@@ -36,12 +38,18 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
                     const TcOut& o, cudaStream_t s);
 
 // rnn_small.cu / rnn_cluster.cu
+// xrow (optional, H=512 LSTM): (B,S) int32 row of xg feeding frame (b,t) (default b*S + t).  ldo: out row stride
+// (default 2H); lo_off > 0: the 16-bit rounding remainder h - hi is written lo_off elements after hi.
 int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
-              int out_bf16, cudaStream_t s);
+              int out_bf16, cudaStream_t s, const int32_t* xrow = nullptr, int ldo = 0, int lo_off = 0);
 
 // rnn_tc.cu: decoder LSTM (H=512) over packed sequences -- state zero and output pad_value wherever t >= lens[b]
 int lstm512_packed(const float* xg, const float* w_hh, void* out, const int* lens, float pad_value, int B, int S,
-                   int out_bf16, cudaStream_t s);
+                   int out_bf16, cudaStream_t s, const int32_t* xrow = nullptr, int ldo = 0, int lo_off = 0);
+
+// length_regulator.cu: idx (B,L) int32 <- row of the phoneme-rate tensor that frame (b, j) repeats: b*T + t with
+// cum[b,t-1] <= j < cum[b,t], or pad_row for the zero-padded tail j >= cum[b,T-1]
+int length_index(const int32_t* cum, int32_t* idx, int B, int T, int L, int pad_row, cudaStream_t s);
 
 // attention.cu : softmax(q k^T / sqrt(hd) + key_pad_mask) v on packed qkv (B,S,3E)
 template <typename T>

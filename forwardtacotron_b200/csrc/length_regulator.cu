@@ -7,7 +7,7 @@
 //            and stored reps times with 16-byte vector stores (coalesced: a row is
 //            C*elem contiguous bytes); extra warps zero-fill [total_b, L).
 //            HBM traffic = B*T*C*e read + B*L*C*e written = the algorithmic minimum.
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace ftb {
 
@@ -99,6 +99,32 @@ __global__ void __launch_bounds__(kExpandWarps * 32)
   }
 }
 
+// Frame -> source-row map of the expansion (the LengthRegulator as an index instead of a copy): idx[b, j] = b*T + t for
+// cum[b,t-1] <= j < cum[b,t] (upper-bound search in the inclusive prefix sum), pad_row for the zero tail.  A consumer
+// that is linear per row (the decoder LSTM's input projection) runs at phoneme rate and is gathered through this map.
+__global__ void __launch_bounds__(256) length_index_kernel(const int32_t* __restrict__ cum, int32_t* __restrict__ idx, int T,
+                                                           int L, int pad_row) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= L) return;
+  const int32_t* c = cum + (int64_t)b * T;
+  int lo = 0, hi = T;  // first t with c[t] > j
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(c + mid) > j) hi = mid;
+    else lo = mid + 1;
+  }
+  idx[(int64_t)b * L + j] = lo < T ? b * T + lo : pad_row;
+}
+
+int length_index(const int32_t* cum, int32_t* idx, int B, int T, int L, int pad_row, cudaStream_t s) {
+  FTB_REQUIRE(cum && idx && B > 0 && T > 0 && L > 0 && B <= 65535, FTB_ERR_INVALID, "length_index: bad arguments");
+  FTB_REQUIRE((int64_t)B * T < (1ll << 31) - 1, FTB_ERR_INVALID, "length_index: B*T overflows the int32 row index");
+  ProfScope prof(FAM_LENGTH, 0.0, (double)B * L * 4 + (double)B * T * 4, s);
+  length_index_kernel<<<dim3(cdiv(L, 256), B), 256, 0, s>>>(cum, idx, T, L, pad_row);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+
 // ---- duration fallback ----------------------------------------------------
 __global__ void dur_trunc_sum_kernel(const float* __restrict__ dur, int64_t n, long long* __restrict__ acc) {
   long long s = 0;
@@ -150,6 +176,10 @@ extern "C" int ftb_length_expand(const void* x, const int32_t* cum, void* out, i
     length_expand_kernel<8><<<blocks, kExpandWarps * 32, 0, s>>>(xs, cum, os, B, T, L, chunks);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
+}
+
+extern "C" int ftb_length_index(const int32_t* cum, int32_t* idx, int B, int T, int L, int pad_row, void* stream) {
+  return length_index(cum, idx, B, T, L, pad_row, (cudaStream_t)stream);
 }
 
 extern "C" int ftb_duration_fallback(float* dur, int64_t n, void* scratch8, void* stream) {

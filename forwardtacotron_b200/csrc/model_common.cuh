@@ -14,6 +14,7 @@ using f16 = __half;  // FastPitch's 16-bit activation / weight type (DESIGN.md 2
 // padded channels) so the same activation buffers serve the tcgen05 and the fp32 kernel.
 struct Layer {
   int N = 0, Cin = 0, CinP = 0, k = 1, pad = 0, relu = 0;
+  bool hl = false;  // w16 is packed [hi | hi | lo] (pack mode 4 / 5): the input comes as the 16-bit pair hi | lo, (B,S,2*CinP)
   float* w32 = nullptr;
   bf16* w16 = nullptr;
   bf16* w16s = nullptr;  // split-precision copy (ftb_pack_conv_weight mode 3): (N, 6, k, CinP) bf16
@@ -83,8 +84,9 @@ struct ModelBase {
 
   // conv weight (N,Cin,k) [+ BatchNorm `bn` prefix] [+ bias] -> Layer
   int make_conv(Layer& L, const std::string& wname, int N, int Cin, int k, int pad, bool relu, const std::string& bn,
-                const std::string& bias, bool want32, bool want16, bool want_split = false) {
+                const std::string& bias, bool want32, bool want16, bool want_split = false, bool want_hl = false) {
     L.N = N;
+    L.hl = want_hl && want16;
     L.Cin = Cin;
     L.CinP = (int)align_up(Cin, 64);
     L.k = k;
@@ -102,9 +104,9 @@ struct ModelBase {
       FTB_TRY(ftb_pack_conv_weight(w, L.w32, N, Cin, k, N, L.CinP, 0, prep));
     }
     if (want16) {
-      L.w16 = dalloc<bf16>(n);
+      L.w16 = dalloc<bf16>(L.hl ? 3 * n : n);
       FTB_REQUIRE(L.w16, FTB_ERR_CUDA, "out of device memory packing %s", wname.c_str());
-      FTB_TRY(ftb_pack_conv_weight(w, L.w16, N, Cin, k, N, L.CinP, pack16, prep));
+      FTB_TRY(ftb_pack_conv_weight(w, L.w16, N, Cin, k, N, L.CinP, L.hl ? pack16 + 3 : pack16, prep));
     }
     if (want_split) {
       L.w16s = dalloc<bf16>(6 * n);
@@ -223,6 +225,7 @@ struct ModelBase {
     to.ldr = ldr;
     to.out_scale = out_scale;
     to.fp16 = std::is_same<T, f16>::value;
+    to.hl_in = L.hl;
     return conv_gemm_group((const bf16*)x, lda, B, S, L.CinP, &it, 1, to, s);
   }
 

@@ -61,19 +61,7 @@ __device__ __forceinline__ void st_async_16(uint32_t remote_addr, const uint4& v
                ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
                : "memory");
 }
-__device__ __forceinline__ void rnn_mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (++spins > (1u << 24)) break;  // bounded: a protocol bug must not hang the GPU
-  }
-}
+__device__ __forceinline__ void rnn_mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_or_trap(bar, parity); }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const float* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -112,7 +100,8 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
     rnn_cluster_kernel(const float* __restrict__ xg,    // (B,S,2,G*H)
                        const float* __restrict__ w_hh,  // (2,G*H,H)
                        const float* __restrict__ b_hn,  // (2,H) GRU only
-                       void* __restrict__ out, int B, int S, int out_bf16) {
+                       void* __restrict__ out, int B, int S, int out_bf16,
+                       int ldo, int lo_off) {  // out row stride; > 0: 16-bit remainder h - hi at this offset (rnn_tc.cu)
   using C = RnnCfg<G, H, CL, BC>;
   constexpr int HC = C::HC, NT = C::NT, KT = C::KT, HP = C::HP, PPT = C::PPT, PRE_LD = C::PRE_LD, NTL = C::NTL,
                 PAIRS = C::PAIRS;
@@ -170,7 +159,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
     hprev[p] = 0.f;
     const int hu = rank * HC + u;
     bhn[p] = (G == 3 && pvalid[p]) ? b_hn[dir * H + hu] : 0.f;
-    optr[p] = ((int64_t)(b0 + n) * S) * (2 * H) + dir * H + hu;
+    optr[p] = ((int64_t)(b0 + n) * S) * ldo + dir * H + hu;
   }
   __syncthreads();  // xs zero-fill done before the first cp.async lands on it
   // input pre-activations of `step` -> xs[step & 1], layout [g][n][u] (same index as the pair id),
@@ -303,15 +292,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
         hprev[p] = hn;
         reinterpret_cast<unsigned short*>(hstage)[n * HC + u] =
             F16 ? __half_as_ushort(__float2half_rn(hn)) : __bfloat16_as_ushort(__float2bfloat16_rn(hn));
-        if (pvalid[p]) {
-          const int64_t o = optr[p] + (int64_t)t * 2 * H;
-          if (out_bf16 == 2)
-            reinterpret_cast<__half*>(out)[o] = __float2half_rn(hn);
-          else if (out_bf16)
-            reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(hn);
-          else
-            reinterpret_cast<float*>(out)[o] = hn;
-        }
+        if (pvalid[p]) store_h(out, optr[p] + (int64_t)t * ldo, lo_off, out_bf16, hn);
       }
     }
     __syncthreads();
@@ -335,7 +316,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
 
 template <int G, int H, int CL, int BC, bool F16 = false>
 static int launch_rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S,
-                              int out_bf16, cudaStream_t s, int* max_clusters) {
+                              int out_bf16, cudaStream_t s, int* max_clusters, int ldo = 0, int lo_off = 0) {
   using C = RnnCfg<G, H, CL, BC>;
   auto kern = rnn_cluster_kernel<G, H, CL, BC, F16>;
   static bool configured = false;
@@ -363,7 +344,8 @@ static int launch_rnn_cluster(const float* xg, const float* w_hh, const float* b
     return FTB_OK;
   }
   FTB_REQUIRE(max_active > 0, FTB_ERR_UNSUPPORTED, "a cluster of %d CTAs cannot be scheduled on this device", CL);
-  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16));
+  if (ldo <= 0) ldo = 2 * H;
+  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16, ldo, lo_off));
   count_launch();
   return FTB_OK;
 }
@@ -376,7 +358,7 @@ static int launch_rnn_cluster(const float* xg, const float* w_hh, const float* b
 std::atomic<int> g_gru_min_chunk{getenv("FTB_GRU_MIN_CHUNK") ? atoi(getenv("FTB_GRU_MIN_CHUNK")) : 8};
 template <int G, int H, int CL>
 static int dispatch_bc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
-                       cudaStream_t s) {
+                       cudaStream_t s, int ldo, int lo_off) {
   int m8 = 0, m16 = 0, m24 = 0;
   FTB_TRY((launch_rnn_cluster<G, H, CL, 8>(nullptr, nullptr, nullptr, nullptr, B, S, 0, s, &m8)));
   FTB_TRY((launch_rnn_cluster<G, H, CL, 16>(nullptr, nullptr, nullptr, nullptr, B, S, 0, s, &m16)));
@@ -387,8 +369,8 @@ static int dispatch_bc(const float* xg, const float* w_hh, const float* b_hn, vo
   // IEEE-half activations (output type 2) take IEEE-half recurrent operands as well: same kernel, f16 mma
 #define FTB_RNN_BC(N)                                                                                         \
   case N:                                                                                                     \
-    return out_bf16 == 2 ? launch_rnn_cluster<G, H, CL, N, true>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr) \
-                         : launch_rnn_cluster<G, H, CL, N, false>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr);
+    return out_bf16 == 2 ? launch_rnn_cluster<G, H, CL, N, true>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr, ldo, lo_off) \
+                         : launch_rnn_cluster<G, H, CL, N, false>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr, ldo, lo_off);
   switch (bc) {
     FTB_RNN_BC(8)
     FTB_RNN_BC(16)
@@ -402,14 +384,16 @@ static int dispatch_bc(const float* xg, const float* w_hh, const float* b_hn, vo
 // GRU H=256 (the two CBHG RNNs): 8 utterances per cluster make the register-resident mma.sync step cheaper than
 // streaming the weight slice through tcgen05 every step (measured: 1.0 vs 1.6 us/step; DESIGN.md "recurrences").
 int rnn_gru256_mma(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
-                   cudaStream_t s) {
+                   cudaStream_t s, int ldo, int lo_off) {
   FTB_REQUIRE(b_hn, FTB_ERR_INVALID, "rnn_cluster: GRU needs b_hn");
   // Cluster of 4 (each CTA: 192 gate rows = 12 warps x 64 registers of A fragments) rather than 8: the hand-off to 3
   // instead of 7 peers shortens the step more than the doubled mma.sync work per SM lengthens it (cfg2: 1.32 vs
   // 1.41 ms for both CBHG GRUs) and the recurrence holds 64 instead of 128 SMs (FTB_GRU_CL=8 selects the old shape).
   static const int cl = getenv("FTB_GRU_CL") ? atoi(getenv("FTB_GRU_CL")) : 4;
-  if (cl == 8) return dispatch_bc<3, 256, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
-  return dispatch_bc<3, 256, 4>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
+  if (cl == 8) return dispatch_bc<3, 256, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, s, ldo, lo_off);
+  return dispatch_bc<3, 256, 4>(xg, w_hh, b_hn, out, B, S, out_bf16, s, ldo, lo_off);
 }
+
+FTB_DEFINE_TIMEOUT_READER(rnn_mma_timeouts)
 
 }  // namespace ftb

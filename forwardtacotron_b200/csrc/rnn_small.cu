@@ -6,7 +6,7 @@
 // the row in shared memory as well the step was bound by 2H shared loads per thread: 1.7 us at H = 128).  No
 // inter-CTA traffic, no grid synchronisation: a step is one mat-vec, two block barriers and the gate maths.
 // Latency-bound by design (SURVEY 8d "recurrences").
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace ftb {
 
@@ -108,17 +108,23 @@ static int launch_gru_small(const float* xg, const float* w_hh, const float* b_h
 }
 
 int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
-                int out_bf16, cudaStream_t s);  // rnn_cluster.cu
+                int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off);  // rnn_tc.cu
 
 int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
-              int out_bf16, cudaStream_t s) {
+              int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off) {
   FTB_REQUIRE(xg && w_hh && out && B > 0 && S > 0, FTB_ERR_INVALID, "rnn_bidir: bad arguments");
+  FTB_REQUIRE(ldo == 0 || ldo >= 2 * H + (lo_off ? 2 * H : 0), FTB_ERR_INVALID, "rnn_bidir: output row stride %d too small", ldo);
+  FTB_REQUIRE(lo_off == 0 || lo_off >= 2 * H, FTB_ERR_INVALID, "rnn_bidir: the remainder part must not overlap the 2H main part");
   const int G = is_lstm ? 4 : 3;
   ProfScope prof(is_lstm ? FAM_RNN_LSTM : (H >= 256 ? FAM_RNN_GRU : FAM_RNN_SMALL), 2.0 * 2 * B * S * (double)G * H * H,
-                 (double)B * S * 2 * G * H * 4 + (double)B * S * 2 * H * (out_bf16 ? 2 : 4), s);
-  if (!is_lstm && H == 64) return launch_gru_small<64>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
-  if (!is_lstm && H == 128) return launch_gru_small<128>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
-  return rnn_cluster(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, s);
+                 (double)B * S * 2 * G * H * 4 + (double)B * S * 2 * H * (out_bf16 ? (lo_off ? 4 : 2) : 4), s);
+  if (!is_lstm && (H == 64 || H == 128)) {
+    FTB_REQUIRE(!xrow && !lo_off && (ldo == 0 || ldo == 2 * H), FTB_ERR_UNSUPPORTED,
+                "rnn_bidir: the small-GRU kernel writes plain (B,S,2H) rows");
+    return H == 64 ? launch_gru_small<64>(xg, w_hh, b_hn, out, B, S, out_bf16, s)
+                   : launch_gru_small<128>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
+  }
+  return rnn_cluster(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, s, xrow, ldo, lo_off);
 }
 
 }  // namespace ftb
@@ -126,4 +132,9 @@ int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, 
 extern "C" int ftb_rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H,
                              int is_lstm, int out_bf16, void* stream) {
   return ftb::rnn_bidir(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, (cudaStream_t)stream);
+}
+
+extern "C" int ftb_rnn_bidir_rows(const float* xg, const int32_t* xrow, const float* w_hh, const float* b_hn, void* out,
+                                  int B, int S, int H, int is_lstm, int out_kind, int ldo, int lo_off, void* stream) {
+  return ftb::rnn_bidir(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_kind, (cudaStream_t)stream, xrow, ldo, lo_off);
 }

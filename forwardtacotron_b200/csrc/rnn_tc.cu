@@ -27,26 +27,13 @@ namespace cg = cooperative_groups;
 namespace ftb {
 
 namespace rt {
-constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
 __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t cta) {
   uint32_t r;
   asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
   return r;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (++spins > SPIN_LIMIT) break;  // bounded: a protocol bug must not hang the GPU
-  }
-}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_or_trap(bar, parity); }
 // 16 x H bf16 B operand, K-major, no swizzle: 16-byte cell (n, kc) = 8 consecutive hidden units kc*8.. of
 // utterance n, stored at cell index (n/8)*(H/8)*8 + kc*8 + n%8.  Core matrix (8 utterances x 8 units) is
 // 128 contiguous bytes; LBO (next 8 units) = 128 B; SBO (next 8 utterances) = (H/8)*128 B.
@@ -159,7 +146,9 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
     rnn_tc_kernel(const float* __restrict__ xg,    // (B,S,2,G*H)
                   const float* __restrict__ w_hh,  // (2,G*H,H)
                   const float* __restrict__ b_hn,  // (2,H) GRU only
-                  void* __restrict__ out, int B, int S, int out_bf16, int bc) {
+                  void* __restrict__ out, int B, int S, int out_bf16, int bc,
+                  const int32_t* __restrict__ xrow,  // optional (B,S): row of xg that feeds (b, t) -- see rnn_bidir_rows
+                  int ldo, int lo_off) {             // out row stride; > 0: second 16-bit part h - hi at this offset
   using C = RtCfg<G, H, CL, NCOLS, CW, UC>;
   using namespace rt;
   constexpr int THREADS = C::THREADS, WARPS = C::WARPS, PRE_LD = C::PRE_LD, PPT = C::PPT, KSPLIT = C::KSPLIT;
@@ -235,10 +224,18 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
   long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) ? g_rnn_dbg : nullptr;
   float* pre = pre_all + warp * 32 * PRE_LD;
   float cst[PPT], hprev[PPT], xcur[PPT][G];
-  const float* xp[PPT];  // input pre-activations of the NEXT step to fetch
-  int64_t op[PPT];       // output element of the CURRENT step
+  // Input pre-activations.  Row r of xg is 2*G*H floats.  Without `xrow` frame (b, t) reads row b*S + t.  With it the
+  // row comes from the (B,S) index: the LengthRegulator's frame -> phoneme map, so the input projection runs once per
+  // PHONEME (Linear(repeat(x)) == repeat(Linear(x)), models/common_layers.py:12-19 + forward_tacotron.py:317-321) and
+  // the ~6 frames of a phoneme re-read the same row (L1 / L2 hits instead of a frame-rate fp32 tensor in HBM).
+  // The row of step s + 1 is fetched during step s, its index one step earlier still.
+  const float* xbase = xg + (int64_t)dir * (G * H) + hu;
+  const int32_t* ip[PPT];  // index of the step after next
+  int64_t rnext[PPT];      // xg row of the NEXT step
+  int64_t op[PPT];         // output element of the CURRENT step
   bool ok[PPT];
-  const int64_t xstep = (dir ? -1 : 1) * (int64_t)(2 * G * H), ostep = (dir ? -1 : 1) * (int64_t)(2 * H);
+  const int tstep = dir ? -1 : 1;
+  const int64_t ostep = (int64_t)tstep * ldo;
   const float bhn = (G == 3) ? b_hn[dir * H + hu] : 0.f;
   const int t_first = dir ? S - 1 : 0;
   const int ng8 = (nvalid + 7) >> 3;  // 8-utterance groups that carry data
@@ -249,11 +246,13 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
     cst[e] = 0.f;
     hprev[e] = 0.f;
     const int64_t b = b0 + (ok[e] ? n : 0);
-    xp[e] = xg + ((b * S + t_first) * 2 + dir) * (int64_t)(G * H) + hu;
-    op[e] = (b * S + t_first) * (2 * H) + dir * H + hu;
+    const int64_t f0 = b * S + t_first;
+    op[e] = f0 * ldo + dir * H + hu;
+    const int64_t r0 = xrow ? (int64_t)__ldg(xrow + f0) : f0;
 #pragma unroll
-    for (int g = 0; g < G; ++g) xcur[e][g] = ok[e] ? __ldg(xp[e] + g * H) : 0.f;
-    xp[e] += xstep;
+    for (int g = 0; g < G; ++g) xcur[e][g] = ok[e] ? __ldg(xbase + r0 * (2 * G * H) + g * H) : 0.f;
+    rnext[e] = (S > 1) ? (xrow ? (int64_t)__ldg(xrow + f0 + tstep) : f0 + tstep) : r0;
+    ip[e] = xrow + f0 + 2 * tstep;
   }
   // own slice cell of utterance n: rank*SL + (n/8)*512 + q*128 + (n%8)*16 + (unit%8)*2
   const int n0 = cgp * CW + sub * PPT;
@@ -277,9 +276,15 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
     if (s + 1 < S) {
 #pragma unroll
       for (int e = 0; e < PPT; ++e) {
+        const float* xr = xbase + rnext[e] * (2 * G * H);
 #pragma unroll
-        for (int g = 0; g < G; ++g) xnext[e][g] = ok[e] ? __ldg(xp[e] + g * H) : 0.f;
-        xp[e] += xstep;
+        for (int g = 0; g < G; ++g) xnext[e][g] = ok[e] ? __ldg(xr + g * H) : 0.f;
+        if (xrow) {
+          if (s + 2 < S) rnext[e] = (int64_t)__ldg(ip[e]);
+          ip[e] += tstep;
+        } else {
+          rnext[e] += tstep;
+        }
       }
     }
     // all MMAs of this step have retired (every thread polls: parking 15 warps on a hardware barrier behind one
@@ -341,14 +346,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
         hn[e] = (1.f - gz) * gn + gz * hprev[e];
       }
       hprev[e] = hn[e];
-      if (ok[e]) {
-        if (out_bf16 == 2)
-          reinterpret_cast<__half*>(out)[op[e]] = __float2half_rn(hn[e]);
-        else if (out_bf16)
-          reinterpret_cast<__nv_bfloat16*>(out)[op[e]] = __float2bfloat16_rn(hn[e]);
-        else
-          reinterpret_cast<float*>(out)[op[e]] = hn[e];
-      }
+      if (ok[e]) store_h(out, op[e], lo_off, out_bf16, hn[e]);
       op[e] += ostep;
 #pragma unroll
       for (int g = 0; g < G; ++g) xcur[e][g] = xnext[e][g];
@@ -417,7 +415,8 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
 
 template <int G, int H, int CL, int NCOLS, int CW, int UC>
 static int launch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
-                         int bc, cudaStream_t s, int* max_clusters) {
+                         int bc, cudaStream_t s, int* max_clusters, const int32_t* xrow = nullptr, int ldo = 0,
+                         int lo_off = 0) {
   using C = RtCfg<G, H, CL, NCOLS, CW, UC>;
   auto kern = rnn_tc_kernel<G, H, CL, NCOLS, CW, UC>;
   static bool configured = false;
@@ -445,7 +444,8 @@ static int launch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, 
     return FTB_OK;
   }
   FTB_REQUIRE(max_active > 0, FTB_ERR_UNSUPPORTED, "a cluster of %d CTAs cannot be scheduled on this device", CL);
-  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16, bc));
+  if (ldo <= 0) ldo = 2 * H;
+  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16, bc, xrow, ldo, lo_off));
   count_launch();
   return FTB_OK;
 }
@@ -487,7 +487,8 @@ static_assert(WCOLS + 2 * IW * NS <= TMEM_COLS && SMEM <= 227 * 1024, "TMEM / sh
 __global__ void __launch_bounds__(pp::THREADS, 1)
     lstm_pp_kernel(const float* __restrict__ xg,    // (B,S,2,4H)
                    const float* __restrict__ w_hh,  // (2,4H,H)
-                   void* __restrict__ out, const int* __restrict__ lens, float pad_value, int B, int S, int out_bf16) {
+                   void* __restrict__ out, const int* __restrict__ lens, float pad_value, int B, int S, int out_bf16,
+                   const int32_t* __restrict__ xrow, int ldo, int lo_off) {  // as in rnn_tc_kernel
   using namespace pp;
   using namespace rt;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -612,12 +613,15 @@ __global__ void __launch_bounds__(pp::THREADS, 1)
   } else {  // ================= gate warps =================
     float* pre = pre_all + warp * 32 * PRE_LD;
     float cst[2][PPT], xcur[2][PPT][G];
-    const float* xp[2][PPT];
+    const float* xbase = xg + (int64_t)dir * (G * H) + hu;
+    const int32_t* ip[2][PPT];
+    int64_t rnext[2][PPT];
     int64_t op[2][PPT];
     bool ok[2][PPT];
     int len[2][PPT];
     uint32_t cell[2];
-    const int64_t xstep = (dir ? -1 : 1) * (int64_t)(2 * G * H), ostep = (dir ? -1 : 1) * (int64_t)(2 * H);
+    const int tstep = dir ? -1 : 1;
+    const int64_t ostep = (int64_t)tstep * ldo;
     const int t_first = dir ? S - 1 : 0;
     const int n0 = cgp * CW + sub * PPT;  // first utterance (of the sub-chunk) of this thread
 #pragma unroll
@@ -629,11 +633,13 @@ __global__ void __launch_bounds__(pp::THREADS, 1)
         cst[c][e] = 0.f;
         const int64_t b = b0 + (ok[c][e] ? (c ? n_c0 : 0) + n : 0);
         len[c][e] = lens ? __ldg(lens + b) : S;
-        xp[c][e] = xg + ((b * S + t_first) * 2 + dir) * (int64_t)(G * H) + hu;
-        op[c][e] = (b * S + t_first) * (2 * H) + dir * H + hu;
+        const int64_t f0 = b * S + t_first;
+        op[c][e] = f0 * ldo + dir * H + hu;
+        const int64_t r0 = xrow ? (int64_t)__ldg(xrow + f0) : f0;
 #pragma unroll
-        for (int g = 0; g < G; ++g) xcur[c][e][g] = ok[c][e] ? __ldg(xp[c][e] + g * H) : 0.f;
-        xp[c][e] += xstep;
+        for (int g = 0; g < G; ++g) xcur[c][e][g] = ok[c][e] ? __ldg(xbase + r0 * (2 * G * H) + g * H) : 0.f;
+        rnext[c][e] = (S > 1) ? (xrow ? (int64_t)__ldg(xrow + f0 + tstep) : f0 + tstep) : r0;
+        ip[c][e] = xrow + f0 + 2 * tstep;
       }
       cell[c] = rank * SL + (uint32_t)(n0 >> 3) * 512u + (uint32_t)q * 128u + (uint32_t)(n0 & 7) * 16u + (lane >> 2) * 2u;
     }
@@ -647,9 +653,15 @@ __global__ void __launch_bounds__(pp::THREADS, 1)
         if (s + 1 < S) {
 #pragma unroll
           for (int e = 0; e < PPT; ++e) {
+            const float* xr = xbase + rnext[c][e] * (2 * G * H);
 #pragma unroll
-            for (int g = 0; g < G; ++g) xnext[e][g] = ok[c][e] ? __ldg(xp[c][e] + g * H) : 0.f;
-            xp[c][e] += xstep;
+            for (int g = 0; g < G; ++g) xnext[e][g] = ok[c][e] ? __ldg(xr + g * H) : 0.f;
+            if (xrow) {
+              if (s + 2 < S) rnext[c][e] = (int64_t)__ldg(ip[c][e]);
+              ip[c][e] += tstep;
+            } else {
+              rnext[c][e] += tstep;
+            }
           }
         }
         if (s > 0) mbar_wait(dfull0 + 8 * c, (s - 1) & 1);  // the MMAs of this step of this sub-chunk have retired
@@ -692,15 +704,7 @@ __global__ void __launch_bounds__(pp::THREADS, 1)
           const bool live = t < len[c][e];
           cst[c][e] = live ? gf * cst[c][e] + gi * gg : 0.f;
           hn[e] = live ? go * tanh_mufu(cst[c][e]) : 0.f;
-          if (ok[c][e]) {
-            const float ov = live ? hn[e] : pad_value;
-            if (out_bf16 == 2)
-              reinterpret_cast<__half*>(out)[op[c][e]] = __float2half_rn(ov);
-            else if (out_bf16)
-              reinterpret_cast<__nv_bfloat16*>(out)[op[c][e]] = __float2bfloat16_rn(ov);
-            else
-              reinterpret_cast<float*>(out)[op[c][e]] = ov;
-          }
+          if (ok[c][e]) store_h(out, op[c][e], lo_off, out_bf16, live ? hn[e] : pad_value);
           op[c][e] += ostep;
 #pragma unroll
           for (int g = 0; g < G; ++g) xcur[c][e][g] = xnext[e][g];
@@ -743,7 +747,7 @@ __global__ void __launch_bounds__(pp::THREADS, 1)
 #undef PP_STAMP
 
 static int launch_lstm_pp(const float* xg, const float* w_hh, void* out, const int* lens, float pad_value, int B, int S,
-                          int out_bf16, cudaStream_t s) {
+                          int out_bf16, cudaStream_t s, const int32_t* xrow = nullptr, int ldo = 0, int lo_off = 0) {
   static bool configured = false;
   static int max_active = 0;
   cudaLaunchConfig_t cfg = {};
@@ -765,7 +769,8 @@ static int launch_lstm_pp(const float* xg, const float* w_hh, void* out, const i
     configured = true;
   }
   FTB_REQUIRE(max_active > 0, FTB_ERR_UNSUPPORTED, "a cluster of %d CTAs cannot be scheduled on this device", pp::CL);
-  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pp_kernel, xg, w_hh, out, lens, pad_value, B, S, out_bf16));
+  if (ldo <= 0) ldo = 2 * pp::H;
+  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pp_kernel, xg, w_hh, out, lens, pad_value, B, S, out_bf16, xrow, ldo, lo_off));
   count_launch();
   return FTB_OK;
 }
@@ -780,43 +785,47 @@ static std::atomic<int> g_lstm_min_chunk{getenv("FTB_LSTM_MIN_CHUNK") ? atoi(get
 
 template <int G, int H, int CL>
 static int dispatch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
-                           cudaStream_t s) {
+                           cudaStream_t s, const int32_t* xrow, int ldo, int lo_off) {
   int m8 = 0, m16 = 0, m32 = 0;
   FTB_TRY((launch_rnn_tc<G, H, CL, 16, 4, 8>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 8, s, &m8)));
   FTB_TRY((launch_rnn_tc<G, H, CL, 16, 8, 16>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 16, s, &m16)));
   FTB_TRY((launch_rnn_tc<G, H, CL, 32, 8, 32>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 32, s, &m32)));
   // 8 utterances: only the first column group of a 16-wide MMA carries data, 1 pair per gate thread
-  if (2 * cdiv(B, 8) <= m8) return launch_rnn_tc<G, H, CL, 16, 4, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, 8, s, nullptr);
-  if (2 * cdiv(B, 16) <= m16) return launch_rnn_tc<G, H, CL, 16, 8, 16>(xg, w_hh, b_hn, out, B, S, out_bf16, 16, s, nullptr);
+  if (2 * cdiv(B, 8) <= m8) return launch_rnn_tc<G, H, CL, 16, 4, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, 8, s, nullptr, xrow, ldo, lo_off);
+  if (2 * cdiv(B, 16) <= m16) return launch_rnn_tc<G, H, CL, 16, 8, 16>(xg, w_hh, b_hn, out, B, S, out_bf16, 16, s, nullptr, xrow, ldo, lo_off);
   const int min_chunk = g_lstm_min_chunk.load(std::memory_order_relaxed);
-  if (min_chunk <= 24 && 2 * cdiv(B, 24) <= m32) return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 24, s, nullptr);
-  return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 32, s, nullptr);
+  if (min_chunk <= 24 && 2 * cdiv(B, 24) <= m32) return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 24, s, nullptr, xrow, ldo, lo_off);
+  return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 32, s, nullptr, xrow, ldo, lo_off);
 }
 
 // Decoder LSTM over packed sequences (pack_padded_sequence semantics): rows stop at lens[b]; beyond it the state is
 // zero and the output is pad_value.  xg (B,S,2,4H) f32; out (B,S,2H).
 int lstm512_packed(const float* xg, const float* w_hh, void* out, const int* lens, float pad_value, int B, int S,
-                   int out_bf16, cudaStream_t s) {
-  return launch_lstm_pp(xg, w_hh, out, lens, pad_value, B, S, out_bf16, s);
+                   int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off) {
+  return launch_lstm_pp(xg, w_hh, out, lens, pad_value, B, S, out_bf16, s, xrow, ldo, lo_off);
 }
 
 int rnn_gru256_mma(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
-                   cudaStream_t s);  // rnn_mma.cu
+                   cudaStream_t s, int ldo, int lo_off);  // rnn_mma.cu
 
 int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
-                int out_bf16, cudaStream_t s) {
+                int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off) {
+  FTB_REQUIRE(!lo_off || out_bf16, FTB_ERR_INVALID, "rnn_bidir: the hi/lo output pair exists for 16-bit outputs only");
   if (is_lstm && H == 512) {
     // FTB_LSTM_PP=1: the two-sub-chunk kernel (64 utterances per cluster, W_hh in TMEM).  It holds half the SMs of
     // the default but its step is 1.8x longer (the tensor pipe serialises the dependent accumulations of a chain:
     // measured ~120 clk per MMA with 4 accumulators per sub-chunk), so it only serves the packed-sequence path.
     static const int use_pp = getenv("FTB_LSTM_PP") ? atoi(getenv("FTB_LSTM_PP")) : 0;
-    if (use_pp && B > 16) return launch_lstm_pp(xg, w_hh, out, nullptr, 0.f, B, S, out_bf16, s);
-    return dispatch_rnn_tc<4, 512, 16>(xg, w_hh, nullptr, out, B, S, out_bf16, s);
+    if (use_pp && B > 16) return launch_lstm_pp(xg, w_hh, out, nullptr, 0.f, B, S, out_bf16, s, xrow, ldo, lo_off);
+    return dispatch_rnn_tc<4, 512, 16>(xg, w_hh, nullptr, out, B, S, out_bf16, s, xrow, ldo, lo_off);
   }
-  if (!is_lstm && H == 256) return rnn_gru256_mma(xg, w_hh, b_hn, out, B, S, out_bf16, s);
+  FTB_REQUIRE(!xrow, FTB_ERR_UNSUPPORTED, "rnn_bidir: the row-indexed input exists for the H=512 LSTM only");
+  if (!is_lstm && H == 256) return rnn_gru256_mma(xg, w_hh, b_hn, out, B, S, out_bf16, s, ldo, lo_off);
   set_error("rnn_bidir: no kernel for %s with H=%d (built: GRU 64/128/256, LSTM 512)", is_lstm ? "LSTM" : "GRU", H);
   return FTB_ERR_UNSUPPORTED;
 }
+
+FTB_DEFINE_TIMEOUT_READER(rnn_tc_timeouts)
 
 }  // namespace ftb
 

@@ -104,6 +104,11 @@ int ftb_device_check(int device, int* sm_count, int* cc_major, int* cc_minor);
 int ftb_length_plan(float* dur, int32_t* cum, int32_t* total, int B, int T, void* stream);
 int ftb_length_expand(const void* x, const int32_t* cum, void* out, int B, int T, int L, int C,
                       int elem_bytes, void* stream);
+/* The same expansion as an index: idx (B,L) int32 <- b*T + t for the phoneme t whose frames hold j
+ * (cum[b,t-1] <= j < cum[b,t]); pad_row for the zero-padded tail (line 18).  out[b,j] == x_rows[idx[b,j]] when row
+ * pad_row of x_rows is zero.  Lets a per-row-linear consumer (the decoder LSTM's input projection,
+ * models/forward_tacotron.py:317-321) run once per phoneme instead of once per frame. */
+int ftb_length_index(const int32_t* cum, int32_t* idx, int B, int T, int L, int pad_row, void* stream);
 
 /* Duration fallback, models/forward_tacotron.py:254-255: if the batch-global sum
  * of trunc-toward-zero(dur) is <= 0, fill dur with 2.0.  scratch: 8 bytes. */
@@ -145,14 +150,25 @@ int ftb_conv_gemm_bf16(const void* x, const void* w_packed, const ftb_conv_desc*
  * pointers; no residual / transposed output.  All N must select the same tile width (equal N is enough). */
 int ftb_conv_bank_bf16(const void* x, const void* const* w_packed, const ftb_conv_desc* descs, int n_convs,
                        int maxpool, void* stream);
-/* Every mbarrier wait in the tcgen05 kernel is bounded so a protocol bug cannot hang the GPU;
- * this returns how many waits gave up since the library was loaded (0 in a healthy run). */
+/* Every mbarrier wait of the pipelined kernels (tcgen05 GEMM, LSTM / GRU clusters) is bounded so a protocol bug cannot
+ * hang the GPU; a wait that expires counts itself and TRAPS the kernel, so the launch fails loudly (the next CUDA call
+ * returns an error) instead of continuing on data that has not arrived.  Returns the number of expired waits since the
+ * library was loaded: 0 in a healthy run, -1 when the context is already dead. */
 int ftb_tc_timeout_count(void);
 /* Pack a reference-layout conv weight (N, Cin, k) f32 into (Npad, k*Cin_pad) K-major
  * f32 (out_bf16 = 0), bf16 (1) or IEEE half (2), zero padded.  Mode 3: (Npad, 6, k, Cin_pad) bf16, the K axis of the
- * split-precision GEMM (three bf16 parts per weight, arranged for the six part products). */
+ * split-precision GEMM (three bf16 parts per weight, arranged for the six part products).  Modes 4 (bf16) / 5 (IEEE
+ * half): (Npad, 3, k, Cin_pad) = [hi | hi | lo], the K axis of a GEMM over a two-part activation hi | lo
+ * (ftb_rnn_bidir_rows lo_off): hi.hi + lo.hi + hi.lo, the operand pair of the output heads. */
 int ftb_pack_conv_weight(const float* w, void* out, int N, int Cin, int k, int Npad, int Cin_pad,
                          int out_bf16, void* stream);
+
+/* Linear layer over a two-part 16-bit activation (the output heads lin / post_proj, models/forward_tacotron.py:322,326):
+ * x_pair (B,S,2*Cin) = [hi | lo] as written by ftb_rnn_bidir_rows with lo_off = Cin, w_packed from
+ * ftb_pack_conv_weight mode 4 (bf16) / 5 (IEEE half); out_f32 (B,S,ldo) = (hi + lo) . (w_hi + w_lo)^T + bias up to the
+ * lo.lo term, fp32 accumulation on tcgen05.  Cin % 64 == 0. */
+int ftb_linear_pair(const void* x_pair, const void* w_packed, int B, int S, int Cin, int N, const float* bias,
+                    float* out_f32, int ldo, int fp16, void* stream);
 
 /* Bidirectional single-layer GRU / LSTM recurrence (torch.nn.GRU / nn.LSTM,
  * batch_first, zero initial state; models/common_layers.py:84, models/forward_tacotron.py:39,165).
@@ -166,6 +182,14 @@ int ftb_pack_conv_weight(const float* w, void* out, int N, int Cin, int k, int N
  * Both exchange the hidden state through distributed shared memory. */
 int ftb_rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H,
                   int is_lstm, int out_bf16, void* stream);
+/* As ftb_rnn_bidir with two extensions the models use (nn.LSTM after LengthRegulator, forward_tacotron.py:317-321):
+ *   xrow (H = 512 LSTM; NULL = off): (B,S) int32, frame (b,t) reads row xrow[b,t] of xg (rows of 2*G*H floats) --
+ *     the input projection is computed once per PHONEME and gathered by the recurrence (ftb_length_index);
+ *   ldo / lo_off (H >= 256): out rows are ldo elements apart (0 = 2H); with a 16-bit out_kind and lo_off > 0 the
+ *     rounding remainder h - hi is stored lo_off elements after hi in the same 16-bit type, so the consumer GEMM can
+ *     read hi + lo (the output heads need more than an 11-bit activation at trained mel magnitude). */
+int ftb_rnn_bidir_rows(const float* xg, const int32_t* xrow, const float* w_hh, const float* b_hn, void* out,
+                       int B, int S, int H, int is_lstm, int out_kind, int ldo, int lo_off, void* stream);
 
 /* DSP.wav_to_mel, utils/dsp.py:71-87,105-107, for a batch of clips packed back to
  * back: audio f32, clip_offsets (n_clips+1) int64 sample offsets, frame_offsets
@@ -197,8 +221,9 @@ typedef struct ftb_ft_config { /* keys of config.yaml forward_tacotron.model + n
   int32_t postnet_dims, postnet_k, postnet_num_highways;
   int32_t n_mels;
   float pitch_strength, energy_strength;
-  int32_t gemm_mode; /* 0: bf16 tcgen05 GEMMs (duration predictor stays fp32); 1: all GEMMs fp32 SIMT;
-                        2: IEEE-half tcgen05 GEMMs (same rate, 11-bit significand: for trained-magnitude mels) */
+  int32_t gemm_mode; /* 0 (default): IEEE-half operands, fp32 accumulation on tcgen05 (11-bit significand: holds the
+                        absolute mel tolerance at trained-checkpoint magnitude; duration predictor fp32-grade, output
+                        heads on two-part operands); 1: all GEMMs fp32 SIMT; 2: bf16 operands (same kernels and rate) */
 } ftb_ft_config;
 
 typedef struct ftb_ft_handle ftb_ft_handle;

@@ -150,3 +150,35 @@ def test_conv_bank_grouped(B, S, Cin, ch, K, pool):
     assert float((got[:, :, :K * ch] - want).abs().max()) < 3e-3
     assert torch.all(got[:, :, K * ch:] == 7.0)
     assert lib.ftb_tc_timeout_count() == 0
+
+
+@pytest.mark.parametrize('fp16', [False, True])
+@pytest.mark.parametrize('B,S,Cin,N', [(2, 150, 1024, 80), (3, 70, 512, 80), (1, 129, 64, 256)])
+def test_linear_over_hi_lo_pair(B, S, Cin, N, fp16):
+    """The output heads: activation and weight both as 16-bit pairs hi + lo, three part products on tcgen05.  Against an
+    fp64 product of the fp32 operands: the error is that of a 16-bit (bf16 pair) / 21-bit (half pair) operand, orders
+    below the single-part kernel's."""
+    lib, dev = _lib.lib(), torch.device('cuda')
+    g = torch.Generator().manual_seed(Cin + N + S)
+    x = torch.randn(B, S, Cin, generator=g) * 0.3
+    w = torch.randn(N, Cin, generator=g) * (30.0 / Cin ** 0.5)            # trained-magnitude head
+    bias = torch.randn(N, generator=g)
+    dt = torch.float16 if fp16 else torch.bfloat16
+    hi = x.to(dt)
+    lo = (x - hi.float()).to(dt)
+    pair = torch.cat([hi, lo], dim=2).contiguous().to(dev)
+    wd = w.to(dev).contiguous()
+    wp = torch.empty(N * 3 * Cin, dtype=dt, device=dev)
+    _lib.check(lib.ftb_pack_conv_weight(_lib.ptr(wd), _lib.ptr(wp), N, Cin, 1, N, Cin, 5 if fp16 else 4, None))
+    bd = bias.to(dev)
+    out = torch.full((B, S, N + 4), 7.0, dtype=torch.float32, device=dev)
+    _lib.check(lib.ftb_linear_pair(_lib.ptr(pair), _lib.ptr(wp), B, S, Cin, N, _lib.ptr(bd), _lib.ptr(out), N + 4, int(fp16),
+                                   _lib.current_stream(dev)))
+    torch.cuda.synchronize()
+    want = (x.double() @ w.double().T + bias.double()).float()
+    got = out.cpu()
+    single = (hi.float().double() @ w.to(dt).float().double().T + bias.double()).float()  # what one 16-bit part gives
+    e_pair, e_single = float((got[:, :, :N] - want).abs().max()), float((single - want).abs().max())
+    print(f'fp16={fp16} Cin={Cin}: pair max-abs {e_pair:.2e}, single-part {e_single:.2e}, |y| max {float(want.abs().max()):.1f}')
+    assert e_pair < (2e-5 if fp16 else 6e-4) * max(1.0, float(want.abs().max())) and e_pair < e_single / 20
+    assert torch.all(got[:, :, N:] == 7.0) and lib.ftb_tc_timeout_count() == 0

@@ -61,9 +61,10 @@ def test_batch_against_oracle(gemm_mode):
 
 @pytest.mark.parametrize('gemm_mode', [0, 2])
 def test_trained_magnitude_stress(gemm_mode):
-    """Output heads scaled so mels have trained-checkpoint magnitude (std ~2): the absolute tolerance is the
-    hard case here (last hard part) -> report, and require the RELATIVE error to stay small.
-    gemm_mode 2 (IEEE-half operands) is the mode offered for this case; both are reported."""
+    """Output heads scaled so mels have trained-checkpoint magnitude (std ~2): the hard case for the ABSOLUTE
+    north-star tolerance (last hard part).  The default mode (0: IEEE-half operands, fp32 accumulation,
+    two-part operands for the heads) must hold max-abs 1e-2 / mean-abs 1e-3 here; bf16 operands (mode 2, opt-in) are
+    reported and held to a relative bound only."""
     model, _ = cuda_model('forward_tacotron', gemm_mode, mel_gain=30.0)
     x = synth.synthetic_tokens(4, 60, seed=4)
     want = mo.ft_generate(cpu_state_dict(model), x)
@@ -76,7 +77,8 @@ def test_trained_magnitude_stress(gemm_mode):
         print(f'stress gemm_mode {gemm_mode} {k}: std {float(want[k].std()):.2f} max-abs {float(d.max()):.3e} mean-abs {float(d.mean()):.3e} '
               f'rel {rel_max:.3e}/{rel_mean:.3e}')
         assert rel_max < 0.1 and rel_mean < 0.01
-        if gemm_mode == 2:  # IEEE-half operands hold the ABSOLUTE north-star tolerance at this magnitude too
+        if gemm_mode == 0:
+            assert float(want[k].std()) > 1.5
             assert float(d.max()) < MAX_ABS and float(d.mean()) < MEAN_ABS
 
 
@@ -84,14 +86,15 @@ def test_submodules_against_reference_fixture():
     g = load('ft_submodules')
     for mode in (1, 0):
         model, _ = cuda_model('forward_tacotron', mode)
-        tol = (2e-4, 2e-5) if mode == 1 else (MAX_ABS, MEAN_ABS)
-        # the GRU of the CBHG runs bf16 recurrent operands in both modes
-        assert_close(model.run_cbhg('prenet', g['prenet_in'].cuda()), g['prenet_out'], what='prenet')
-        assert_close(model.run_cbhg('postnet', g['postnet_in'].cuda()), g['postnet_out'], what='postnet')
+        # all-fp32 mode: fp32 GEMMs and epilogues; only the CBHG GRU's recurrent operand (h, W_hh) is 16-bit (bf16 with
+        # an fp32 output), which bounds the output error at a few 1e-4 -- a genuine epilogue bug of size 1e-3 fails
+        tol = (1e-3, 1e-4) if mode == 1 else (MAX_ABS, MEAN_ABS)
+        r1 = assert_close(model.run_cbhg('prenet', g['prenet_in'].cuda()), g['prenet_out'], *tol, what='prenet')
+        r2 = assert_close(model.run_cbhg('postnet', g['postnet_in'].cuda()), g['postnet_out'], *tol, what='postnet')
+        print('submodules mode', mode, 'prenet', r1, 'postnet', r2)
         # the duration predictor is exact fp32 in both modes
         assert_close(model.run_series_predictor('dur_pred', g['dur_tokens'].cuda(), 0.9), g['dur_out'], 2e-4, 2e-5,
                      'dur_pred')
-        del tol
 
 
 def test_api_surface():

@@ -66,3 +66,25 @@ def test_duration_fallback(case):
     scratch = torch.zeros(8, dtype=torch.uint8, device='cuda')
     _lib.check(_lib.lib().ftb_duration_fallback(_lib.ptr(d), d.numel(), _lib.ptr(scratch), _lib.current_stream(d.device)))
     assert torch.equal(d.cpu(), want)
+
+
+@pytest.mark.parametrize('B,T,L_cut', [(3, 50, 0), (64, 200, 0), (2, 2000, 0), (4, 33, 17), (1, 1, 0)])
+def test_frame_index_matches_the_expansion(B, T, L_cut):
+    """ftb_length_index is the LengthRegulator as a gather map: x_rows[idx] == expand(x), pad row for the zero tail."""
+    g = torch.Generator().manual_seed(B * 31 + T)
+    dur = (torch.rand(B, T, generator=g) * 9 - 1).cuda()
+    cum, total = LengthRegulator.plan(dur)
+    L = int(total.max()) if not L_cut else min(L_cut, int(total.max()))
+    if L == 0:
+        pytest.skip('all durations rounded to zero')
+    idx = torch.empty(B, L, dtype=torch.int32, device='cuda')
+    _lib.check(_lib.lib().ftb_length_index(_lib.ptr(cum), _lib.ptr(idx), B, T, L, B * T, _lib.current_stream(idx.device)))
+    x = torch.randn(B, T, 64, generator=g).cuda()
+    rows = torch.cat([x.view(B * T, 64), torch.zeros(1, 64, device='cuda')])
+    want = LengthRegulator.expand(x, cum, L)
+    assert torch.equal(rows[idx.long()], want)
+    # and against the oracle's own repeat_interleave
+    r = (dur.cpu().clamp(min=0) + 0.5).long()
+    for b in range(B):
+        seq = torch.repeat_interleave(torch.arange(T) + b * T, r[b])[:L]
+        assert torch.equal(idx[b, :len(seq)].cpu().long(), seq) and bool((idx[b, len(seq):] == B * T).all())
