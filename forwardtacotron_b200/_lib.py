@@ -88,6 +88,8 @@ SIGNATURES = {
     'ftb_length_expand': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'ftb_length_index': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'ftb_duration_fallback': (_I, [_P, _L, _P, _P]),
+    'ftb_zero_tail_rows': (_I, [_P, _I, _I, _L, _P, _P]),
+    'ftb_duration_fallback_rows': (_I, [_P, _P, _I, _I, _P]),
     'ftb_conv_gemm_f32': (_I, [_P, _P, C.POINTER(ConvDesc), _P]),
     'ftb_conv_gemm_bf16': (_I, [_P, _P, C.POINTER(ConvDesc), _P]),
     'ftb_conv_bank_bf16': (_I, [_P, C.POINTER(_P), C.POINTER(ConvDesc), _I, _I, _P]),
@@ -96,6 +98,7 @@ SIGNATURES = {
     'ftb_linear_pair': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     'ftb_rnn_bidir': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'ftb_rnn_bidir_rows': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'ftb_rnn_bidir_packed': (_I, [_P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'ftb_mel_create': (_I, [C.POINTER(MelConfig), _I, C.POINTER(_P)]),
     'ftb_mel_destroy': (None, [_P]),
     'ftb_mel_run': (_I, [_P, _P, _P, _P, _I, _L, _P, _I, _P]),
@@ -107,6 +110,8 @@ SIGNATURES = {
     'ftb_ft_predict': (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _L, _P]),
     'ftb_ft_synthesize': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _L, _P]),
     'ftb_ft_synthesize_packed': (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _L, _P]),
+    'ftb_ft_predict_ragged': (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _L, _P]),
+    'ftb_ft_synthesize_ragged': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _L, _P]),
     'ftb_ft_series_predictor': (_I, [_P, _I, _P, _I, _I, _F, _P, _P, _L, _P]),
     'ftb_ft_cbhg': (_I, [_P, _I, _P, _I, _I, _P, _P, _L, _P]),
     'ftb_ft_last_launch_count': (_I, [_P]),

@@ -1,6 +1,8 @@
 // Small bandwidth-bound kernels around the GEMMs: embedding lookup, CBHG max-pool,
 // highway gate mix, pitch/energy conditioning, the N=1 predictor heads, LayerNorm,
 // positional encoding, and the one-time weight preparation kernels.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace ftb {
@@ -35,6 +37,67 @@ __global__ void embed_split3_kernel(const int64_t* __restrict__ tok, const float
     __nv_bfloat16* o = out + r * 3 * C + c;
     o[0] = hi, o[C] = mid, o[2 * C] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
   }
+}
+
+// ---- ragged batches: zero the rows t >= lens[b] of a (B, S, row_bytes) tensor ----------------------------------------
+// A padded batch equals the per-sentence runs of the reference (gen_forward.py:106-118, B = 1) when every conv sees
+// zeros beyond the end of a row -- exactly the zero padding of the solo run -- and every recurrence stops at the row's
+// length.  This kernel restores the zeros after each layer whose output feeds a conv with k > 1; it touches only the
+// padded rows, which length bucketing keeps few.  One block per (chunk of the tail, utterance); 16-byte stores.
+__global__ void __launch_bounds__(256) zero_tail_rows_kernel(unsigned char* __restrict__ x, int S, int64_t row_bytes,
+                                                             const int32_t* __restrict__ lens) {
+  const int b = blockIdx.y;
+  const int len = min(max(__ldg(lens + b), 0), S);
+  const int64_t n16 = (int64_t)(S - len) * row_bytes / 16;  // row_bytes % 16 == 0 or the scalar path below
+  unsigned char* p = x + ((int64_t)b * S + len) * row_bytes;
+  if (row_bytes % 16 == 0 && ((uintptr_t)x & 15) == 0) {
+    uint4* p16 = reinterpret_cast<uint4*>(p);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+      p16[i] = make_uint4(0, 0, 0, 0);
+  } else {
+    const int64_t n = (int64_t)(S - len) * row_bytes;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0;
+  }
+}
+
+int zero_tail_rows(void* x, int B, int S, int64_t row_bytes, const int32_t* lens, cudaStream_t s) {
+  FTB_REQUIRE(x && lens && B > 0 && S > 0 && row_bytes > 0 && B <= 65535, FTB_ERR_INVALID, "zero_tail_rows: bad arguments");
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
+  // grid.x sized for a tail of up to ~1/8 of the rows; longer tails loop
+  const int gx = (int)std::min<int64_t>(std::max<int64_t>(1, (int64_t)S * row_bytes / 16 / 256 / 8), 64);
+  zero_tail_rows_kernel<<<dim3(gx, B), 256, 0, s>>>((unsigned char*)x, S, row_bytes, lens);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+
+// Duration fallback of a ragged batch: the reference evaluates `if dur.long().sum() <= 0: dur[:] = 2` per generate()
+// call, i.e. per SENTENCE in gen_forward.py; here per row over its lens[b] valid positions.  One block per row.
+__global__ void __launch_bounds__(256) dur_fallback_rows_kernel(float* __restrict__ dur, const int32_t* __restrict__ lens, int T) {
+  __shared__ long long part[8];
+  __shared__ int fill;
+  const int b = blockIdx.x, len = min(max(__ldg(lens + b), 0), T);
+  float* d = dur + (int64_t)b * T;
+  long long s = 0;
+  for (int t = threadIdx.x; t < len; t += blockDim.x) s += (long long)d[t];  // .long(): truncation toward zero
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tot = 0;
+    for (int i = 0; i < 8; ++i) tot += part[i];
+    fill = tot <= 0;
+  }
+  __syncthreads();
+  if (fill)
+    for (int t = threadIdx.x; t < len; t += blockDim.x) d[t] = 2.0f;
+}
+
+int dur_fallback_rows(float* dur, const int32_t* lens, int B, int T, cudaStream_t s) {
+  FTB_REQUIRE(dur && lens && B > 0 && T > 0, FTB_ERR_INVALID, "dur_fallback_rows: bad arguments");
+  dur_fallback_rows_kernel<<<B, 256, 0, s>>>(dur, lens, T);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
 }
 
 // ---- MaxPool1d(2,1,1)[:S] along t on channel-last data, in place (common_layers.py:73,100) --
@@ -359,3 +422,10 @@ template int to_f32<__nv_bfloat16>(const __nv_bfloat16*, float*, int64_t, cudaSt
 template int to_f32<__half>(const __half*, float*, int64_t, cudaStream_t);
 
 }  // namespace ftb
+
+extern "C" int ftb_zero_tail_rows(void* x, int B, int S, int64_t row_bytes, const int32_t* lens, void* stream) {
+  return ftb::zero_tail_rows(x, B, S, row_bytes, lens, (cudaStream_t)stream);
+}
+extern "C" int ftb_duration_fallback_rows(float* dur, const int32_t* lens, int B, int T, void* stream) {
+  return ftb::dur_fallback_rows(dur, lens, B, T, (cudaStream_t)stream);
+}

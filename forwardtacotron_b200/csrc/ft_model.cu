@@ -60,6 +60,7 @@ struct ftb_ft_handle : ftb::ModelBase {
   char* pre_buf = nullptr;
   int64_t pre_cap = 0;
   const int64_t* pre_tok = nullptr;
+  const int32_t* pre_lens = nullptr;
   int pre_B = 0, pre_T = 0;
   bool pre_valid = false;
   void* pre_enc = nullptr;
@@ -203,9 +204,19 @@ static CbhgBufs<T> plan_cbhg(Arena& A, const CbhgW& W, int B, int S) {
 }
 
 // ---- stage runners ----------------------------------------------------------------------
+// lens (optional, (B) int32 token counts): ragged batch -- every row is computed as if it were alone (zero padding
+// beyond its length for the convs, the GRU stops / starts at its last token), outputs beyond the length are zero.
+#define FTB_ZERO_TAIL(ptr, S_, row_bytes)                                            \
+  do {                                                                               \
+    if (lens) {                                                                      \
+      FTB_TRY(zero_tail_rows((ptr), B, (S_), (int64_t)(row_bytes), lens, s));        \
+      ++h->launches;                                                                 \
+    }                                                                                \
+  } while (0)
+
 template <typename T>
 static int run_series(ftb_ft_handle* h, SeriesW& P, const int64_t* tok, int B, int Tn, float alpha, float* out,
-                      Arena& A, cudaStream_t s) {
+                      Arena& A, cudaStream_t s, const int32_t* lens = nullptr) {
   const int64_t mark = A.mark();
   SeriesBufs<T> w = plan_series<T>(A, P, B, Tn);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for SeriesPredictor");
@@ -213,23 +224,31 @@ static int run_series(ftb_ft_handle* h, SeriesW& P, const int64_t* tok, int B, i
   if (std::is_same<T, float>::value && P.tc_split && !h->opt_dur_simt) {
     bf16 *e3 = (bf16*)w.emb, *a3 = (bf16*)w.a, *b3 = (bf16*)w.b;
     FTB_TRY(embed_split3(tok, P.emb, e3, M, P.E, h->cfg.num_chars, s));
+    FTB_ZERO_TAIL(e3, Tn, 3 * P.E * 2);
     FTB_TRY(h->gemm_split(P.conv[0], e3, B, Tn, nullptr, 0, a3, s));
+    FTB_ZERO_TAIL(a3, Tn, 3 * P.C * 2);
     FTB_TRY(h->gemm_split(P.conv[1], a3, B, Tn, nullptr, 0, b3, s));
+    FTB_ZERO_TAIL(b3, Tn, 3 * P.C * 2);
     FTB_TRY(h->gemm_split(P.conv[2], b3, B, Tn, nullptr, 0, a3, s));
     FTB_TRY(h->gemm_split(P.rnn.in, a3, B, Tn, w.xg, 6 * P.H, nullptr, s));
-    FTB_TRY(rnn_bidir(w.xg, P.rnn.w_hh, P.rnn.b_hn, w.ro, B, Tn, P.H, 0, 0, s));
+    FTB_TRY(rnn_bidir(w.xg, P.rnn.w_hh, P.rnn.b_hn, w.ro, B, Tn, P.H, 0, 0, s, nullptr, 0, 0, lens));
     FTB_TRY(head1<float>(w.ro, P.lin_w, P.lin_b, alpha, out, M, 2 * P.H, s));
+    FTB_ZERO_TAIL(out, Tn, 4);
     h->launches += 3;
     A.reset(mark);
     return FTB_OK;
   }
   FTB_TRY(embed<T>(tok, P.emb, w.emb, M, P.E, P.E, h->cfg.num_chars, s));
+  FTB_ZERO_TAIL(w.emb, Tn, P.E * sizeof(T));
   FTB_TRY(h->gemm<T>(P.conv[0], w.emb, P.E, B, Tn, act_out(w.a, P.C), nullptr, 0, 1.f, s));
+  FTB_ZERO_TAIL(w.a, Tn, P.C * sizeof(T));
   FTB_TRY(h->gemm<T>(P.conv[1], w.a, P.C, B, Tn, act_out(w.b, P.C), nullptr, 0, 1.f, s));
+  FTB_ZERO_TAIL(w.b, Tn, P.C * sizeof(T));
   FTB_TRY(h->gemm<T>(P.conv[2], w.b, P.C, B, Tn, act_out(w.a, P.C), nullptr, 0, 1.f, s));
   FTB_TRY(h->gemm<T>(P.rnn.in, w.a, P.C, B, Tn, act_out(w.xg, 6 * P.H), nullptr, 0, 1.f, s));
-  FTB_TRY(rnn_bidir(w.xg, P.rnn.w_hh, P.rnn.b_hn, w.ro, B, Tn, P.H, 0, 0, s));
+  FTB_TRY(rnn_bidir(w.xg, P.rnn.w_hh, P.rnn.b_hn, w.ro, B, Tn, P.H, 0, 0, s, nullptr, 0, 0, lens));
   FTB_TRY(head1<float>(w.ro, P.lin_w, P.lin_b, alpha, out, M, 2 * P.H, s));
+  FTB_ZERO_TAIL(out, Tn, 4);
   h->launches += 3;
   A.reset(mark);
   return FTB_OK;
@@ -238,15 +257,18 @@ static int run_series(ftb_ft_handle* h, SeriesW& P, const int64_t* tok, int B, i
 // x: (B,S,ldx) with ldx >= CinP of the bank convs and zero padding columns; out: (B,S,2*ch)
 // out_ld / out_lo: row stride of `out` and offset of the 16-bit remainder part (rnn_bidir); 0 = plain (B,S,2*ch)
 template <typename T>
+// lens: ragged batch (see run_series); x must already be zero beyond each row's length
 static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int S, T* out, Arena& A, cudaStream_t s,
-                    int out_ld = 0, int out_lo = 0) {
+                    int out_ld = 0, int out_lo = 0, const int32_t* lens = nullptr) {
   const int64_t mark = A.mark();
   CbhgBufs<T> w = plan_cbhg<T>(A, W, B, S);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for CBHG");
   const int64_t M = (int64_t)B * S;
   const int bank_c = W.K * W.ch;
   FTB_TRY(h->conv_bank<T>(W.bank, x, ldx, B, S, w.bank, W.ch, s));
+  FTB_ZERO_TAIL(w.bank, S, bank_c * sizeof(T));
   FTB_TRY(h->gemm<T>(W.proj1, w.bank, bank_c, B, S, act_out(w.p1, W.p0), nullptr, 0, 1.f, s));
+  FTB_ZERO_TAIL(w.p1, S, W.p0 * sizeof(T));
   if (w.ld2 != W.p1) FTB_CHECK_CUDA(cudaMemsetAsync(w.p2, 0, (size_t)M * w.ld2 * sizeof(T), s));
   FTB_TRY(h->gemm<T>(W.proj2, w.p1, W.p0, B, S, act_out(w.p2, w.ld2), x, ldx, 1.f, s));  // + residual
   FTB_TRY(h->gemm<T>(W.pre_hw, w.p2, w.ld2, B, S, act_out(w.ha, W.ch), nullptr, 0, 1.f, s));
@@ -262,19 +284,24 @@ static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int 
     std::swap(cur, nxt);
   }
   FTB_TRY(h->gemm<T>(W.rnn.in, cur, W.ch, B, S, act_out(w.xg, 6 * W.ch), nullptr, 0, 1.f, s));
-  FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, out_kind<T>(), s, nullptr, out_ld, out_lo));
+  FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, out_kind<T>(), s, nullptr, out_ld, out_lo, lens));
   h->launches += 1;
   A.reset(mark);
   return FTB_OK;
 }
 
 template <typename T>
-static int run_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn, T* x0, T* enc, Arena& A, cudaStream_t s);
+static int run_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn, T* x0, T* enc, Arena& A, cudaStream_t s,
+                      const int32_t* lens);
 
 template <typename T>
 static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* cum, const float* pitch,
                           const float* energy, int B, int Tn, int L, float* mel, float* mel_post, Arena& A,
-                          cudaStream_t s, const int32_t* mel_lens = nullptr, float pad_value = 0.f) {
+                          cudaStream_t s, const int32_t* mel_lens = nullptr, float pad_value = 0.f,
+                          const int32_t* tok_lens = nullptr) {
+  // tok_lens != nullptr: ragged batch -- row b is synthesised as if it were alone (tok_lens[b] tokens, mel_lens[b]
+  // frames); mel_lens alone: only the decoder LSTM runs over packed sequences (teacher-forced forward()).
+  const int32_t* lens = nullptr;  // the FTB_ZERO_TAIL mask of the current stage
   const ftb_ft_config& c = h->cfg;
   const int E = c.embed_dims, D = 2 * c.prenet_dims, RH = c.rnn_dims, NM = c.n_mels;
   const int melP = (int)align_up(NM, 64);
@@ -291,11 +318,11 @@ static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* c
   T* post = A.take<T>(ML * post_ld);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for synthesize");
 
-  if (h->pre_valid && h->pre_tok == tok && h->pre_B == B && h->pre_T == Tn) {
+  if (h->pre_valid && h->pre_tok == tok && h->pre_lens == tok_lens && h->pre_B == B && h->pre_T == Tn) {
     FTB_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_join[3], 0));  // prenet already computed (or in flight) on side stream 3
     enc = (T*)h->pre_enc;
   } else {
-    FTB_TRY(run_prenet<T>(h, tok, B, Tn, x0, enc, A, s));
+    FTB_TRY(run_prenet<T>(h, tok, B, Tn, x0, enc, A, s, tok_lens));
   }
   h->pre_valid = false;
   FTB_TRY(cond_add<T>(enc, pitch, energy, h->pitch_w, h->pitch_b, h->energy_w, h->energy_b, c.pitch_strength,
@@ -308,18 +335,16 @@ static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* c
   FTB_TRY(h->gemm<T>(h->lstm.in, enc, D, B, Tn, act_out(xg, 8 * RH), nullptr, 0, 1.f, s));
   FTB_CHECK_CUDA(cudaMemcpyAsync(xg + MT * 8 * RH, h->lstm.in.bias, sizeof(float) * 8 * RH, cudaMemcpyDeviceToDevice, s));
   FTB_TRY(length_index(cum, fidx, B, Tn, L, (int)MT, s));
-  if (mel_lens) {  // packed sequences (teacher-forced forward in eval mode)
-    ProfScope prof(FAM_RNN_LSTM, 2.0 * 2 * B * L * 4.0 * RH * RH, 0.0, s);
-    FTB_TRY(lstm512_packed(xg, h->lstm.w_hh, dec, mel_lens, pad_value, B, L, out_kind<T>(), s, fidx, dec_ld,
-                           HP == 2 ? 2 * RH : 0));
-  } else {
-    FTB_TRY(rnn_bidir(xg, h->lstm.w_hh, nullptr, dec, B, L, RH, 1, out_kind<T>(), s, fidx, dec_ld, HP == 2 ? 2 * RH : 0));
-  }
+  // mel_lens: packed sequences (teacher-forced forward in eval mode; ragged batches) -- rows stop at mel_lens[b]
+  FTB_TRY(rnn_bidir(xg, h->lstm.w_hh, nullptr, dec, B, L, RH, 1, out_kind<T>(), s, fidx, dec_ld, HP == 2 ? 2 * RH : 0,
+                    mel_lens, pad_value));
   if (melP != NM) FTB_CHECK_CUDA(cudaMemsetAsync(mel_cl, 0, (size_t)ML * melP * sizeof(T), s));
   Out o = act_out(mel_cl, melP);
   o.t = mel;  // 'mel' (B,80,L) and the channel-last copy the postnet reads, from one epilogue
   FTB_TRY(h->gemm<T>(h->lin, dec, dec_ld, B, L, o, nullptr, 0, 1.f, s));
-  FTB_TRY(run_cbhg<T>(h, h->postnet, mel_cl, melP, B, L, post, A, s, post_ld, HP == 2 ? 2 * c.postnet_dims : 0));
+  lens = tok_lens ? mel_lens : nullptr;  // frame-rate stages of a ragged batch mask by the frame counts
+  FTB_ZERO_TAIL(mel_cl, L, melP * sizeof(T));
+  FTB_TRY(run_cbhg<T>(h, h->postnet, mel_cl, melP, B, L, post, A, s, post_ld, HP == 2 ? 2 * c.postnet_dims : 0, lens));
   Out op;
   op.t = mel_post;
   FTB_TRY(h->gemm<T>(h->post_proj, post, post_ld, B, L, op, nullptr, 0, 1.f, s));
@@ -329,11 +354,13 @@ static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* c
 
 // embedding -> CBHG prenet into `enc` (B,T,2*prenet_dims); x0 and the CBHG scratch come from A
 template <typename T>
-static int run_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn, T* x0, T* enc, Arena& A, cudaStream_t s) {
+static int run_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn, T* x0, T* enc, Arena& A, cudaStream_t s,
+                      const int32_t* lens) {
   const int E = h->cfg.embed_dims;
   FTB_TRY(embed<T>(tok, h->embedding, x0, (int64_t)B * Tn, E, E, h->cfg.num_chars, s));
   ++h->launches;
-  return run_cbhg<T>(h, h->prenet, x0, E, B, Tn, enc, A, s);
+  FTB_ZERO_TAIL(x0, Tn, E * sizeof(T));
+  return run_cbhg<T>(h, h->prenet, x0, E, B, Tn, enc, A, s, 0, 0, lens);
 }
 
 template <typename T>
@@ -348,7 +375,7 @@ static int64_t prenet_bytes(const ftb_ft_handle* h, int B, int Tn) {
 
 // starts the prenet on side stream 3 into handle-owned memory (FTB_OPT_OVERLAP_PRENET)
 template <typename T>
-static int prefetch_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn) {
+static int prefetch_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn, const int32_t* lens) {
   const int64_t need = prenet_bytes<T>(h, B, Tn);
   if (need > h->pre_cap) {
     FTB_CHECK_CUDA(cudaStreamSynchronize(h->side[3]));
@@ -362,9 +389,10 @@ static int prefetch_prenet(ftb_ft_handle* h, const int64_t* tok, int B, int Tn) 
   const int64_t MT = (int64_t)B * Tn;
   T* x0 = A.take<T>(MT * h->cfg.embed_dims);
   T* enc = A.take<T>(MT * 2 * h->cfg.prenet_dims);
-  FTB_TRY(run_prenet<T>(h, tok, B, Tn, x0, enc, A, h->side[3]));
+  FTB_TRY(run_prenet<T>(h, tok, B, Tn, x0, enc, A, h->side[3], lens));
   h->pre_enc = enc;
   h->pre_tok = tok;
+  h->pre_lens = lens;
   h->pre_B = B;
   h->pre_T = Tn;
   h->pre_valid = true;
@@ -478,16 +506,21 @@ extern "C" int64_t ftb_ft_workspace_bytes(const ftb_ft_handle* h, int B, int T, 
   return p;
 }
 
-extern "C" int ftb_ft_series_predictor(ftb_ft_handle* h, int which, const int64_t* tokens, int B, int T, float alpha,
-                                       float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+static int series_predictor(ftb_ft_handle* h, int which, const int64_t* tokens, const int32_t* lens, int B, int T,
+                            float alpha, float* out, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
   FTB_REQUIRE(h && tokens && out && which >= 0 && which < 3 && B > 0 && T > 0, FTB_ERR_INVALID,
               "ftb_ft_series_predictor: bad arguments");
   FTB_REQUIRE(alpha != 0.f, FTB_ERR_INVALID, "alpha must be non-zero");
   Arena A(workspace, workspace_bytes);
   SeriesW& P = h->series[which];
-  if (P.f32_only || !h->bf16_mode()) return run_series<float>(h, P, tokens, B, T, alpha, out, A, (cudaStream_t)stream);
-  return h->is_fp16() ? run_series<f16>(h, P, tokens, B, T, alpha, out, A, (cudaStream_t)stream)
-                      : run_series<bf16>(h, P, tokens, B, T, alpha, out, A, (cudaStream_t)stream);
+  if (P.f32_only || !h->bf16_mode()) return run_series<float>(h, P, tokens, B, T, alpha, out, A, s, lens);
+  return h->is_fp16() ? run_series<f16>(h, P, tokens, B, T, alpha, out, A, s, lens)
+                      : run_series<bf16>(h, P, tokens, B, T, alpha, out, A, s, lens);
+}
+
+extern "C" int ftb_ft_series_predictor(ftb_ft_handle* h, int which, const int64_t* tokens, int B, int T, float alpha,
+                                       float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  return series_predictor(h, which, tokens, nullptr, B, T, alpha, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int ftb_ft_set_option(ftb_ft_handle* h, int option, int value) {
@@ -509,8 +542,8 @@ extern "C" int ftb_ft_set_option(ftb_ft_handle* h, int option, int value) {
   return FTB_ERR_INVALID;
 }
 
-extern "C" int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, int T, float alpha, float* dur,
-                              float* pitch, float* energy, void* workspace, int64_t workspace_bytes, void* stream) {
+static int predict_impl(ftb_ft_handle* h, const int64_t* tokens, const int32_t* lens, int B, int T, float alpha, float* dur,
+                        float* pitch, float* energy, void* workspace, int64_t workspace_bytes, void* stream) {
   FTB_REQUIRE(h && tokens && dur && pitch && energy && workspace, FTB_ERR_INVALID, "ftb_ft_predict: bad arguments");
   FTB_REQUIRE(B > 0 && T > 0 && alpha != 0.f, FTB_ERR_INVALID, "ftb_ft_predict: bad sizes / alpha");
   h->launches = 0;
@@ -529,10 +562,15 @@ extern "C" int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, in
     const int64_t bytes = b16 ? series_bytes<bf16>(h, i, B, T) : series_bytes<float>(h, i, B, T);
     cudaStream_t si = fork ? h->side[i] : s;
     if (fork) FTB_CHECK_CUDA(cudaStreamWaitEvent(si, h->ev_fork, 0));
-    FTB_TRY(ftb_ft_series_predictor(h, i, tokens, B, T, i == 0 ? alpha : 1.f, outs[i], ws + off, bytes, si));
+    FTB_TRY(series_predictor(h, i, tokens, lens, B, T, i == 0 ? alpha : 1.f, outs[i], ws + off, bytes, si));
     if (i == 0) {
-      FTB_TRY(ftb_duration_fallback(dur, (int64_t)B * T, ws, si));
-      h->launches += 2;
+      if (lens) {  // ragged batch: the fallback is a per-sentence decision upstream (gen_forward.py runs B = 1)
+        FTB_TRY(dur_fallback_rows(dur, lens, B, T, si));
+        h->launches += 1;
+      } else {
+        FTB_TRY(ftb_duration_fallback(dur, (int64_t)B * T, ws, si));
+        h->launches += 2;
+      }
     }
     if (fork) FTB_CHECK_CUDA(cudaEventRecord(h->ev_join[i], si));
     off += bytes;
@@ -540,12 +578,40 @@ extern "C" int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, in
   if (!fork) return FTB_OK;
   if (h->opt_overlap_prenet) {
     FTB_CHECK_CUDA(cudaStreamWaitEvent(h->side[3], h->ev_fork, 0));
-    FTB_TRY(!b16 ? prefetch_prenet<float>(h, tokens, B, T)
-                 : h->is_fp16() ? prefetch_prenet<f16>(h, tokens, B, T) : prefetch_prenet<bf16>(h, tokens, B, T));
+    FTB_TRY(!b16 ? prefetch_prenet<float>(h, tokens, B, T, lens)
+                 : h->is_fp16() ? prefetch_prenet<f16>(h, tokens, B, T, lens) : prefetch_prenet<bf16>(h, tokens, B, T, lens));
     FTB_CHECK_CUDA(cudaEventRecord(h->ev_join[3], h->side[3]));
   }
   for (int i = 0; i < 3; ++i) FTB_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_join[i], 0));  // join
   return FTB_OK;
+}
+
+extern "C" int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, int T, float alpha, float* dur,
+                              float* pitch, float* energy, void* workspace, int64_t workspace_bytes, void* stream) {
+  return predict_impl(h, tokens, nullptr, B, T, alpha, dur, pitch, energy, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ftb_ft_predict_ragged(ftb_ft_handle* h, const int64_t* tokens, const int32_t* tok_lens, int B, int T,
+                                     float alpha, float* dur, float* pitch, float* energy, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+  FTB_REQUIRE(tok_lens, FTB_ERR_INVALID, "ftb_ft_predict_ragged: tok_lens is required");
+  return predict_impl(h, tokens, tok_lens, B, T, alpha, dur, pitch, energy, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ftb_ft_synthesize_ragged(ftb_ft_handle* h, const int64_t* tokens, const int32_t* tok_lens, const int32_t* cum,
+                                        const float* pitch, const float* energy, const int32_t* mel_lens, int B, int T,
+                                        int L, float* mel, float* mel_post, void* workspace, int64_t workspace_bytes,
+                                        void* stream) {
+  FTB_REQUIRE(h && tokens && tok_lens && cum && pitch && energy && mel_lens && mel && mel_post && workspace, FTB_ERR_INVALID,
+              "ftb_ft_synthesize_ragged: bad arguments");
+  FTB_REQUIRE(B > 0 && T > 0 && L > 0, FTB_ERR_INVALID, "ftb_ft_synthesize_ragged: bad sizes B=%d T=%d L=%d", B, T, L);
+  h->launches = 0;
+  Arena A(workspace, workspace_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->bf16_mode())
+    return h->is_fp16() ? run_synthesize<f16>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, s, mel_lens, 0.f, tok_lens)
+                        : run_synthesize<bf16>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, s, mel_lens, 0.f, tok_lens);
+  return run_synthesize<float>(h, tokens, cum, pitch, energy, B, T, L, mel, mel_post, A, s, mel_lens, 0.f, tok_lens);
 }
 
 extern "C" int ftb_ft_synthesize(ftb_ft_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,

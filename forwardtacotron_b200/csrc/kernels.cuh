@@ -40,12 +40,11 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
 // rnn_small.cu / rnn_cluster.cu
 // xrow (optional, H=512 LSTM): (B,S) int32 row of xg feeding frame (b,t) (default b*S + t).  ldo: out row stride
 // (default 2H); lo_off > 0: the 16-bit rounding remainder h - hi is written lo_off elements after hi.
+// lens (optional, (B) int32): packed-sequence semantics -- row b has lens[b] valid steps, the state is zero and the
+// output pad_value (LSTM; 0 elsewhere) beyond them, the reverse direction starts at the last valid step.
 int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
-              int out_bf16, cudaStream_t s, const int32_t* xrow = nullptr, int ldo = 0, int lo_off = 0);
-
-// rnn_tc.cu: decoder LSTM (H=512) over packed sequences -- state zero and output pad_value wherever t >= lens[b]
-int lstm512_packed(const float* xg, const float* w_hh, void* out, const int* lens, float pad_value, int B, int S,
-                   int out_bf16, cudaStream_t s, const int32_t* xrow = nullptr, int ldo = 0, int lo_off = 0);
+              int out_bf16, cudaStream_t s, const int32_t* xrow = nullptr, int ldo = 0, int lo_off = 0,
+              const int32_t* lens = nullptr, float pad_value = 0.f);
 
 // length_regulator.cu: idx (B,L) int32 <- row of the phoneme-rate tensor that frame (b, j) repeats: b*T + t with
 // cum[b,t-1] <= j < cum[b,t], or pad_row for the zero-padded tail j >= cum[b,T-1]
@@ -56,6 +55,8 @@ template <typename T>
 int attention(const T* qkv, const int64_t* tokens_for_mask, T* ctx, int B, int S, int E, int heads, cudaStream_t s);
 
 // elementwise.cu
+int zero_tail_rows(void* x, int B, int S, int64_t row_bytes, const int32_t* lens, cudaStream_t s);
+int dur_fallback_rows(float* dur, const int32_t* lens, int B, int T, cudaStream_t s);
 template <typename T>
 int embed(const int64_t* tok, const float* table, T* out, int64_t rows, int C, int ldo, int num_chars, cudaStream_t s);
 int split3_rows(const float* in, __nv_bfloat16* out, int64_t rows, int C, cudaStream_t s);

@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
                        const float* __restrict__ w_hh,  // (2,G*H,H)
                        const float* __restrict__ b_hn,  // (2,H) GRU only
                        void* __restrict__ out, int B, int S, int out_bf16,
-                       int ldo, int lo_off) {  // out row stride; > 0: 16-bit remainder h - hi at this offset (rnn_tc.cu)
+                       int ldo, int lo_off,    // out row stride; > 0: 16-bit remainder h - hi at this offset (rnn_tc.cu)
+                       const int32_t* __restrict__ lens) {  // optional (B): valid steps per row (packed-sequence semantics)
   using C = RnnCfg<G, H, CL, BC>;
   constexpr int HC = C::HC, NT = C::NT, KT = C::KT, HP = C::HP, PPT = C::PPT, PRE_LD = C::PRE_LD, NTL = C::NTL,
                 PAIRS = C::PAIRS;
@@ -150,11 +151,13 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
   float cstate[PPT], hprev[PPT], bhn[PPT];
   int64_t optr[PPT];
   bool pvalid[PPT];
+  int plen[PPT];  // valid steps of the pair's utterance: beyond it the state and the output are zero
 #pragma unroll
   for (int p = 0; p < PPT; ++p) {
     const int idx = tid + p * NT;
     const int u = idx % HC, n = idx / HC;
     pvalid[p] = idx < PAIRS && (b0 + n) < B;
+    plen[p] = (lens && pvalid[p]) ? __ldg(lens + b0 + n) : S;
     cstate[p] = 0.f;
     hprev[p] = 0.f;
     const int hu = rank * HC + u;
@@ -289,6 +292,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
           const float gn = tanh_mufu(xc[2 * PAIRS + idx] + gr * (pre[(2 * HC + u) * PRE_LD + n] + bhn[p]));
           hn = (1.f - gz) * gn + gz * hprev[p];
         }
+        if (t >= plen[p]) hn = 0.f, cstate[p] = 0.f;
         hprev[p] = hn;
         reinterpret_cast<unsigned short*>(hstage)[n * HC + u] =
             F16 ? __half_as_ushort(__float2half_rn(hn)) : __bfloat16_as_ushort(__float2bfloat16_rn(hn));
@@ -316,7 +320,8 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
 
 template <int G, int H, int CL, int BC, bool F16 = false>
 static int launch_rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S,
-                              int out_bf16, cudaStream_t s, int* max_clusters, int ldo = 0, int lo_off = 0) {
+                              int out_bf16, cudaStream_t s, int* max_clusters, int ldo = 0, int lo_off = 0,
+                              const int32_t* lens = nullptr) {
   using C = RnnCfg<G, H, CL, BC>;
   auto kern = rnn_cluster_kernel<G, H, CL, BC, F16>;
   static bool configured = false;
@@ -345,7 +350,7 @@ static int launch_rnn_cluster(const float* xg, const float* w_hh, const float* b
   }
   FTB_REQUIRE(max_active > 0, FTB_ERR_UNSUPPORTED, "a cluster of %d CTAs cannot be scheduled on this device", CL);
   if (ldo <= 0) ldo = 2 * H;
-  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16, ldo, lo_off));
+  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16, ldo, lo_off, lens));
   count_launch();
   return FTB_OK;
 }
@@ -358,7 +363,7 @@ static int launch_rnn_cluster(const float* xg, const float* w_hh, const float* b
 std::atomic<int> g_gru_min_chunk{getenv("FTB_GRU_MIN_CHUNK") ? atoi(getenv("FTB_GRU_MIN_CHUNK")) : 8};
 template <int G, int H, int CL>
 static int dispatch_bc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
-                       cudaStream_t s, int ldo, int lo_off) {
+                       cudaStream_t s, int ldo, int lo_off, const int32_t* lens) {
   int m8 = 0, m16 = 0, m24 = 0;
   FTB_TRY((launch_rnn_cluster<G, H, CL, 8>(nullptr, nullptr, nullptr, nullptr, B, S, 0, s, &m8)));
   FTB_TRY((launch_rnn_cluster<G, H, CL, 16>(nullptr, nullptr, nullptr, nullptr, B, S, 0, s, &m16)));
@@ -369,8 +374,8 @@ static int dispatch_bc(const float* xg, const float* w_hh, const float* b_hn, vo
   // IEEE-half activations (output type 2) take IEEE-half recurrent operands as well: same kernel, f16 mma
 #define FTB_RNN_BC(N)                                                                                         \
   case N:                                                                                                     \
-    return out_bf16 == 2 ? launch_rnn_cluster<G, H, CL, N, true>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr, ldo, lo_off) \
-                         : launch_rnn_cluster<G, H, CL, N, false>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr, ldo, lo_off);
+    return out_bf16 == 2 ? launch_rnn_cluster<G, H, CL, N, true>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr, ldo, lo_off, lens) \
+                         : launch_rnn_cluster<G, H, CL, N, false>(xg, w_hh, b_hn, out, B, S, out_bf16, s, nullptr, ldo, lo_off, lens);
   switch (bc) {
     FTB_RNN_BC(8)
     FTB_RNN_BC(16)
@@ -384,14 +389,14 @@ static int dispatch_bc(const float* xg, const float* w_hh, const float* b_hn, vo
 // GRU H=256 (the two CBHG RNNs): 8 utterances per cluster make the register-resident mma.sync step cheaper than
 // streaming the weight slice through tcgen05 every step (measured: 1.0 vs 1.6 us/step; DESIGN.md "recurrences").
 int rnn_gru256_mma(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
-                   cudaStream_t s, int ldo, int lo_off) {
+                   cudaStream_t s, int ldo, int lo_off, const int32_t* lens) {
   FTB_REQUIRE(b_hn, FTB_ERR_INVALID, "rnn_cluster: GRU needs b_hn");
   // Cluster of 4 (each CTA: 192 gate rows = 12 warps x 64 registers of A fragments) rather than 8: the hand-off to 3
   // instead of 7 peers shortens the step more than the doubled mma.sync work per SM lengthens it (cfg2: 1.32 vs
   // 1.41 ms for both CBHG GRUs) and the recurrence holds 64 instead of 128 SMs (FTB_GRU_CL=8 selects the old shape).
   static const int cl = getenv("FTB_GRU_CL") ? atoi(getenv("FTB_GRU_CL")) : 4;
-  if (cl == 8) return dispatch_bc<3, 256, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, s, ldo, lo_off);
-  return dispatch_bc<3, 256, 4>(xg, w_hh, b_hn, out, B, S, out_bf16, s, ldo, lo_off);
+  if (cl == 8) return dispatch_bc<3, 256, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, s, ldo, lo_off, lens);
+  return dispatch_bc<3, 256, 4>(xg, w_hh, b_hn, out, B, S, out_bf16, s, ldo, lo_off, lens);
 }
 
 FTB_DEFINE_TIMEOUT_READER(rnn_mma_timeouts)

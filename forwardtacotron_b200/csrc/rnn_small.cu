@@ -14,11 +14,24 @@ template <int H>
 __global__ void __launch_bounds__(3 * H) gru_small_kernel(const float* __restrict__ xg,    // (B,S,2,3H)
                                                           const float* __restrict__ w_hh,  // (2,3H,H)
                                                           const float* __restrict__ b_hn,  // (2,H)
-                                                          void* __restrict__ out, int S, int out_bf16) {
+                                                          void* __restrict__ out, int S_full, int out_bf16,
+                                                          const int32_t* __restrict__ lens) {  // optional (B): valid steps
   constexpr int G = 3 * H;
   __shared__ __align__(16) float h[H];
   __shared__ float gh[G];
   const int b = blockIdx.x, dir = blockIdx.y, tid = threadIdx.x;
+  // packed-sequence semantics: the row is a sequence of S = lens[b] steps (the reverse direction starts at its last valid
+  // step); the output beyond it is zero
+  const int S = lens ? min(max(__ldg(lens + b), 0), S_full) : S_full;
+  if (tid < H) {
+    for (int t = S; t < S_full; ++t) {
+      const int64_t o = ((int64_t)b * S_full + t) * (2 * H) + dir * H + tid;
+      if (out_bf16 == 2) ((__half*)out)[o] = __float2half_rn(0.f);
+      else if (out_bf16) ((__nv_bfloat16*)out)[o] = __float2bfloat16_rn(0.f);
+      else ((float*)out)[o] = 0.f;
+    }
+  }
+  if (S == 0) return;
 
   float w[H];  // this thread's gate row
   {
@@ -31,7 +44,7 @@ __global__ void __launch_bounds__(3 * H) gru_small_kernel(const float* __restric
   }
   if (tid < H) h[tid] = 0.f;
   const float bn = tid >= 2 * H ? b_hn[dir * H + tid - 2 * H] : 0.f;
-  const float* xrow = xg + (((int64_t)b * S) * 2 + dir) * G;  // + t*2*G
+  const float* xrow = xg + (((int64_t)b * S_full) * 2 + dir) * G;  // + t*2*G
   const int64_t xstride = 2 * G;
   // Input pre-activations: thread tid < H (r row of unit tid) carries x_r and x_n of its unit, thread H + u (z row)
   // carries x_z, so the r and z sigmoids of a unit run on two threads side by side.  The values of the current and
@@ -84,7 +97,7 @@ __global__ void __launch_bounds__(3 * H) gru_small_kernel(const float* __restric
       const float n = tanhf(xb0 + r * gh[2 * H + tid]);
       const float hn = (1.f - z) * n + z * h[tid];
       h[tid] = hn;
-      const int64_t o = ((int64_t)b * S + t) * (2 * H) + dir * H + tid;
+      const int64_t o = ((int64_t)b * S_full + t) * (2 * H) + dir * H + tid;
       if (out_bf16 == 2)
         ((__half*)out)[o] = __float2half_rn(hn);
       else if (out_bf16)
@@ -100,18 +113,20 @@ __global__ void __launch_bounds__(3 * H) gru_small_kernel(const float* __restric
 
 template <int H>
 static int launch_gru_small(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S,
-                            int out_bf16, cudaStream_t s) {
+                            int out_bf16, cudaStream_t s, const int32_t* lens) {
   constexpr int G = 3 * H;
-  gru_small_kernel<H><<<dim3(B, 2), G, 0, s>>>(xg, w_hh, b_hn, out, S, out_bf16);
+  gru_small_kernel<H><<<dim3(B, 2), G, 0, s>>>(xg, w_hh, b_hn, out, S, out_bf16, lens);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }
 
 int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
-                int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off);  // rnn_tc.cu
+                int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens,
+                float pad_value);  // rnn_tc.cu
 
 int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
-              int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off) {
+              int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens,
+              float pad_value) {
   FTB_REQUIRE(xg && w_hh && out && B > 0 && S > 0, FTB_ERR_INVALID, "rnn_bidir: bad arguments");
   FTB_REQUIRE(ldo == 0 || ldo >= 2 * H + (lo_off ? 2 * H : 0), FTB_ERR_INVALID, "rnn_bidir: output row stride %d too small", ldo);
   FTB_REQUIRE(lo_off == 0 || lo_off >= 2 * H, FTB_ERR_INVALID, "rnn_bidir: the remainder part must not overlap the 2H main part");
@@ -119,12 +134,12 @@ int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, 
   ProfScope prof(is_lstm ? FAM_RNN_LSTM : (H >= 256 ? FAM_RNN_GRU : FAM_RNN_SMALL), 2.0 * 2 * B * S * (double)G * H * H,
                  (double)B * S * 2 * G * H * 4 + (double)B * S * 2 * H * (out_bf16 ? (lo_off ? 4 : 2) : 4), s);
   if (!is_lstm && (H == 64 || H == 128)) {
-    FTB_REQUIRE(!xrow && !lo_off && (ldo == 0 || ldo == 2 * H), FTB_ERR_UNSUPPORTED,
+    FTB_REQUIRE(!xrow && !lo_off && (ldo == 0 || ldo == 2 * H) && pad_value == 0.f, FTB_ERR_UNSUPPORTED,
                 "rnn_bidir: the small-GRU kernel writes plain (B,S,2H) rows");
-    return H == 64 ? launch_gru_small<64>(xg, w_hh, b_hn, out, B, S, out_bf16, s)
-                   : launch_gru_small<128>(xg, w_hh, b_hn, out, B, S, out_bf16, s);
+    return H == 64 ? launch_gru_small<64>(xg, w_hh, b_hn, out, B, S, out_bf16, s, lens)
+                   : launch_gru_small<128>(xg, w_hh, b_hn, out, B, S, out_bf16, s, lens);
   }
-  return rnn_cluster(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, s, xrow, ldo, lo_off);
+  return rnn_cluster(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, s, xrow, ldo, lo_off, lens, pad_value);
 }
 
 }  // namespace ftb
@@ -137,4 +152,11 @@ extern "C" int ftb_rnn_bidir(const float* xg, const float* w_hh, const float* b_
 extern "C" int ftb_rnn_bidir_rows(const float* xg, const int32_t* xrow, const float* w_hh, const float* b_hn, void* out,
                                   int B, int S, int H, int is_lstm, int out_kind, int ldo, int lo_off, void* stream) {
   return ftb::rnn_bidir(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_kind, (cudaStream_t)stream, xrow, ldo, lo_off);
+}
+
+extern "C" int ftb_rnn_bidir_packed(const float* xg, const int32_t* lens, float pad_value, const float* w_hh,
+                                    const float* b_hn, void* out, int B, int S, int H, int is_lstm, int out_kind,
+                                    void* stream) {
+  FTB_REQUIRE(lens, FTB_ERR_INVALID, "ftb_rnn_bidir_packed: lens is required");
+  return ftb::rnn_bidir(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_kind, (cudaStream_t)stream, nullptr, 0, 0, lens, pad_value);
 }

@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
                   const float* __restrict__ b_hn,  // (2,H) GRU only
                   void* __restrict__ out, int B, int S, int out_bf16, int bc,
                   const int32_t* __restrict__ xrow,  // optional (B,S): row of xg that feeds (b, t) -- see rnn_bidir_rows
-                  int ldo, int lo_off) {             // out row stride; > 0: second 16-bit part h - hi at this offset
+                  int ldo, int lo_off,               // out row stride; > 0: second 16-bit part h - hi at this offset
+                  const int32_t* __restrict__ lens,  // optional (B): row b is a sequence of lens[b] <= S steps
+                  float pad_value) {                 // ... and its output beyond that is pad_value (packed sequences)
   using C = RtCfg<G, H, CL, NCOLS, CW, UC>;
   using namespace rt;
   constexpr int THREADS = C::THREADS, WARPS = C::WARPS, PRE_LD = C::PRE_LD, PPT = C::PPT, KSPLIT = C::KSPLIT;
@@ -231,9 +233,12 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
   // The row of step s + 1 is fetched during step s, its index one step earlier still.
   const float* xbase = xg + (int64_t)dir * (G * H) + hu;
   const int32_t* ip[PPT];  // index of the step after next
-  int64_t rnext[PPT];      // xg row of the NEXT step
+  int32_t rnext[PPT];      // xg row of the NEXT step (kept as the raw loaded word: a GPU thread issues in order, so any
+                           // arithmetic on it right after the load would stall the warp for the load's latency)
   int64_t op[PPT];         // output element of the CURRENT step
   bool ok[PPT];
+  int len[PPT];            // valid steps of the utterance: beyond it the state is zero and the output pad_value, so the
+                           // reverse direction starts at the last valid step with a zero state (pack_padded_sequence)
   const int tstep = dir ? -1 : 1;
   const int64_t ostep = (int64_t)tstep * ldo;
   const float bhn = (G == 3) ? b_hn[dir * H + hu] : 0.f;
@@ -246,12 +251,13 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
     cst[e] = 0.f;
     hprev[e] = 0.f;
     const int64_t b = b0 + (ok[e] ? n : 0);
+    len[e] = lens ? __ldg(lens + b) : S;
     const int64_t f0 = b * S + t_first;
     op[e] = f0 * ldo + dir * H + hu;
-    const int64_t r0 = xrow ? (int64_t)__ldg(xrow + f0) : f0;
+    const int32_t r0 = xrow ? __ldg(xrow + f0) : (int32_t)f0;
 #pragma unroll
-    for (int g = 0; g < G; ++g) xcur[e][g] = ok[e] ? __ldg(xbase + r0 * (2 * G * H) + g * H) : 0.f;
-    rnext[e] = (S > 1) ? (xrow ? (int64_t)__ldg(xrow + f0 + tstep) : f0 + tstep) : r0;
+    for (int g = 0; g < G; ++g) xcur[e][g] = ok[e] ? __ldg(xbase + (int64_t)r0 * (2 * G * H) + g * H) : 0.f;
+    rnext[e] = (S > 1) ? (xrow ? __ldg(xrow + f0 + tstep) : (int32_t)(f0 + tstep)) : r0;
     ip[e] = xrow + f0 + 2 * tstep;
   }
   // own slice cell of utterance n: rank*SL + (n/8)*512 + q*128 + (n%8)*16 + (unit%8)*2
@@ -271,16 +277,20 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
 
   for (int s = 0; s < S; ++s) {
     const uint32_t nbuf = (s & 1) ^ 1;
+    const int t = dir ? S - 1 - s : s;
     // next step's input pre-activations: in flight while this step computes
     float xnext[PPT][G];
     if (s + 1 < S) {
 #pragma unroll
       for (int e = 0; e < PPT; ++e) {
-        const float* xr = xbase + rnext[e] * (2 * G * H);
+        const float* xr = xbase + (int64_t)rnext[e] * (2 * G * H);
 #pragma unroll
         for (int g = 0; g < G; ++g) xnext[e][g] = ok[e] ? __ldg(xr + g * H) : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < PPT; ++e) {
         if (xrow) {
-          if (s + 2 < S) rnext[e] = (int64_t)__ldg(ip[e]);
+          if (s + 2 < S) rnext[e] = __ldg(ip[e]);
           ip[e] += tstep;
         } else {
           rnext[e] += tstep;
@@ -345,8 +355,10 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
         const float gn = tanh_mufu(xcur[e][2] + gr * (p[2][e] + bhn));
         hn[e] = (1.f - gz) * gn + gz * hprev[e];
       }
+      const bool live = t < len[e];
+      if (!live) hn[e] = 0.f, cst[e] = 0.f;
       hprev[e] = hn[e];
-      if (ok[e]) store_h(out, op[e], lo_off, out_bf16, hn[e]);
+      if (ok[e]) store_h(out, op[e], lo_off, out_bf16, live ? hn[e] : pad_value);
       op[e] += ostep;
 #pragma unroll
       for (int g = 0; g < G; ++g) xcur[e][g] = xnext[e][g];
@@ -416,7 +428,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
 template <int G, int H, int CL, int NCOLS, int CW, int UC>
 static int launch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
                          int bc, cudaStream_t s, int* max_clusters, const int32_t* xrow = nullptr, int ldo = 0,
-                         int lo_off = 0) {
+                         int lo_off = 0, const int32_t* lens = nullptr, float pad_value = 0.f) {
   using C = RtCfg<G, H, CL, NCOLS, CW, UC>;
   auto kern = rnn_tc_kernel<G, H, CL, NCOLS, CW, UC>;
   static bool configured = false;
@@ -445,332 +457,7 @@ static int launch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, 
   }
   FTB_REQUIRE(max_active > 0, FTB_ERR_UNSUPPORTED, "a cluster of %d CTAs cannot be scheduled on this device", CL);
   if (ldo <= 0) ldo = 2 * H;
-  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16, bc, xrow, ldo, lo_off));
-  count_launch();
-  return FTB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Two-sub-chunk ("ping-pong") variant of the decoder LSTM step loop: 64 utterances per cluster.
-//
-// A step of one chunk is a chain  gate maths -> DSMEM all-gather of h_t -> 32 MMAs -> TMEM read -> gate maths ...  in
-// which the gate warps idle during the exchange and the MMAs, and the tensor pipe idles during the gate maths.  A
-// tcgen05.mma with a 128 x 16 A tile costs the pipe ~60 clocks whether N is 16 or 64, so the pipe time of a step is
-// ~32 x 60 clocks per B operand.  This kernel gives a cluster TWO independent sub-chunks of <= 32 utterances each
-// and dedicated MMA-issuing warps, so the gate maths and hand-off of one sub-chunk run in the shadow of the other's
-// MMAs and the cluster's 16 SMs carry 64 utterances instead of 32.  To make room for four 32 KB B operands
-// (2 sub-chunks x 2 buffers) the W_hh slice lives in TENSOR MEMORY (A operand from TMEM, 128 lanes x 256 columns):
-//   warps 0..15  gate warps: for c in {0, 1}: wait d_full[c] -> tcgen05.ld -> gate maths -> h_t(c) into the own slice
-//                of the next B operand -> bar.sync (gate warps only) -> one bulk push per peer -> arrive own_ready[c];
-//                they never wait for a peer;
-//   warps 16..19 MMA issuers (lane 0): issuer w owns ring slices w, w+4, w+8, w+12 of both sub-chunks and its own TMEM
-//                accumulator per sub-chunk (fixed order inside -> bit-reproducible); it issues the 2 MMAs (M128 N32 K16)
-//                of a slice as soon as that slice has landed and commits to d_full[c].
-// Optional per-utterance lengths give the packed-sequence semantics of the reference's teacher-forced forward()
-// (models/forward_tacotron.py:225-231): state stays zero and the output is `pad_value` wherever t >= lens[b].
-namespace pp {
-constexpr int G = 4, H = 512, CL = 16, HC = H / CL, NS = 32, CW = 8, PPT = CW / 4, GW = 16, IW = 4;
-constexpr int THREADS = 32 * (GW + IW);
-constexpr uint32_t SL = (NS / 8) * 512;   // bytes of one CTA's slice of one sub-chunk: 32 units x 32 utterances
-constexpr uint32_t HB_BYTES = CL * SL;    // one B operand: 32 utterances x 512 units bf16
-constexpr int PRE_LD = CW + 4;
-constexpr size_t OFF_PRE = (size_t)4 * HB_BYTES;  // hB[c][buf] first
-constexpr size_t OFF_BAR = OFF_PRE + sizeof(float) * GW * 32 * PRE_LD;
-constexpr int NBAR = 4 * CL + 4;          // h_full[c][buf][slice], d_full[c], own_ready[c]
-constexpr size_t SMEM = OFF_BAR + 8 * NBAR + 16;
-constexpr uint32_t WCOLS = H / 2;         // TMEM columns of the W slice (two 16-bit weights per column)
-constexpr uint32_t TMEM_COLS = 512;       // W slice + 2 sub-chunks x IW accumulators x NS columns
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-static_assert(WCOLS + 2 * IW * NS <= TMEM_COLS && SMEM <= 227 * 1024, "TMEM / shared memory layout");
-}  // namespace pp
-
-__global__ void __launch_bounds__(pp::THREADS, 1)
-    lstm_pp_kernel(const float* __restrict__ xg,    // (B,S,2,4H)
-                   const float* __restrict__ w_hh,  // (2,4H,H)
-                   void* __restrict__ out, const int* __restrict__ lens, float pad_value, int B, int S, int out_bf16,
-                   const int32_t* __restrict__ xrow, int ldo, int lo_off) {  // as in rnn_tc_kernel
-  using namespace pp;
-  using namespace rt;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  float* pre_all = reinterpret_cast<float*>(smem_raw + OFF_PRE);
-  const uint32_t hb0 = smem_u32(smem_raw);                // hB[c][buf] at hb0 + (2c + buf) * HB_BYTES
-  const uint32_t bar0 = smem_u32(smem_raw + OFF_BAR);     // h_full[c][buf][slice] at bar0 + 8*((2c + buf)*CL + slice)
-  const uint32_t dfull0 = bar0 + 8 * 4 * CL, own0 = dfull0 + 16;
-  const bool f16op = out_bf16 == 2;
-  const uint32_t idesc = f16op ? (IDESC & ~((1u << 7) | (1u << 10))) : IDESC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BAR + 8 * NBAR);
-
-  cg::cluster_group cluster = cg::this_cluster();
-  const uint32_t rank = cluster.block_rank();
-  const int b0 = blockIdx.y * 2 * NS, dir = blockIdx.z;
-  const int nvalid = min(2 * NS, B - b0);
-  // the utterances of a cluster are split evenly (in groups of 8) over the two sub-chunks
-  const int n_c0 = min(min(NS, ((nvalid + 15) >> 4) << 3), nvalid), n_c1 = nvalid - n_c0;
-  const int nch = n_c1 > 0 ? 2 : 1;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  for (int i = tid; i < (int)(OFF_PRE / 16); i += THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) {
-    for (int i = 0; i < NBAR; ++i)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"((i >= 4 * CL && i < 4 * CL + 2) ? IW : 1));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc_base = tmem_base + WCOLS;
-
-  // gate-warp geometry (warps 0..15): TMEM lane quarter q, accumulator row 32q + lane = (unit 8q + lane/4, gate lane%4);
-  // column group cgp = 8 utterances of the sub-chunk
-  const int q = warp & 3, cgp = (warp >> 2) & 3;
-  const int u_local = 8 * q + (lane >> 2), sub = lane & 3;
-  const int hu = (int)rank * HC + u_local;
-  if (warp < GW) {  // ---- W_hh slice -> TMEM: lane = gate row, column k/2 holds weights k, k+1; the 4 warps of a quarter split K
-    const float* wrow = w_hh + ((int64_t)(dir * G + sub) * H + hu) * H;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int PER = (int)WCOLS / 8 / 4;  // 8-column groups per warp
-    for (int c8 = cgp * PER; c8 < (cgp + 1) * PER; ++c8) {
-      uint32_t r[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 v = *reinterpret_cast<const float4*>(wrow + c8 * 16 + i * 4);
-        r[2 * i] = f16op ? pack_f16x2(v.x, v.y) : pack_bf16x2(v.x, v.y);
-        r[2 * i + 1] = f16op ? pack_f16x2(v.z, v.w) : pack_bf16x2(v.z, v.w);
-      }
-      tmem_st8(trow + c8 * 8, r);
-    }
-    // step 0 reads the accumulators without any MMA (h_{-1} = 0): clear this warp's windows of all of them
-    const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int a = 0; a < 2 * IW; ++a) tmem_st8(acc_base + ((uint32_t)(q * 32) << 16) + a * NS + cgp * CW, z);
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  cluster.sync();  // every CTA of the cluster is resident, its barriers initialised and h buffers zeroed
-
-  const uint32_t bytes_c[2] = {(uint32_t)((n_c0 + 7) >> 3) * 512u, (uint32_t)((n_c1 + 7) >> 3) * 512u};
-  if (warp >= GW && lane == 0) {  // issuers arm the first use of the slice barriers they will wait on
-    const int w = warp - GW;
-    for (int c = 0; c < nch; ++c)
-      for (int i = w; i < CL; i += IW)
-        if (i > 0)
-          for (int bf = 0; bf < 2; ++bf)
-            if (S > 1 + (bf ^ 1))
-              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * ((2 * c + bf) * CL + (rank + i) % CL)),
-                           "r"(bytes_c[c])
-                           : "memory");
-  }
-  cluster.sync();  // all barriers armed before any peer can push
-  // developer tool (scripts/lstm_pp_timing.py): clock stamps of the first 64 steps, 16 slots per step
-  long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? g_rnn_dbg : nullptr;
-#define PP_STAMP(cond, slot)                                              \
-  do {                                                                    \
-    if (dbg && (cond) && s < 64) dbg[s * 16 + (slot)] = clock64();        \
-  } while (0)
-
-  if (warp >= GW) {
-    if (lane == 0) {  // ================= MMA issuer =================
-      const int w = warp - GW;
-      for (int s = 0; s + 1 < S; ++s) {
-        const uint32_t nbuf = (s & 1) ^ 1;
-        for (int c = 0; c < nch; ++c) {
-          const uint32_t hbn = hb0 + (2 * c + nbuf) * HB_BYTES;
-          const uint32_t d_acc = acc_base + (c * IW + w) * NS;
-          // the gate warps have read this step's accumulators and written the own slice: only now may any issuer
-          // overwrite its accumulator (a peer's slice can land before this CTA has even started its gate maths)
-          mbar_wait(own0 + 8 * c, (uint32_t)s & 1);
-          PP_STAMP(w == 0, 10 + 3 * c);
-          for (int i = w; i < CL; i += IW) {
-            const uint32_t r = (rank + i) % CL;
-            if (i > 0) {
-              const uint32_t hbar = bar0 + 8 * ((2 * c + nbuf) * CL + r);
-              mbar_wait(hbar, ((uint32_t)s >> 1) & 1);
-              if (s + 3 < S)  // re-arm for h_{t+2}: it cannot be sent before this CTA has sent h_{t+1}
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hbar), "r"(bytes_c[c]) : "memory");
-            }
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {  // k-step ks = 16 hidden units: A = W columns ks*8.., B = slice r, half j
-              const uint32_t ks = 2 * r + j;
-              umma_ts_bf16(d_acc, tmem_base + ks * 8, bdesc_kmajor(hbn + r * SL + j * 256, 512), idesc, (i >= IW || j > 0) ? 1u : 0u);
-            }
-          }
-          PP_STAMP(w == 0, 11 + 3 * c);
-          umma_commit(dfull0 + 8 * c);
-          PP_STAMP(w == 0, 12 + 3 * c);
-        }
-      }
-    }
-    __syncwarp();
-  } else {  // ================= gate warps =================
-    float* pre = pre_all + warp * 32 * PRE_LD;
-    float cst[2][PPT], xcur[2][PPT][G];
-    const float* xbase = xg + (int64_t)dir * (G * H) + hu;
-    const int32_t* ip[2][PPT];
-    int64_t rnext[2][PPT];
-    int64_t op[2][PPT];
-    bool ok[2][PPT];
-    int len[2][PPT];
-    uint32_t cell[2];
-    const int tstep = dir ? -1 : 1;
-    const int64_t ostep = (int64_t)tstep * ldo;
-    const int t_first = dir ? S - 1 : 0;
-    const int n0 = cgp * CW + sub * PPT;  // first utterance (of the sub-chunk) of this thread
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-#pragma unroll
-      for (int e = 0; e < PPT; ++e) {
-        const int n = n0 + e;
-        ok[c][e] = n < (c ? n_c1 : n_c0);
-        cst[c][e] = 0.f;
-        const int64_t b = b0 + (ok[c][e] ? (c ? n_c0 : 0) + n : 0);
-        len[c][e] = lens ? __ldg(lens + b) : S;
-        const int64_t f0 = b * S + t_first;
-        op[c][e] = f0 * ldo + dir * H + hu;
-        const int64_t r0 = xrow ? (int64_t)__ldg(xrow + f0) : f0;
-#pragma unroll
-        for (int g = 0; g < G; ++g) xcur[c][e][g] = ok[c][e] ? __ldg(xbase + r0 * (2 * G * H) + g * H) : 0.f;
-        rnext[c][e] = (S > 1) ? (xrow ? (int64_t)__ldg(xrow + f0 + tstep) : f0 + tstep) : r0;
-        ip[c][e] = xrow + f0 + 2 * tstep;
-      }
-      cell[c] = rank * SL + (uint32_t)(n0 >> 3) * 512u + (uint32_t)q * 128u + (uint32_t)(n0 & 7) * 16u + (lane >> 2) * 2u;
-    }
-    for (int s = 0; s < S; ++s) {
-      const uint32_t nbuf = (s & 1) ^ 1;
-      const int t = dir ? S - 1 - s : s;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        if (c >= nch) break;
-        float xnext[PPT][G];
-        if (s + 1 < S) {
-#pragma unroll
-          for (int e = 0; e < PPT; ++e) {
-            const float* xr = xbase + rnext[c][e] * (2 * G * H);
-#pragma unroll
-            for (int g = 0; g < G; ++g) xnext[e][g] = ok[c][e] ? __ldg(xr + g * H) : 0.f;
-            if (xrow) {
-              if (s + 2 < S) rnext[c][e] = (int64_t)__ldg(ip[c][e]);
-              ip[c][e] += tstep;
-            } else {
-              rnext[c][e] += tstep;
-            }
-          }
-        }
-        if (s > 0) mbar_wait(dfull0 + 8 * c, (s - 1) & 1);  // the MMAs of this step of this sub-chunk have retired
-        PP_STAMP(tid == 0, 5 * c);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float acc[CW];
-        {
-          uint32_t r[IW][CW];
-          const uint32_t tacc = acc_base + ((uint32_t)(q * 32) << 16) + c * IW * NS + cgp * CW;
-#pragma unroll
-          for (int a = 0; a < IW; ++a) tmem_ld8(tacc + a * NS, r[a]);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < CW; ++i) {
-            float v = __uint_as_float(r[0][i]);
-#pragma unroll
-            for (int a = 1; a < IW; ++a) v += __uint_as_float(r[a][i]);
-            acc[i] = v;
-          }
-        }
-        PP_STAMP(tid == 0, 5 * c + 1);
-        // regroup: row (unit, gate) x 8 utterances  ->  thread (unit, 2 utterances) x 4 gates
-        *reinterpret_cast<float4*>(pre + lane * PRE_LD) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(pre + lane * PRE_LD + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        __syncwarp();
-        float pg[G][PPT];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const float2 v = *reinterpret_cast<const float2*>(pre + ((lane & ~3) + g) * PRE_LD + sub * PPT);
-          pg[g][0] = v.x, pg[g][1] = v.y;
-        }
-        __syncwarp();
-        float hn[PPT];
-#pragma unroll
-        for (int e = 0; e < PPT; ++e) {
-          const float gi = sigmoid_mufu(xcur[c][e][0] + pg[0][e]);
-          const float gf = sigmoid_mufu(xcur[c][e][1] + pg[1][e]);
-          const float gg = tanh_mufu(xcur[c][e][2] + pg[2][e]);
-          const float go = sigmoid_mufu(xcur[c][e][3] + pg[3][e]);
-          const bool live = t < len[c][e];
-          cst[c][e] = live ? gf * cst[c][e] + gi * gg : 0.f;
-          hn[e] = live ? go * tanh_mufu(cst[c][e]) : 0.f;
-          if (ok[c][e]) store_h(out, op[c][e], lo_off, out_bf16, live ? hn[e] : pad_value);
-          op[c][e] += ostep;
-#pragma unroll
-          for (int g = 0; g < G; ++g) xcur[c][e][g] = xnext[e][g];
-        }
-        if (s + 1 < S) {
-          unsigned char* hb_next = smem_raw + (2 * c + nbuf) * HB_BYTES;
-#pragma unroll
-          for (int e = 0; e < PPT; ++e)
-            if (ok[c][e])
-              *reinterpret_cast<unsigned short*>(hb_next + cell[c] + e * 16) =
-                  f16op ? __half_as_ushort(__float2half_rn(hn[e])) : __bfloat16_as_ushort(__float2bfloat16_rn(hn[e]));
-          PP_STAMP(tid == 0, 5 * c + 2);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to UMMA / bulk copy
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          asm volatile("bar.sync 1, %0;" ::"r"(32 * GW) : "memory");    // gate warps only
-          PP_STAMP(tid == 0, 5 * c + 3);
-          if (lane == 0) {
-            const uint32_t hbn = hb0 + (2 * c + nbuf) * HB_BYTES, src = hbn + rank * SL;
-            if (warp < CL - 1) {  // one bulk copy per peer; barrier [c][nbuf][rank] of the peer tracks this slice
-              const uint32_t peer = (rank + 1 + warp) % CL;
-              bulk_push(mapa(src, peer), src, bytes_c[c], mapa(bar0 + 8 * ((2 * c + nbuf) * CL + rank), peer));
-            } else {
-              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(own0 + 8 * c) : "memory");
-            }
-          }
-          PP_STAMP(tid == 0, 5 * c + 4);
-          __syncwarp();
-        }
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pp::TMEM_COLS) : "memory");
-  }
-  cluster.sync();  // no CTA exits while a peer may still address its shared memory
-}
-#undef PP_STAMP
-
-static int launch_lstm_pp(const float* xg, const float* w_hh, void* out, const int* lens, float pad_value, int B, int S,
-                          int out_bf16, cudaStream_t s, const int32_t* xrow = nullptr, int ldo = 0, int lo_off = 0) {
-  static bool configured = false;
-  static int max_active = 0;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(pp::CL, cdiv(B, 2 * pp::NS), 2);
-  cfg.blockDim = dim3(pp::THREADS);
-  cfg.dynamicSmemBytes = pp::SMEM;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = pp::CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (!configured) {
-    FTB_CHECK_CUDA(cudaFuncSetAttribute(lstm_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp::SMEM));
-    FTB_CHECK_CUDA(cudaFuncSetAttribute(lstm_pp_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    FTB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_active, lstm_pp_kernel, &cfg));
-    configured = true;
-  }
-  FTB_REQUIRE(max_active > 0, FTB_ERR_UNSUPPORTED, "a cluster of %d CTAs cannot be scheduled on this device", pp::CL);
-  if (ldo <= 0) ldo = 2 * pp::H;
-  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pp_kernel, xg, w_hh, out, lens, pad_value, B, S, out_bf16, xrow, ldo, lo_off));
+  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16, bc, xrow, ldo, lo_off, lens, pad_value));
   count_launch();
   return FTB_OK;
 }
@@ -785,42 +472,32 @@ static std::atomic<int> g_lstm_min_chunk{getenv("FTB_LSTM_MIN_CHUNK") ? atoi(get
 
 template <int G, int H, int CL>
 static int dispatch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
-                           cudaStream_t s, const int32_t* xrow, int ldo, int lo_off) {
+                           cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens, float pad_value) {
   int m8 = 0, m16 = 0, m32 = 0;
   FTB_TRY((launch_rnn_tc<G, H, CL, 16, 4, 8>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 8, s, &m8)));
   FTB_TRY((launch_rnn_tc<G, H, CL, 16, 8, 16>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 16, s, &m16)));
   FTB_TRY((launch_rnn_tc<G, H, CL, 32, 8, 32>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 32, s, &m32)));
   // 8 utterances: only the first column group of a 16-wide MMA carries data, 1 pair per gate thread
-  if (2 * cdiv(B, 8) <= m8) return launch_rnn_tc<G, H, CL, 16, 4, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, 8, s, nullptr, xrow, ldo, lo_off);
-  if (2 * cdiv(B, 16) <= m16) return launch_rnn_tc<G, H, CL, 16, 8, 16>(xg, w_hh, b_hn, out, B, S, out_bf16, 16, s, nullptr, xrow, ldo, lo_off);
+  if (2 * cdiv(B, 8) <= m8) return launch_rnn_tc<G, H, CL, 16, 4, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, 8, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
+  if (2 * cdiv(B, 16) <= m16) return launch_rnn_tc<G, H, CL, 16, 8, 16>(xg, w_hh, b_hn, out, B, S, out_bf16, 16, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
   const int min_chunk = g_lstm_min_chunk.load(std::memory_order_relaxed);
-  if (min_chunk <= 24 && 2 * cdiv(B, 24) <= m32) return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 24, s, nullptr, xrow, ldo, lo_off);
-  return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 32, s, nullptr, xrow, ldo, lo_off);
-}
-
-// Decoder LSTM over packed sequences (pack_padded_sequence semantics): rows stop at lens[b]; beyond it the state is
-// zero and the output is pad_value.  xg (B,S,2,4H) f32; out (B,S,2H).
-int lstm512_packed(const float* xg, const float* w_hh, void* out, const int* lens, float pad_value, int B, int S,
-                   int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off) {
-  return launch_lstm_pp(xg, w_hh, out, lens, pad_value, B, S, out_bf16, s, xrow, ldo, lo_off);
+  if (min_chunk <= 24 && 2 * cdiv(B, 24) <= m32) return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 24, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
+  return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 32, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
 }
 
 int rnn_gru256_mma(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
-                   cudaStream_t s, int ldo, int lo_off);  // rnn_mma.cu
+                   cudaStream_t s, int ldo, int lo_off, const int32_t* lens);  // rnn_mma.cu
 
+// lens (optional, (B) int32): row b is a sequence of lens[b] steps (pack_padded_sequence semantics): state zero and output
+// pad_value beyond it, the reverse direction starts at its last valid step.
 int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
-                int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off) {
+                int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens, float pad_value) {
   FTB_REQUIRE(!lo_off || out_bf16, FTB_ERR_INVALID, "rnn_bidir: the hi/lo output pair exists for 16-bit outputs only");
-  if (is_lstm && H == 512) {
-    // FTB_LSTM_PP=1: the two-sub-chunk kernel (64 utterances per cluster, W_hh in TMEM).  It holds half the SMs of
-    // the default but its step is 1.8x longer (the tensor pipe serialises the dependent accumulations of a chain:
-    // measured ~120 clk per MMA with 4 accumulators per sub-chunk), so it only serves the packed-sequence path.
-    static const int use_pp = getenv("FTB_LSTM_PP") ? atoi(getenv("FTB_LSTM_PP")) : 0;
-    if (use_pp && B > 16) return launch_lstm_pp(xg, w_hh, out, nullptr, 0.f, B, S, out_bf16, s, xrow, ldo, lo_off);
-    return dispatch_rnn_tc<4, 512, 16>(xg, w_hh, nullptr, out, B, S, out_bf16, s, xrow, ldo, lo_off);
-  }
+  FTB_REQUIRE((int64_t)B * S < (1ll << 31), FTB_ERR_INVALID, "rnn_bidir: B*S overflows the int32 row index");
+  if (is_lstm && H == 512) return dispatch_rnn_tc<4, 512, 16>(xg, w_hh, nullptr, out, B, S, out_bf16, s, xrow, ldo, lo_off, lens, pad_value);
   FTB_REQUIRE(!xrow, FTB_ERR_UNSUPPORTED, "rnn_bidir: the row-indexed input exists for the H=512 LSTM only");
-  if (!is_lstm && H == 256) return rnn_gru256_mma(xg, w_hh, b_hn, out, B, S, out_bf16, s, ldo, lo_off);
+  FTB_REQUIRE(pad_value == 0.f, FTB_ERR_UNSUPPORTED, "rnn_bidir: a non-zero pad value exists for the H=512 LSTM only");
+  if (!is_lstm && H == 256) return rnn_gru256_mma(xg, w_hh, b_hn, out, B, S, out_bf16, s, ldo, lo_off, lens);
   set_error("rnn_bidir: no kernel for %s with H=%d (built: GRU 64/128/256, LSTM 512)", is_lstm ? "LSTM" : "GRU", H);
   return FTB_ERR_UNSUPPORTED;
 }

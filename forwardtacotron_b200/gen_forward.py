@@ -6,8 +6,11 @@ HiFi-GAN :124).  WaveRNN / Griffin-Lim synthesis and the espeak cleaner are outs
         --alpha 1.0 --amp 1.0 --format npy [--exact]
 
 The reference runs one sentence at a time.  Here sentences are bucketed by length and run as padded batches
-(``utils/batching.py``); with the reference's no-mask semantics a padded batch is not identical to the per-sentence
-runs, so ``--exact`` keeps B = 1 per call and reproduces upstream output file for file.
+(``utils/batching.py``).  ForwardTacotron batches carry every row's own length into the kernels
+(``ForwardTacotron.generate_ragged``), so each sentence gets exactly the mel of its own one-sentence ``generate`` call
+-- upstream's output, file for file, at batched throughput.  ``--no-mask`` runs the reference's no-mask arithmetic on
+the padded batch instead (pad tokens are ordinary symbols there, SURVEY 7; rows are cut after their real tokens' frames);
+``--exact`` forces one sentence per call (the only exact mode for FastPitch, which has no ragged path).
 """
 from __future__ import annotations
 
@@ -24,7 +27,7 @@ from .utils.text import Tokenizer
 
 
 def synthesize_texts(model, texts: List[str], alpha: float = 1.0, amp: float = 1.0, exact: bool = False,
-                     max_tokens: int = 16384) -> List[torch.Tensor]:
+                     max_tokens: int = 16384, no_mask: bool = False) -> List[torch.Tensor]:
     """phonemised strings -> list of (1, n_mels, L_i) CPU tensors (``gen['mel_post'].cpu()`` of the reference)."""
     tok = Tokenizer()
     utts = [tok(t) for t in texts]
@@ -32,8 +35,9 @@ def synthesize_texts(model, texts: List[str], alpha: float = 1.0, amp: float = 1
         raise ValueError('a sentence has no symbol of the phoneme inventory')
     pf = lambda p: p * amp      # gen_forward.py:103 "simple amplification of pitch"
     ef = lambda e: e            # gen_forward.py:104
+    ragged = hasattr(model, 'generate_ragged') and not no_mask
     mels = batching.synthesize_corpus(model, utts, alpha=alpha, max_tokens=max_tokens, max_batch=1 if exact else 256,
-                                      pitch_function=pf, energy_function=ef)
+                                      exact=ragged, pitch_function=pf, energy_function=ef)
     return [m.unsqueeze(0).cpu() for m in mels]
 
 
@@ -46,6 +50,7 @@ def main(argv=None) -> None:
     ap.add_argument('--amp', type=float, default=1.0, help='pitch amplification')
     ap.add_argument('--format', choices=['mel', 'npy'], default='npy', help='.mel (MelGAN) or .npy (HiFi-GAN)')
     ap.add_argument('--exact', action='store_true', help='one sentence per call, as upstream')
+    ap.add_argument('--no-mask', action='store_true', help="padded batches with the reference's no-mask arithmetic")
     ap.add_argument('--out', default='model_outputs')
     args = ap.parse_args(argv)
 
@@ -56,7 +61,7 @@ def main(argv=None) -> None:
     out = Path(args.out)
     out.mkdir(parents=True, exist_ok=True)
     k = model.get_step() // 1000
-    mels = synthesize_texts(model, texts, args.alpha, args.amp, args.exact)
+    mels = synthesize_texts(model, texts, args.alpha, args.amp, args.exact, no_mask=args.no_mask)
     for i, m in enumerate(mels, 1):
         name = f'{i}_forward_{k}k_alpha{args.alpha}_amp{args.amp}_{"melgan" if args.format == "mel" else "hifigan"}'
         if args.format == 'mel':

@@ -111,8 +111,15 @@ class ForwardTacotron(NativeModel):
         return self._get_workspace(n, device)
 
     # ------------------------------------------------------------------ stages
-    def predict(self, x: torch.Tensor, alpha: float = 1.0):
-        """Stage A -> (dur (B,T), pitch (B,1,T), energy (B,1,T)), fallback applied."""
+    def _check_lengths(self, x: torch.Tensor, lengths) -> torch.Tensor:
+        lens = torch.as_tensor(lengths).to(device=x.device, dtype=torch.int32).contiguous()
+        if lens.shape != (x.shape[0],):
+            raise TypeError('lengths must have one entry per row of x')
+        return lens
+
+    def predict(self, x: torch.Tensor, alpha: float = 1.0, lengths=None):
+        """Stage A -> (dur (B,T), pitch (B,1,T), energy (B,1,T)), fallback applied.  ``lengths`` (B,) token counts:
+        ragged batch, every row computed as if alone, outputs zero beyond its length (see ``generate_ragged``)."""
         x = self._check_tokens(x)
         lib, dev = _lib.lib(), x.device
         B, T = x.shape
@@ -122,13 +129,20 @@ class ForwardTacotron(NativeModel):
         pitch = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
         energy = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.ftb_ft_predict(h, _lib.ptr(x), B, T, float(alpha), _lib.ptr(dur), _lib.ptr(pitch),
-                                          _lib.ptr(energy), _lib.ptr(ws), ws.numel(), _lib.current_stream(dev)))
+            if lengths is None:
+                _lib.check(lib.ftb_ft_predict(h, _lib.ptr(x), B, T, float(alpha), _lib.ptr(dur), _lib.ptr(pitch),
+                                              _lib.ptr(energy), _lib.ptr(ws), ws.numel(), _lib.current_stream(dev)))
+            else:
+                lens = self._check_lengths(x, lengths)
+                _lib.check(lib.ftb_ft_predict_ragged(h, _lib.ptr(x), _lib.ptr(lens), B, T, float(alpha), _lib.ptr(dur),
+                                                     _lib.ptr(pitch), _lib.ptr(energy), _lib.ptr(ws), ws.numel(),
+                                                     _lib.current_stream(dev)))
         return dur, pitch, energy
 
     def synthesize(self, x: torch.Tensor, dur_hat: torch.Tensor, pitch_hat: torch.Tensor,
-                   energy_hat: torch.Tensor, mel_post_alloc=None) -> Dict[str, torch.Tensor]:
+                   energy_hat: torch.Tensor, mel_post_alloc=None, lengths=None) -> Dict[str, torch.Tensor]:
         """Stage B == the reference's ``_generate_mel`` (:289-330); clamps ``dur_hat`` in place.
+        ``lengths``: ragged batch (see ``generate_ragged``); frames of row b beyond ``mel_len[b]`` are padding.
 
         ``mel_post_alloc(B, n_mels, L) -> float32 tensor`` (or utils/peer_window.PeerSlot; optional) supplies the memory ``mel_post`` is written to
         by the last GEMM's epilogue.  It may live on ANOTHER GPU of the node (peer-mapped, utils/peer_window.py): the
@@ -141,6 +155,18 @@ class ForwardTacotron(NativeModel):
             raise TypeError('dur_hat must be a contiguous float32 (B, T) tensor')
         pitch_c = pitch_hat.to(device=dev, dtype=torch.float32).reshape(B, T).contiguous()
         energy_c = energy_hat.to(device=dev, dtype=torch.float32).reshape(B, T).contiguous()
+        lens = None
+        if lengths is not None:
+            # the callbacks may have written to the padded positions (e.g. e + 0.1): the conditioning convs of a solo
+            # run see zeros there, and padded tokens must not expand into frames
+            lens = self._check_lengths(x, lengths)
+            if pitch_c.data_ptr() == pitch_hat.data_ptr():
+                pitch_c = pitch_c.clone()
+            if energy_c.data_ptr() == energy_hat.data_ptr():
+                energy_c = energy_c.clone()
+            with torch.cuda.device(dev):
+                for t in (pitch_c, energy_c, dur_hat):
+                    _lib.check(lib.ftb_zero_tail_rows(_lib.ptr(t), B, T, 4, _lib.ptr(lens), _lib.current_stream(dev)))
         cum, total = LengthRegulator.plan(dur_hat)
         L = int(total.max().item())  # D2H: sizes the outputs
         if L <= 0:
@@ -156,31 +182,49 @@ class ForwardTacotron(NativeModel):
                     and tuple(mel_post.shape) == (B, n_mels, L)):
                 raise TypeError('mel_post_alloc must return a contiguous float32 CUDA tensor of shape (B, n_mels, L)')
         with torch.cuda.device(dev):
-            _lib.check(lib.ftb_ft_synthesize(h, _lib.ptr(x), _lib.ptr(cum), _lib.ptr(pitch_c), _lib.ptr(energy_c),
-                                             B, T, L, _lib.ptr(mel), _lib.ptr(mel_post), _lib.ptr(ws), ws.numel(),
-                                             _lib.current_stream(dev)))
+            if lens is None:
+                _lib.check(lib.ftb_ft_synthesize(h, _lib.ptr(x), _lib.ptr(cum), _lib.ptr(pitch_c), _lib.ptr(energy_c),
+                                                 B, T, L, _lib.ptr(mel), _lib.ptr(mel_post), _lib.ptr(ws), ws.numel(),
+                                                 _lib.current_stream(dev)))
+            else:
+                _lib.check(lib.ftb_ft_synthesize_ragged(h, _lib.ptr(x), _lib.ptr(lens), _lib.ptr(cum), _lib.ptr(pitch_c),
+                                                        _lib.ptr(energy_c), _lib.ptr(total), B, T, L, _lib.ptr(mel),
+                                                        _lib.ptr(mel_post), _lib.ptr(ws), ws.numel(),
+                                                        _lib.current_stream(dev)))
         return {'mel': mel, 'mel_post': mel_post, 'dur': dur_hat, 'pitch': pitch_hat, 'energy': energy_hat,
                 'mel_len': total}
 
     def generate(self, x: torch.Tensor, alpha=1.0,
                  pitch_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x,
                  energy_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x,
-                 mel_post_alloc=None) -> Dict[str, torch.Tensor]:
+                 mel_post_alloc=None, lengths=None) -> Dict[str, torch.Tensor]:
         self.eval()
         with torch.no_grad():
             x = self._check_tokens(x)
             h = self._get_handle(x.device)
             lib = _lib.lib()
+            lens = None if lengths is None else self._check_lengths(x, lengths)
             # stage B's prenet depends on the tokens only: let stage A start it on a side stream (x is not
             # touched between the two calls)
             _lib.check(lib.ftb_ft_set_option(h, _lib.FTB_OPT_OVERLAP_PRENET, 1))
             try:
-                dur_hat, pitch_hat, energy_hat = self.predict(x, alpha)
+                dur_hat, pitch_hat, energy_hat = self.predict(x, alpha, lens)
                 pitch_hat = pitch_function(pitch_hat)
                 energy_hat = energy_function(energy_hat)
-                return self.synthesize(x, dur_hat, pitch_hat, energy_hat, mel_post_alloc)
+                return self.synthesize(x, dur_hat, pitch_hat, energy_hat, mel_post_alloc, lens)
             finally:
                 _lib.check(lib.ftb_ft_set_option(h, _lib.FTB_OPT_OVERLAP_PRENET, 0))
+
+    def generate_ragged(self, x: torch.Tensor, lengths, alpha=1.0,
+                        pitch_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x,
+                        energy_function: Callable[[torch.Tensor], torch.Tensor] = lambda x: x,
+                        mel_post_alloc=None) -> Dict[str, torch.Tensor]:
+        """The reference's per-sentence loop (gen_forward.py:106-118: one ``generate`` call per sentence, B = 1) as ONE
+        padded batch: ``x`` (B, T) holds ``lengths[b]`` tokens per row (padding id arbitrary).  Row b of every output
+        equals what ``generate(x[b:b+1, :lengths[b]])`` returns for that sentence alone, cut at ``mel_len[b]`` frames
+        (``dur`` / ``pitch`` / ``energy`` at the first ``lengths[b]`` positions).  Plain ``generate`` on a padded batch
+        keeps the reference's no-mask semantics instead: pad tokens are ordinary symbols there."""
+        return self.generate(x, alpha, pitch_function, energy_function, mel_post_alloc, lengths=lengths)
 
     def generate_jit(self, x: torch.Tensor, alpha: float = 1.0, beta: float = 1.0) -> Dict[str, torch.Tensor]:
         """The TorchScript-exported entry point of the reference (models/forward_tacotron.py:270-284): ``generate``

@@ -4,14 +4,21 @@ Host-side logic only (no kernels): length-bucketed padded batches, utterance sha
 ``torch.distributed`` ranks, and the one exchange step of the path — the final gather of the
 variable-length mels.  Utterances are independent, so there is no collective inside ``generate``.
 
-Reference semantics that are kept on purpose: the pad id is 0 = ``'_'`` (utils/text/symbols.py),
-and pad tokens are ordinary symbols for ForwardTacotron — they receive durations and expand into frames.
-Bucketing by length keeps the padding (and that effect) small; it does not remove it.
+Two batch semantics (``synthesize_corpus(exact=...)``):
+
+* ``exact=True`` (default for models that offer ``generate_ragged``, i.e. ForwardTacotron): every row carries its own
+  token count into the kernels — convs see zero padding beyond the row's end, recurrences run over the row's own
+  length, the duration fallback is decided per row — so each utterance gets exactly the mel the reference's
+  one-sentence-per-call loop produces, at batched throughput.
+* ``exact=False``: the reference's no-mask semantics on the padded batch (pad id 0 = ``'_'`` is an ordinary symbol for
+  ForwardTacotron: pad tokens receive durations and would expand into frames).  Rows are cut after the frames
+  of their REAL tokens, so pad frames never reach the output, but the real frames still feel the padding through the
+  bidirectional recurrences.  Kept for FastPitch (whose prenet masks pad keys itself) and for measurements.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 import torch
 
@@ -72,131 +79,153 @@ def shard_for_rank(batches: Sequence[Batch], rank: int, world_size: int) -> List
     return mine
 
 
+def _dist_state(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(group), dist.get_world_size(group)
+    return None, 0, 1
+
+
 def gather_mels(mels: Sequence[torch.Tensor], index: Sequence[int], n_total: int, dst: int = 0,
                 group=None) -> Optional[List[Optional[torch.Tensor]]]:
-    """The path's single collective: collect variable-length ``(n_mels, L_i)`` results of every rank on
-    ``dst`` in the caller's original order.  ``mels[k]`` belongs to utterance ``index[k]``.
+    """The path's single exchange step: collect the variable-length ``(n_mels, L_i)`` results of every rank on ``dst``
+    in the caller's original order.  ``mels[k]`` belongs to utterance ``index[k]``.
 
-    NCCL / gloo have no gatherv, so: all-gather the per-rank (count, max L), then one all-gather of the
-    rank's mels padded to the global max (payload is tiny next to the compute: 80 x L floats per utterance).
-    Returns the list on ``dst`` (``None`` for utterances nobody produced) and ``None`` elsewhere.
-    Works without an initialised process group (single process)."""
-    import torch.distributed as dist
+    NCCL has no gatherv, so: the per-utterance (index, n_mels, L) metadata travels as one small object
+    all-gather, then every rank packs its mels into ONE flat buffer and sends exactly those bytes to ``dst`` — grouped
+    point-to-point (``batch_isend_irecv`` = ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd).  Nothing is padded to
+    a global maximum, no rank but ``dst`` receives anything, and ``dst`` hands out views of the received buffers.
+    Returns the list on ``dst`` (``None`` for utterances nobody produced) and ``None`` elsewhere.  Works without an
+    initialised process group (single process) and with the gloo backend (CPU tests)."""
     if len(mels) != len(index):
         raise ValueError('mels and index must have the same length')
-    if not (dist.is_available() and dist.is_initialized()):
+    dist, rank, world = _dist_state(group)
+    if dist is None:
         out: List[Optional[torch.Tensor]] = [None] * n_total
         for m, i in zip(mels, index):
             out[int(i)] = m
         return out
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    dev = mels[0].device if len(mels) else torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' \
-        else torch.device('cpu')
-    n_mels = mels[0].shape[0] if len(mels) else 0
-    meta = torch.tensor([len(mels), max((m.shape[1] for m in mels), default=0), n_mels], dtype=torch.long, device=dev)
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta, group=group)
-    cnt = max(int(m[0]) for m in metas)
-    lmax = max(int(m[1]) for m in metas)
-    n_mels = max(int(m[2]) for m in metas)
-    if cnt == 0:
-        return [None] * n_total if rank == dst else None
-    payload = torch.zeros((cnt, n_mels, lmax), dtype=torch.float32, device=dev)
-    info = torch.full((cnt, 2), -1, dtype=torch.long, device=dev)  # (utterance index, L)
-    for k, (m, i) in enumerate(zip(mels, index)):
-        payload[k, :, :m.shape[1]] = m
-        info[k, 0], info[k, 1] = int(i), m.shape[1]
-    payloads = [torch.zeros_like(payload) for _ in range(world)]
-    infos = [torch.zeros_like(info) for _ in range(world)]
-    dist.all_gather(payloads, payload, group=group)
-    dist.all_gather(infos, info, group=group)
+    if dist.get_backend(group) == 'nccl':
+        dev = mels[0].device if len(mels) else torch.device('cuda', torch.cuda.current_device())
+    else:
+        dev = torch.device('cpu')
+    info = [(int(i), int(m.shape[0]), int(m.shape[1])) for m, i in zip(mels, index)]  # host-side, no device reads
+    infos: List[Optional[list]] = [None] * world
+    dist.all_gather_object(infos, info, group=group)
+    sizes = [sum(c * l for _, c, l in inf) for inf in infos]
+    flat = torch.cat([m.reshape(-1) for m in mels]).to(device=dev, dtype=torch.float32) if len(mels) \
+        else torch.empty(0, dtype=torch.float32, device=dev)
+    ops, bufs = [], {}
+    if rank == dst:
+        bufs[rank] = flat
+        for r in range(world):
+            if r != dst and sizes[r] > 0:
+                bufs[r] = torch.empty(sizes[r], dtype=torch.float32, device=dev)
+                ops.append(dist.P2POp(dist.irecv, bufs[r], _global_rank(dist, r, group), group))
+    elif sizes[rank] > 0:
+        ops.append(dist.P2POp(dist.isend, flat, _global_rank(dist, dst, group), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     if rank != dst:
         return None
     out = [None] * n_total
-    for p, inf in zip(payloads, infos):
-        for k in range(cnt):
-            i, L = int(inf[k, 0]), int(inf[k, 1])
-            if i >= 0:
-                out[i] = p[k, :, :L].clone()
+    for r, inf in enumerate(infos):
+        if not inf:
+            continue
+        parts = bufs[r].split([c * l for _, c, l in inf])
+        for (i, c, l), p in zip(inf, parts):
+            out[i] = p.view(c, l)
     return out
+
+
+def _global_rank(dist, r: int, group) -> int:
+    return r if group is None else dist.get_global_rank(group, r)
+
+
+def _row_frames(out, batch: Batch, exact: bool) -> List[int]:
+    """Frames each row's REAL tokens produced (one device -> host read per batch)."""
+    if exact:
+        return out['mel_len'].tolist()
+    # no-mask batch: pad tokens expanded into frames at the END of the row; count only what the real tokens produced
+    r = (out['dur'].clamp(min=0) + 0.5).long()
+    pos = torch.arange(r.shape[1], device=r.device)[None, :] < batch.lengths.to(r.device)[:, None]
+    return (r * pos).sum(1).tolist()
 
 
 def synthesize_corpus(model, utterances: Sequence[Sequence[int]], alpha: float = 1.0, max_tokens: int = 16384,
                       max_batch: int = 256, key: str = 'mel_post', device=None, window=None, in_flight: int = 3,
+                      exact: Optional[bool] = None, gather: bool = True,
                       **callbacks) -> Optional[List[Optional[torch.Tensor]]]:
-    """gen_forward.py's loop, batched and sharded: bucket, run ``model.generate`` on this rank's batches, cut every
-    row at its own frame count (``mel_len``) and gather on rank 0.  ``model`` is a ForwardTacotron / FastPitch
-    mirror already on its device.  ``in_flight`` batches are issued round-robin on as many CUDA streams (the model
-    keeps one native lane per stream), so one batch's GEMMs fill the SMs its neighbour's recurrences leave idle.
+    """gen_forward.py's loop, batched and sharded: bucket, run the model on this rank's batches, cut every row at its own
+    frame count and collect on rank 0.  ``model`` is a ForwardTacotron / FastPitch mirror already on its device.
+    ``exact`` (default: True when the model offers ``generate_ragged``): every utterance gets the mel of its own
+    one-sentence ``generate`` call (module docstring).  ``in_flight`` batches are issued round-robin on as many CUDA
+    streams (the model keeps one native lane per stream), so one batch's GEMMs fill the SMs its neighbour's recurrences
+    leave idle.
 
     ``window`` (utils/peer_window.PeerWindow): instead of the NCCL gather, every rank's last GEMM stores ``mel_post``
-    directly into rank 0's memory over NVLink; rank 0 slices views out of the window."""
-    import torch.distributed as dist
-    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    directly into rank 0's memory over NVLink; rank 0 slices the results out of the window.
+    ``gather=False`` skips the exchange and returns this rank's own results (others ``None``): the baseline the cost of
+    the exchange is measured against."""
+    _, rank, world = _dist_state()
     device = device or next(model.parameters()).device
-    mels: List[torch.Tensor] = []
-    index: List[int] = []
-    if window is not None:
-        return _synthesize_into_window(model, utterances, alpha, max_tokens, max_batch, device, window, rank, world,
-                                       callbacks)
+    if exact is None:
+        exact = hasattr(model, 'generate_ragged')
+    if exact and not hasattr(model, 'generate_ragged'):
+        raise ValueError(f'{type(model).__name__} has no generate_ragged(); use exact=False (or max_batch=1)')
     mine = shard_for_rank(bucket_by_length(utterances, max_tokens, max_batch), rank, world)
     on_gpu = torch.device(device).type == 'cuda'
     n_streams = max(1, min(int(in_flight), len(mine))) if on_gpu else 1
     if n_streams > 1:  # the model's own long-lived streams: one native lane (packed weights, workspace) per stream
         streams = (model.lane_streams(device, n_streams) if hasattr(model, 'lane_streams')
                    else [torch.cuda.Stream(device) for _ in range(n_streams)])
-    else:
-        streams = [None]
-    if n_streams > 1:
         here = torch.cuda.current_stream(device)
         for s in streams:
             s.wait_stream(here)
+    else:
+        streams = [None]
+    if window is not None:
+        window.reset()
+    alloc = window.alloc if window is not None else None
+
+    def run(b: Batch):
+        tok = b.tokens.to(device, non_blocking=True)
+        kw = dict(callbacks)
+        if alloc is not None:
+            kw['mel_post_alloc'] = alloc
+        if exact:
+            return model.generate_ragged(tok, b.lengths, alpha, **kw)
+        return model.generate(tok, alpha, **kw)
+
     outs = []
     for k, b in enumerate(mine):
         s = streams[k % n_streams]
         if s is None:
-            outs.append((b, model.generate(b.tokens.to(device), alpha, **callbacks)))
+            outs.append((b, run(b)))
         else:
             with torch.cuda.stream(s):
-                outs.append((b, model.generate(b.tokens.to(device, non_blocking=True), alpha, **callbacks)))
+                outs.append((b, run(b)))
     if n_streams > 1:
         for s in streams:
             torch.cuda.current_stream(device).wait_stream(s)
+    mels: List[torch.Tensor] = []
+    index: List[int] = []
     for b, out in outs:
-        if n_streams > 1:
+        if n_streams > 1 and isinstance(out[key], torch.Tensor):
             out[key].record_stream(torch.cuda.current_stream(device))  # produced on a side stream, consumed here
-        lens = out['mel_len'].tolist()
-        for r, i in enumerate(b.index.tolist()):
-            mels.append(out[key][r, :, :lens[r]])
-            index.append(i)
-    return gather_mels(mels, index, len(utterances))
-
-
-def _synthesize_into_window(model, utterances, alpha, max_tokens, max_batch, device, window, rank, world, callbacks):
-    import torch.distributed as dist
-    batches = bucket_by_length(utterances, max_tokens, max_batch)
-    mine = shard_for_rank(batches, rank, world)
-    steps = torch.tensor([len(mine)], dtype=torch.long, device=device)
-    dist.all_reduce(steps, op=dist.ReduceOp.MAX)
-    window.reset()
-    meta = []  # per produced slot on this rank: (utterance indices, frame counts)
-    for k in range(int(steps)):
-        if k < len(mine):
-            out = model.generate(mine[k].tokens.to(device), alpha, mel_post_alloc=window.alloc, **callbacks)
-            meta.append((mine[k].index.tolist(), out['mel_len'].tolist()))
+        rows, lens = b.index.tolist(), _row_frames(out, b, exact)
+        if window is not None:
+            window.note_rows(out[key], rows, lens)
         else:
-            window.alloc(0, 0, 0)  # keep the collective call sequence aligned
-    metas = [None] * world
-    dist.all_gather_object(metas, meta)
-    slots = window.collect()
-    if slots is None:
-        return None
-    out = [None] * len(utterances)
-    seen = [0] * world
-    for r, t in slots:
-        idx, lens = metas[r][seen[r]]
-        seen[r] += 1
-        for row, (i, L) in enumerate(zip(idx, lens)):
-            out[i] = t[row, :, :L]
-    return out
+            for r, (i, n) in enumerate(zip(rows, lens)):
+                mels.append(out[key][r, :, :n])
+                index.append(i)
+    if window is not None:
+        return window.collect(len(utterances))
+    if not gather:
+        local: List[Optional[torch.Tensor]] = [None] * len(utterances)
+        for m, i in zip(mels, index):
+            local[i] = m
+        return local
+    return gather_mels(mels, index, len(utterances))

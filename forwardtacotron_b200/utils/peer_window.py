@@ -3,9 +3,13 @@
 ``generate`` ends with a GEMM (``post_proj``) whose epilogue writes ``mel_post`` (B, 80, L).  In a sharded run the
 plain design gathers those tensors afterwards with NCCL (utils/batching.gather_mels).  Here rank ``dst`` allocates one
 window in its HBM, every rank of the node maps it through CUDA IPC (ftb_ipc_*), and each rank's epilogue stores its
-result tile straight into its slot over NVLink / NVSwitch: compute and "collective" are one kernel, there is no gather
-pass and no staging copy.  The only collective left is a tiny all-gather of the slot sizes (3 integers per rank and
-step).
+result tile straight into the window over NVLink / NVSwitch: compute and "collective" are one kernel, there is no gather
+pass and no staging copy.
+
+The window is cut into one REGION per rank and every rank bump-allocates inside its own region, so ``alloc`` needs no
+communication at all: it is safe to call from inside ``generate`` with several batches in flight, and a rank that raises
+cannot leave its peers waiting in a collective.  The only collective is ``collect`` at the end of the corpus: one small
+object all-gather of the slot metadata (offsets, shapes, utterance ids) after every rank has synchronised its device.
 
 Single node only (CUDA IPC); one process per GPU.
 """
@@ -25,8 +29,8 @@ class PeerSlot:
     rank's kernels can store to.  It quacks enough like a tensor for ``synthesize`` to take it as the output."""
     is_cuda, dtype = True, torch.float32
 
-    def __init__(self, ptr: int, shape: Tuple[int, int, int]):
-        self._ptr, self.shape = ptr, tuple(shape)
+    def __init__(self, ptr: int, shape: Tuple[int, int, int], offset: int):
+        self._ptr, self.shape, self.offset = ptr, tuple(shape), offset
 
     def data_ptr(self) -> int:
         return self._ptr
@@ -47,6 +51,7 @@ class PeerWindow:
         self.group, self.dst = group, dst
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.capacity = int(capacity_bytes)
+        self.region = self.capacity // self.world // 256 * 256      # bytes each rank may fill
         self.device = torch.device('cuda', torch.cuda.current_device())
         lib = _lib.lib()
         self._ptr = C.c_void_p()
@@ -62,8 +67,7 @@ class PeerWindow:
             handle = (C.c_ubyte * 64).from_buffer_copy(payload[0])
             _lib.check(lib.ftb_ipc_open(handle, self.device.index, C.byref(self._ptr)))
             self._view = None
-        self.cursor = 0
-        self.slots: List[Tuple[int, int, Tuple[int, int, int]]] = []  # on dst: (rank, byte offset, shape)
+        self.reset()
 
     def close(self) -> None:
         if self._ptr:
@@ -78,43 +82,45 @@ class PeerWindow:
             self._ptr = C.c_void_p()
 
     def reset(self) -> None:
-        self.cursor = 0
-        self.slots = []
+        """Start a new corpus: the regions are reused from their beginning.  Results handed out by an earlier
+        ``collect`` are copies, so they stay valid."""
+        self.cursor = self.rank * self.region
+        self.meta: List[Tuple[int, Tuple[int, int, int], List[int], List[int]]] = []
 
     def alloc(self, B: int, n_mels: int, L: int):
-        """COLLECTIVE: every rank calls it once per step (ranks without work pass B = 0).  Returns this rank's slot:
-        a float32 (B, n_mels, L) tensor view on the owner, a ``PeerSlot`` elsewhere, None for an empty slot."""
-        mine = torch.tensor([B, n_mels, L], dtype=torch.long, device=self.device)
-        allv = [torch.zeros_like(mine) for _ in range(self.world)]
-        dist.all_gather(allv, mine, group=self.group)
-        sizes = [tuple(int(v) for v in t.tolist()) for t in allv]
-        my_off = None
+        """LOCAL (no communication): reserves a float32 (B, n_mels, L) slot in this rank's region of the window.
+        Returns a tensor view on the owner, a ``PeerSlot`` elsewhere."""
+        nbytes = (B * n_mels * L * 4 + 255) // 256 * 256
         off = self.cursor
-        for r, (b, m, l) in enumerate(sizes):
-            nbytes = (b * m * l * 4 + 255) // 256 * 256
-            if r == self.rank:
-                my_off = off
-            if self.rank == self.dst and b > 0:
-                self.slots.append((r, off, (b, m, l)))
-            off += nbytes
-        if off > self.capacity:
-            raise RuntimeError(f'PeerWindow overflow: {off} > {self.capacity} bytes')
-        self.cursor = off
-        if B == 0:
-            return None
+        if off + nbytes > (self.rank + 1) * self.region:
+            raise RuntimeError(f'PeerWindow: region of rank {self.rank} is full ({self.region} bytes per rank); '
+                               'allocate a larger window')
+        self.cursor = off + nbytes
         if self.rank == self.dst:
-            return self._view[my_off:my_off + B * n_mels * L * 4].view(torch.float32).view(B, n_mels, L)
-        return PeerSlot(self._ptr.value + my_off, (B, n_mels, L))
+            t = self._view[off:off + B * n_mels * L * 4].view(torch.float32).view(B, n_mels, L)
+            t._ftb_window_offset = off
+            return t
+        return PeerSlot(self._ptr.value + off, (B, n_mels, L), off)
 
-    def collect(self) -> Optional[List[Tuple[int, torch.Tensor]]]:
-        """COLLECTIVE: waits until every rank's kernels have finished, then returns on ``dst`` the list of
-        (producing rank, tensor view) in allocation order (views into the window, no copy); None elsewhere."""
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)
+    def note_rows(self, slot, rows: List[int], frames: List[int]) -> None:
+        """Records which utterances (and how many valid frames each) the slot's rows hold."""
+        off = slot.offset if isinstance(slot, PeerSlot) else slot._ftb_window_offset
+        self.meta.append((int(off), tuple(int(v) for v in slot.shape), [int(r) for r in rows], [int(f) for f in frames]))
+
+    def collect(self, n_total: int) -> Optional[List[Optional[torch.Tensor]]]:
+        """COLLECTIVE (the only one): every rank waits for its own kernels, the slot metadata is all-gathered, and
+        ``dst`` returns the per-utterance ``(n_mels, L_i)`` results in the caller's order (copies out of the window, so
+        they survive the next ``reset``); None elsewhere."""
+        torch.cuda.synchronize(self.device)         # this rank's peer stores have landed in the owner's HBM
+        metas: List[Optional[list]] = [None] * self.world
+        dist.all_gather_object(metas, self.meta, group=self.group)
         if self.rank != self.dst:
             return None
-        out = []
-        for r, off, shape in self.slots:
-            n = shape[0] * shape[1] * shape[2]
-            out.append((r, self._view[off:off + n * 4].view(torch.float32).view(*shape)))
+        out: List[Optional[torch.Tensor]] = [None] * n_total
+        for meta in metas:
+            for off, shape, rows, frames in meta:
+                n = shape[0] * shape[1] * shape[2]
+                t = self._view[off:off + n * 4].view(torch.float32).view(*shape)
+                for r, (i, f) in enumerate(zip(rows, frames)):
+                    out[i] = t[r, :, :f].clone()
         return out

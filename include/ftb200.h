@@ -110,6 +110,15 @@ int ftb_length_expand(const void* x, const int32_t* cum, void* out, int B, int T
  * models/forward_tacotron.py:317-321) run once per phoneme instead of once per frame. */
 int ftb_length_index(const int32_t* cum, int32_t* idx, int B, int T, int L, int pad_row, void* stream);
 
+/* Ragged batches (the batched replacement of gen_forward.py:106-118, which runs one sentence per generate() call):
+ * zero the rows t >= lens[b] of a (B, S, row_bytes) tensor (lens: (B) int32, device).  With zeros beyond a row's end
+ * every conv sees the zero padding of the solo run; together with the length-aware recurrences (ftb_rnn_bidir_packed)
+ * a padded batch reproduces the per-sentence outputs. */
+int ftb_zero_tail_rows(void* x, int B, int S, int64_t row_bytes, const int32_t* lens, void* stream);
+/* The duration fallback of models/forward_tacotron.py:254-255 decided per ROW over its lens[b] valid positions (what the
+ * reference's per-sentence loop computes). */
+int ftb_duration_fallback_rows(float* dur, const int32_t* lens, int B, int T, void* stream);
+
 /* Duration fallback, models/forward_tacotron.py:254-255: if the batch-global sum
  * of trunc-toward-zero(dur) is <= 0, fill dur with 2.0.  scratch: 8 bytes. */
 int ftb_duration_fallback(float* dur, int64_t n, void* scratch8, void* stream);
@@ -190,6 +199,11 @@ int ftb_rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* o
  *     read hi + lo (the output heads need more than an 11-bit activation at trained mel magnitude). */
 int ftb_rnn_bidir_rows(const float* xg, const int32_t* xrow, const float* w_hh, const float* b_hn, void* out,
                        int B, int S, int H, int is_lstm, int out_kind, int ldo, int lo_off, void* stream);
+/* Packed-sequence semantics (pack_padded_sequence / pad_packed_sequence, models/forward_tacotron.py:224-231): row b is
+ * a sequence of lens[b] <= S steps ((B) int32, device); the reverse direction starts at its last valid step with a zero
+ * state, and the output beyond it is pad_value (H = 512 LSTM; 0 for the GRUs, where pad_value must be 0). */
+int ftb_rnn_bidir_packed(const float* xg, const int32_t* lens, float pad_value, const float* w_hh, const float* b_hn,
+                         void* out, int B, int S, int H, int is_lstm, int out_kind, void* stream);
 
 /* DSP.wav_to_mel, utils/dsp.py:71-87,105-107, for a batch of clips packed back to
  * back: audio f32, clip_offsets (n_clips+1) int64 sample offsets, frame_offsets
@@ -277,6 +291,18 @@ int ftb_ft_synthesize(ftb_ft_handle* h, const int64_t* tokens, const int32_t* cu
  * over the padded rows exactly as the reference does.  L = max(mel_lens) <= the expanded length. */
 int ftb_ft_synthesize_packed(ftb_ft_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
                              const float* energy, const int32_t* mel_lens, float pad_value, int B, int T, int L,
+                             float* mel, float* mel_post, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Ragged batch = the reference's per-sentence loop (gen_forward.py:106-118) in one call: row b holds tok_lens[b] tokens
+ * (padded with anything), and every output of row b equals what generate() returns for that sentence alone: convs see
+ * zero padding beyond the row's end, recurrences run over the row's own length, the duration fallback is decided per
+ * row.  predict_ragged writes 0 to dur / pitch / energy beyond tok_lens[b]; after the callbacks the caller zeroes those
+ * positions again (ftb_zero_tail_rows), plans the lengths, and passes total (B) as mel_lens to synthesize_ragged.  Frames
+ * of row b beyond mel_lens[b] in mel / mel_post are padding without meaning. */
+int ftb_ft_predict_ragged(ftb_ft_handle* h, const int64_t* tokens, const int32_t* tok_lens, int B, int T, float alpha,
+                          float* dur, float* pitch, float* energy, void* workspace, int64_t workspace_bytes, void* stream);
+int ftb_ft_synthesize_ragged(ftb_ft_handle* h, const int64_t* tokens, const int32_t* tok_lens, const int32_t* cum,
+                             const float* pitch, const float* energy, const int32_t* mel_lens, int B, int T, int L,
                              float* mel, float* mel_post, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Sub-module entry points (row a3 / a4 of the scope table; used by the mirrored

@@ -56,19 +56,41 @@ def test_gather_without_process_group():
 
 
 class FakeModel(torch.nn.Module):
-    """Stands in for the CUDA model: deterministic 'mel' whose length and content depend on the tokens only."""
+    """Stands in for the CUDA model with the reference's NO-MASK semantics: every token -- pad tokens included -- lasts
+    2 frames (+1 for the first), so a padded row is longer than its real tokens' frames and must be cut."""
     def __init__(self):
         super().__init__()
         self.p = torch.nn.Parameter(torch.zeros(1))
 
     def generate(self, x, alpha=1.0, **kw):
         B, T = x.shape
-        lens = (x != 0).sum(1) * 2 + 1
-        L = int(lens.max())
+        dur = torch.full((B, T), 2.0)
+        dur[:, 0] = 3.0
+        L = 2 * T + 1
         mel = torch.zeros(B, 80, L)
         for b in range(B):
-            mel[b, :, :int(lens[b])] = x[b].float().sum() + torch.arange(int(lens[b]))[None, :]
-        return {'mel_post': mel, 'mel': mel, 'mel_len': lens}
+            mel[b] = x[b].float().sum() + torch.arange(L)[None, :]
+        return {'mel_post': mel, 'mel': mel, 'dur': dur, 'mel_len': torch.full((B,), L)}
+
+
+class FakeRaggedModel(FakeModel):
+    """Offers generate_ragged: rows are computed from their own tokens only (mel_len per row)."""
+    def generate_ragged(self, x, lengths, alpha=1.0, **kw):
+        out = self.generate(x, alpha)
+        out['mel_len'] = torch.as_tensor(lengths) * 2 + 1
+        out['mel_post'] = out['mel_post'] + 1000.0          # marks the path taken
+        return out
+
+
+def test_corpus_rows_are_cut_at_the_frames_of_their_real_tokens():
+    utts = make_utts(23, seed=8)
+    for model, marker in ((FakeModel(), 0.0), (FakeRaggedModel(), 1000.0)):
+        out = batching.synthesize_corpus(model, utts, max_tokens=200, device=torch.device('cpu'))
+        for i, u in enumerate(utts):
+            assert out[i].shape == (80, 2 * len(u) + 1)
+            assert float(out[i][0, 0]) == float(sum(u)) + marker
+    with pytest.raises(ValueError):
+        batching.synthesize_corpus(FakeModel(), utts, device=torch.device('cpu'), exact=True)
 
 
 def _worker(rank, world, port, q):

@@ -142,19 +142,100 @@ def test_long_utterances_against_oracle():
     print('B3xT900', res, 'L', out['mel'].shape[-1])
 
 
-def test_corpus_batching_matches_direct_generate():
-    """utils/batching.synthesize_corpus (row a14): bucketed batches give the same mels as generate() on the same
-    padded batch, cut at each row's own frame count."""
+def _ragged_batch(seed, B, lo, hi):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(lo, hi, (B,), generator=g)
+    lens[0] = hi - 1
+    T = int(lens.max())
+    x = torch.randint(1, 135, (B, T), generator=g)
+    x = torch.where(torch.arange(T)[None, :] < lens[:, None], x, torch.full_like(x, 77))   # pad id is arbitrary
+    return x, lens
+
+
+@pytest.mark.parametrize('gemm_mode', [0, 1, 2])
+def test_ragged_batch_equals_per_sentence_generate(gemm_mode):
+    """generate_ragged = the reference's per-sentence loop (gen_forward.py:106-118, B = 1) in one padded batch: every
+    row must equal the solo generate() of its own tokens BIT FOR BIT (zero padding for the convs, recurrences over the
+    row's own length), including a callback that writes to the padded positions."""
+    model, _ = cuda_model('forward_tacotron', gemm_mode)
+    x, lens = _ragged_batch(31, 9, 5, 48)
+    pf, ef = (lambda p: p * 1.1), (lambda e: e + 0.1)
+    out = model.generate_ragged(x.cuda(), lens, alpha=0.9, pitch_function=pf, energy_function=ef)
+    worst = 0.0
+    for b, n in enumerate(lens.tolist()):
+        solo = model.generate(x[b:b + 1, :n].cuda(), alpha=0.9, pitch_function=pf, energy_function=ef)
+        L = int(solo['mel'].shape[-1])
+        assert int(out['mel_len'][b]) == L
+        assert torch.equal(out['dur'][b, :n], solo['dur'][0]) and float(out['dur'][b, n:].abs().sum()) == 0.0
+        for k in ('mel', 'mel_post'):
+            worst = max(worst, float((out[k][b, :, :L] - solo[k][0]).abs().max()))
+            assert torch.equal(out[k][b, :, :L], solo[k][0]), (k, b, worst)
+        assert torch.equal(out['pitch'][b, :, :n], solo['pitch'][0]) and torch.equal(out['energy'][b, :, :n], solo['energy'][0])
+    # and it is NOT what the no-mask arithmetic gives on the same padded batch (pad tokens are symbols there)
+    plain = model.generate(x.cuda(), alpha=0.9, pitch_function=pf, energy_function=ef)
+    assert int(plain['mel_len'][-1]) > int(out['mel_len'][-1]) or not torch.equal(plain['dur'][:, :5], out['dur'][:, :5])
+
+
+def test_ragged_fallback_is_decided_per_row():
+    """Plain random init: every sentence takes the fill_(2.0) fallback upstream (forward_tacotron.py:254-255, one
+    sentence per call); in a ragged batch that decision is per row and covers the row's own tokens only."""
+    model, _ = cuda_model('forward_tacotron', 0, plain_init=True)
+    x, lens = _ragged_batch(5, 4, 3, 20)
+    out = model.generate_ragged(x.cuda(), lens)
+    for b, n in enumerate(lens.tolist()):
+        assert bool((out['dur'][b, :n] == 2.0).all()) and float(out['dur'][b, n:].abs().sum()) == 0.0
+        assert int(out['mel_len'][b]) == 2 * n
+        solo = model.generate(x[b:b + 1, :n].cuda())
+        assert torch.equal(out['mel_post'][b, :, :2 * n], solo['mel_post'][0])
+
+
+def test_corpus_batching_equals_the_per_sentence_loop():
+    """utils/batching.synthesize_corpus (row a14): bucketed ragged batches, several in flight, give every utterance the
+    mel of its own one-sentence generate() call; exact=False reproduces the no-mask arithmetic of the padded batch, cut
+    after the frames of the real tokens."""
     from forwardtacotron_b200.utils import batching
     model, _ = cuda_model('forward_tacotron', 0)
     g = torch.Generator().manual_seed(2)
     utts = [torch.randint(1, 135, (int(n),), generator=g).tolist() for n in torch.randint(5, 40, (11,), generator=g)]
     got = batching.synthesize_corpus(model, utts, max_tokens=160)
+    for i, u in enumerate(utts):
+        solo = model.generate(torch.tensor([u]).cuda())
+        assert torch.equal(got[i], solo['mel_post'][0]), i
+    got_nm = batching.synthesize_corpus(model, utts, max_tokens=160, exact=False)
     for b in batching.bucket_by_length(utts, max_tokens=160):
         out = model.generate(b.tokens.cuda())
-        for r, i in enumerate(b.index.tolist()):
-            L = int(out['mel_len'][r])
-            assert torch.equal(got[i], out['mel_post'][r, :, :L])
+        r = (out['dur'].clamp(min=0) + 0.5).long().cpu()
+        for row, i in enumerate(b.index.tolist()):
+            L = int(r[row, :len(utts[i])].sum())
+            assert torch.equal(got_nm[i], out['mel_post'][row, :, :L])
+
+
+def test_gen_forward_front_end_and_hand_off_formats(tmp_path):
+    """The caller of the path: phonemised text -> tokens -> batched synthesis -> .mel (torch.save, MelGAN)
+    / .npy (HiFi-GAN) files, equal to upstream's per-sentence loop bit for bit."""
+    import numpy as np
+    from forwardtacotron_b200 import gen_forward
+    from forwardtacotron_b200.utils.checkpoints import save_checkpoint
+    from forwardtacotron_b200.utils.text import Tokenizer
+    model, cfg = synth.synthetic_model('forward_tacotron')
+    ckpt = tmp_path / 'forward_step0k.pt'
+    save_checkpoint(model, None, cfg, ckpt)
+    texts = ['ðɪs ɪz ɐ tˈɛst.', 'hɛlˈoʊ wˈɜːld, hˌaʊ ɑːɹ juː?', 'ɐ', 'ðə kwˈɪk bɹˈaʊn fˈɑːks dʒˈʌmps ˌoʊvɚ ðə lˈeɪzi dˈɑːɡ.']
+    (tmp_path / 'sentences.txt').write_text('\n'.join(texts) + '\n', encoding='utf-8')
+    cuda = model.cuda()
+    tok = Tokenizer()
+    want = [cuda.generate(torch.tensor([tok(t)]).cuda(), alpha=1.1, pitch_function=lambda p: p * 1.2)['mel_post'].cpu()
+            for t in texts]
+    for fmt in ('npy', 'mel'):
+        out = tmp_path / fmt
+        gen_forward.main(['--checkpoint', str(ckpt), '--file', str(tmp_path / 'sentences.txt'), '--alpha', '1.1',
+                          '--amp', '1.2', '--format', fmt, '--out', str(out)])
+        files = sorted(out.iterdir(), key=lambda p: int(p.name.split('_')[0]))
+        assert len(files) == len(texts)
+        for f, w in zip(files, want):
+            got = torch.from_numpy(np.load(f)) if fmt == 'npy' else torch.load(f)
+            assert got.dtype == torch.float32 and got.shape == w.shape and torch.equal(got, w), f.name
+    assert files[0].name == '1_forward_0k_alpha1.1_amp1.2_melgan.mel'
 
 
 @pytest.mark.parametrize('B,T', [(1, 1), (1, 3), (70, 33), (9, 129)])

@@ -143,3 +143,32 @@ def test_hi_lo_output_pair(H, lstm, kind):
                                      int(lstm), 0, _lib.current_stream(xg.device)))
         torch.cuda.synchronize()
         assert float((plain.float() + lo - f32).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize('H,lstm', [(64, False), (128, False), (256, False), (512, True)])
+@pytest.mark.parametrize('kind', [0, 2])
+def test_packed_sequences_equal_per_row_runs(H, lstm, kind):
+    """ftb_rnn_bidir_packed (pack_padded_sequence semantics): row b runs over lens[b] steps, the reverse direction starts
+    at its last valid step; bit-identical to running every row alone at its own length; pad_value beyond (LSTM)."""
+    lib = _lib.lib()
+    B, S, G = 11, 37, 4 if lstm else 3
+    g = torch.Generator().manual_seed(H + kind)
+    xg = (torch.randn(B, S, 2, G * H, generator=g) * 0.5).cuda()
+    whh = ((torch.rand(2, G * H, H, generator=g) * 2 - 1) / H ** 0.5).cuda()
+    bhn = (torch.randn(2, H, generator=g) * 0.1).cuda()
+    lens = torch.randint(1, S + 1, (B,), generator=g).int()
+    lens[0], lens[1] = S, 1
+    dt = (torch.float32, torch.bfloat16, torch.float16)[kind]
+    pad = -11.5 if lstm else 0.0
+    out = torch.empty(B, S, 2 * H, dtype=dt, device='cuda')
+    _lib.check(lib.ftb_rnn_bidir_packed(_lib.ptr(xg), _lib.ptr(lens.cuda()), pad, _lib.ptr(whh), None if lstm else _lib.ptr(bhn),
+                                        _lib.ptr(out), B, S, H, int(lstm), kind, _lib.current_stream(out.device)))
+    torch.cuda.synchronize()
+    for b, n in enumerate(lens.tolist()):
+        solo = torch.empty(1, n, 2 * H, dtype=dt, device='cuda')
+        xb = xg[b:b + 1, :n].contiguous()
+        _lib.check(lib.ftb_rnn_bidir(_lib.ptr(xb), _lib.ptr(whh), None if lstm else _lib.ptr(bhn), _lib.ptr(solo), 1, n, H,
+                                     int(lstm), kind, _lib.current_stream(out.device)))
+        torch.cuda.synchronize()
+        assert torch.equal(out[b, :n], solo[0]), (b, n)
+        assert bool((out[b, n:].float() == torch.tensor(pad, dtype=dt).float()).all())
