@@ -25,7 +25,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 B, T = 64, 200                       # BASELINE.json configs[1]
-CPU_SAMPLE_B = 8                     # rows of the same batch the CPU arm times (bounded sample)
+CPU_SAMPLE_B = 64                    # the CPU arm times the whole batch (a few seconds per call on 16 cores)
 METRIC, UNIT = 'mel_frames_per_s', 'frames/s'
 WORKLOAD = 'ForwardTacotron.generate batch 64 x 200 phonemes, alpha 1.0, config.yaml defaults, synthetic weights'
 
@@ -41,8 +41,8 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------ CPU arm
 def cpu_generate_rate(steps: int, warmup: int):
-    """The reference's algorithm (oracle port, torch fp32 on all host cores) on a bounded sample of the
-    same batch: the first CPU_SAMPLE_B utterances."""
+    """The reference's algorithm (oracle port, torch fp32 on all host cores; proven equal to the reference's own
+    generate() by oracle/make_golden.py) on the SAME batch as the GPU arm: all 64 utterances, a few timed calls."""
     import torch
     from forwardtacotron_b200.utils import synth
     from oracle import model_oracle as mo
@@ -61,8 +61,8 @@ def cpu_generate_rate(steps: int, warmup: int):
             frames = int((out['dur'] + 0.5).long().sum())
     total = sum(times)
     return {'value': frames * len(times) / total, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': f'first {CPU_SAMPLE_B} of the {B} utterances (T={T}), {len(times)} timed generate() calls of '
-                      f'oracle/model_oracle.py (torch {torch.__version__} fp32, {cores} threads), '
+            'sample': f'all {CPU_SAMPLE_B} of the {B} utterances (T={T}): the whole cfg2 batch, {len(times)} timed '
+                      f'generate() calls of oracle/model_oracle.py (torch {torch.__version__} fp32, {cores} threads), '
                       f'{frames} valid frames per call'}, total / len(times) * 1e3
 
 
@@ -70,13 +70,14 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     cb, ms = cpu_generate_rate(steps, warmup)
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': B * args.gpus, 'phonemes': T,
-                       'note': 'CPU arm: every step is the bounded sample described in cpu_baseline.sample'},
+                       'note': 'CPU arm: every step is one generate() over the whole 64 x 200 batch (cpu_baseline.sample); '
+                               'steps / warmup are capped at 3 / 1 so the run ends within minutes'},
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
@@ -208,58 +209,134 @@ def roofline_of(fam, pk):
     return out
 
 
-def stft_extra(torch, dev, pk):
-    """Second headline of BASELINE.json: STFT->log-mel audio-seconds/s (clips resident in HBM, > L2)."""
+def _dsp_cpu_clip(args):
+    """Pool worker: the oracle's wav_to_mel over one clip (mirrors the reference's per-file pool, preprocess.py:129-139)."""
+    from oracle import dsp_oracle
+    return dsp_oracle.wav_to_mel(args).shape[1]
+
+
+def stft_cpu_baseline(audio_host, offs, budget_s=12.0):
+    """The reference's CPU path for wav_to_mel -- librosa's algorithm as restated in oracle/dsp_oracle.py (librosa 0.7.2
+    itself is not installable offline) -- over a bounded sample of the same clips: one thread, then a
+    multiprocessing.Pool(cpu_count()) like preprocess.py:129.  audio-seconds per second."""
+    import multiprocessing as mp
+    import numpy as np
+    from oracle import dsp_oracle
+    cores = os.cpu_count() or 1
+    clips = [np.asarray(audio_host[int(offs[i]):int(offs[i + 1])]) for i in range(min(len(offs) - 1, 4 * cores))]
+    t0 = time.perf_counter()
+    n1 = 0
+    for c in clips:                                   # single thread: as many clips as fit in ~1/3 of the budget
+        dsp_oracle.wav_to_mel(c)
+        n1 += 1
+        if time.perf_counter() - t0 > budget_s / 3:
+            break
+    t1 = time.perf_counter() - t0
+    secs1 = sum(len(c) for c in clips[:n1]) / 22050.0
+    with mp.get_context('fork').Pool(cores) as pool:
+        pool.map(_dsp_cpu_clip, clips[:cores])         # warm the workers
+        t0 = time.perf_counter()
+        pool.map(_dsp_cpu_clip, clips)
+        tp = time.perf_counter() - t0
+    secs = sum(len(c) for c in clips) / 22050.0
+    return {'value': secs / tp, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
+            'single_thread_value': secs1 / t1,
+            'sample': f'{len(clips)} of the clips through oracle/dsp_oracle.py (numpy float64 rFFT, Slaney mel) on a '
+                      f'multiprocessing.Pool({cores}); single-thread figure over the first {n1} clips',
+            'parity': 'unpinned against librosa 0.7.2 (not installable offline); the restatement agrees with '
+                      "torchaudio's independent Slaney mel to 5.5e-6 (tests/test_oracle_dsp.py)"}
+
+
+def stft_extra(torch, dev, pk, n_clips=1250, seed=7, cpu=True):
+    """Second headline of BASELINE.json: STFT->log-mel audio-seconds/s (cfg4: 10 000 clips of 2-10 s over 8 GPUs =
+    1 250 per GPU; ~165 M samples = 660 MB of fp32 >> 126 MB L2).  Three figures: the kernel alone (offsets planned
+    once, CUDA events), the packed call as a user makes it (plans the offsets every call), and end to end from pinned
+    HOST audio with the mel read back to the host."""
     from forwardtacotron_b200.utils import synth
     from forwardtacotron_b200.utils.config import default_config
     from forwardtacotron_b200.utils.dsp import DSP
     dsp = DSP.from_config(default_config())
-    n_clips = 1250                                            # cfg4: 10 000 clips over 8 GPUs = 1 250 per GPU
-    audio, offs = synth.synthetic_audio(n_clips, seed=7)      # ~165 M samples = 660 MB of fp32 >> 126 MB L2
-    a = audio.to(dev)
+    audio, offs = synth.synthetic_audio(n_clips, seed=seed)
+    a_host = audio.pin_memory()
+    a = a_host.to(dev)
+    plan = dsp.plan_clips(offs, dev)
+    out = torch.empty(80 * plan.total_frames, dtype=torch.float32, device=dev)
     for _ in range(3):
-        out, fo = dsp.wav_to_mel_packed(a, offs)
+        dsp.wav_to_mel_packed(a, plan, out=out)
+        dsp.wav_to_mel_packed(a, offs)
     torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 10
-    e0.record()
-    for _ in range(reps):
-        out, fo = dsp.wav_to_mel_packed(a, offs)
-    e1.record()
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    ms_kernel = timed(lambda: dsp.wav_to_mel_packed(a, plan, out=out))
+    ms_call = timed(lambda: dsp.wav_to_mel_packed(a, offs))
+    out_host = torch.empty(out.shape, dtype=torch.float32).pin_memory()
     torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / reps
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ad = a_host.to(dev, non_blocking=True)
+        o, _ = dsp.wav_to_mel_packed(ad, offs)
+        out_host.copy_(o, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / 3
     secs = a.numel() / 22050.0
     nbytes = a.numel() * 4 + out.numel() * 4
-    # The kernel is bound by instruction issue, not by HBM (DESIGN.md 4): the fp32 FFT + split + sparse mel cost
-    # WARP_INSTR_PER_FRAME warp instructions per frame (smsp__inst_executed.sum / frames of profiles/r01_stft_v4.txt),
-    # against 4 issue slots per SM and clock.
-    WARP_INSTR_PER_FRAME = 1499.0
+    # The kernel is bound by instruction issue, not by HBM (DESIGN.md 4): warp instructions per frame from the committed
+    # ncu capture (smsp__inst_executed.sum / frames), against 4 issue slots per SM and clock.
+    wipf = 1499.0
+    traffic = None
+    p = ROOT / 'profiles' / 'ncu_traffic.json'
+    if p.exists():
+        d = json.loads(p.read_text())
+        wipf = float(d.get('stft_mel_warp_instr_per_frame', wipf))
+        traffic = d.get('stft_mel')
     frames = out.numel() / 80
     props = torch.cuda.get_device_properties(dev)
     issue_peak = props.multi_processor_count * 4 * 1.965e9
-    issue = {'bound': 'issue', 'achieved': frames * WARP_INSTR_PER_FRAME / (ms / 1e3) / 1e9, 'peak': issue_peak / 1e9,
-             'unit': 'G warp-instr/s', 'frac': frames * WARP_INSTR_PER_FRAME / (ms / 1e3) / issue_peak,
-             'note': 'warp instructions per frame from the committed ncu capture; peak = SMs x 4 schedulers x 1965 MHz'}
-    return {'metric': 'stft_mel_audio_seconds_per_s', 'value': secs / (ms / 1e3), 'unit': 'audio-s/s',
-            'issue_roofline': issue,
-            'ms_per_step': ms, 'clips': n_clips, 'audio_seconds': secs,
-            'workload': 'DSP.wav_to_mel, 22.05 kHz clips of 2-10 s (noise, sines, silence), n_fft 1024 / hop 256 / 80 mels',
-            'roofline': {'kernel': 'stft_mel', 'bound': 'hbm', 'achieved': nbytes / (ms / 1e3) / 1e9,
-                         'peak': pk['hbm'], 'unit': 'GB/s', 'frac': nbytes / (ms / 1e3) / 1e9 / pk['hbm'],
-                         'note': 'includes the host-side offset upload of wav_to_mel_packed'}}
+    res = {'metric': 'stft_mel_audio_seconds_per_s', 'value': secs / (ms_kernel / 1e3), 'unit': 'audio-s/s',
+           'ms_per_step': ms_kernel, 'clips': n_clips, 'audio_seconds': secs,
+           'packed_call': {'value': secs / (ms_call / 1e3), 'ms_per_step': ms_call,
+                           'note': 'DSP.wav_to_mel_packed(audio, clip_offsets) as a user calls it: plans the frame offsets '
+                                   'on the host and uploads them (one pinned H2D) every call'},
+           'e2e': {'value': secs / (ms_e2e / 1e3), 'unit': 'audio-s/s', 'ms_per_step': ms_e2e,
+                   'h2d_bytes_per_step': a.numel() * 4 + (2 * n_clips + 2) * 8, 'd2h_bytes_per_step': out.numel() * 4,
+                   'note': 'pinned host audio -> device, packed call, mel -> pinned host, wall clock'},
+           'workload': 'DSP.wav_to_mel, 22.05 kHz clips of 2-10 s (noise, sines, silence), n_fft 1024 / hop 256 / 80 mels',
+           'issue_roofline': {'bound': 'issue', 'achieved': frames * wipf / (ms_kernel / 1e3) / 1e9, 'peak': issue_peak / 1e9,
+                              'unit': 'G warp-instr/s', 'frac': frames * wipf / (ms_kernel / 1e3) / issue_peak,
+                              'note': 'warp instructions per frame from the committed ncu capture; peak = SMs x 4 schedulers x 1965 MHz'},
+           'roofline': {'kernel': 'stft_mel', 'bound': 'hbm', 'achieved': nbytes / (ms_kernel / 1e3) / 1e9,
+                        'peak': pk['hbm'], 'unit': 'GB/s', 'frac': nbytes / (ms_kernel / 1e3) / 1e9 / pk['hbm'],
+                        'traffic': traffic, 'note': 'kernel alone (CUDA events around the launches, offsets planned once)'}}
+    if cpu:
+        try:
+            res['cpu_baseline'] = stft_cpu_baseline(audio.numpy(), offs.tolist())
+        except Exception as e:
+            res['cpu_baseline'] = {'error': str(e)}
+    return res
 
 
-def fastpitch_extra(torch, dev):
+def fastpitch_extra(torch, dev, seed=5):
     """BASELINE.json configs[2]: FastPitch batch 128 x 300 phonemes with pitch + energy callbacks (per GPU)."""
+    from forwardtacotron_b200 import _lib
     from forwardtacotron_b200.utils import synth
+    lib = _lib.lib()
     model, _ = synth.synthetic_model('fast_pitch')
     model = model.to(dev)
-    x = synth.synthetic_tokens(128, 300, seed=5).to(dev)
+    x = synth.synthetic_tokens(128, 300, seed=seed).to(dev)
     pf, ef = (lambda p: p * 1.2), (lambda e: e + 0.1)
     out = model.generate(x, pitch_function=pf, energy_function=ef)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 2
+    reps = 3
     e0.record()
     for _ in range(reps):
         out = model.generate(x, pitch_function=pf, energy_function=ef)
@@ -267,42 +344,128 @@ def fastpitch_extra(torch, dev):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / reps
     frames = int(out['mel_len'].sum().item())
-    return {'metric': 'mel_frames_per_s', 'value': frames / (ms / 1e3), 'unit': 'frames/s', 'ms_per_step': ms,
-            'workload': 'FastPitch.generate batch 128 x 300 phonemes, pitch*1.2 / energy+0.1 callbacks',
-            'mel_frames_padded_L': int(out['mel'].shape[-1]), 'valid_frames': frames,
-            'numerics': 'IEEE-half tcgen05 GEMMs + mma.sync flash attention, fp32 accumulate / residual stream / '
-                        'LayerNorm; duration predictor fp32 (DESIGN.md 2)'}
+    res = {'metric': 'mel_frames_per_s', 'value': frames / (ms / 1e3), 'unit': 'frames/s', 'ms_per_step': ms,
+           'workload': 'FastPitch.generate batch 128 x 300 phonemes, pitch*1.2 / energy+0.1 callbacks',
+           'mel_frames_padded_L': int(out['mel'].shape[-1]), 'valid_frames': frames,
+           'numerics': 'IEEE-half tcgen05 GEMMs + tensor-core flash attention, fp32 accumulate / residual stream / '
+                       'LayerNorm; duration predictor fp32-grade (DESIGN.md 2)'}
+    try:  # per-family kernel time of one more call (events around every launch)
+        lib.ftb_profile_enable(1)
+        model.generate(x, pitch_function=pf, energy_function=ef)
+        torch.cuda.synchronize(dev)
+        fams = collect_profile(lib, 1)
+        lib.ftb_profile_enable(0)
+        pk = peaks()
+        res['kernels'] = fams
+        res['rooflines'] = [roofline_of(f, pk) for f in fams if f['flops_per_step'] > 0]
+    except Exception as e:
+        res['kernels'] = {'error': str(e)}
+    return res
 
 
-def gather_extra(torch, dist, model, dev, world):
-    """N > 1 only: the path's one exchange step, both ways.  A corpus of 96 x world utterances is
-    bucketed, sharded, synthesised and collected on rank 0 with (a) the NCCL gather, (b) the peer window the last
-    GEMM's epilogue stores into directly.  Wall clock incl. host bucketing, max over ranks."""
+def _agree(torch, dist, dev, ok: bool) -> bool:
+    """All ranks learn whether every rank got through the previous (collective-free) phase."""
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t[0]))
+
+
+def sharded_corpus_extra(torch, dist, model, dev, world):
+    """N > 1: the path's one exchange step.  A corpus of 96 x world utterances is bucketed,
+    sharded over the ranks, synthesised (ragged batches, 3 in flight) and collected on rank 0 three ways:
+      none        -- no exchange: every rank keeps its results (what the exchange is measured against)
+      nccl        -- exact-size grouped ncclSend / ncclRecv to rank 0 (utils/batching.gather_mels)
+      peer_window -- the post_proj epilogue of every rank stores straight into rank 0's HBM over NVLink
+    Wall clock of the whole run incl. host bucketing, max over ranks; second pass of each mode (first = warm-up)."""
     from forwardtacotron_b200.utils import batching
     from forwardtacotron_b200.utils.peer_window import PeerWindow
     g = torch.Generator().manual_seed(3)
     n = 96 * world
     utts = [torch.randint(1, 135, (int(k),), generator=g).tolist() for k in torch.randint(40, 200, (n,), generator=g)]
-    window = PeerWindow(4 << 30)
-    res = {}
-    for mode in ('nccl', 'peer_window', 'nccl', 'peer_window'):   # first pair = warm-up
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        t0 = time.perf_counter()
-        out = batching.synthesize_corpus(model, utts, max_tokens=8192, window=window if mode == 'peer_window' else None)
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        res[mode] = time.perf_counter() - t0
-        if out is not None:
-            frames = sum(int(m.shape[1]) for m in out)
-    t = torch.tensor([res['nccl'], res['peer_window']], dtype=torch.float64, device=dev)
+    window = PeerWindow(min(8 << 30, (1 << 30) * world))
+    res, frames, err = {}, 0, None
+    for rep in range(2):
+        for mode in ('none', 'nccl', 'peer_window'):
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            t0 = time.perf_counter()
+            out = None
+            try:
+                out = batching.synthesize_corpus(model, utts, max_tokens=8192, gather=mode != 'none',
+                                                 window=window if mode == 'peer_window' else None)
+                torch.cuda.synchronize(dev)
+            except Exception as e:  # keep the ranks in step: everybody reaches the barrier below
+                err = f'{mode}: {e}'
+            dist.barrier()
+            res[mode] = time.perf_counter() - t0
+            if mode == 'nccl' and out is not None and dist.get_rank() == 0:
+                frames = sum(int(m.shape[1]) for m in out)
+    t = torch.tensor([res['none'], res['nccl'], res['peer_window']], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     window.close()
     if dist.get_rank() != 0:
         return None
-    return {'utterances': n, 'frames': frames, 'nccl_gather_ms': float(t[0]) * 1e3, 'peer_window_ms': float(t[1]) * 1e3,
-            'note': 'whole sharded corpus run (bucket, generate, collect on rank 0); peer window = post_proj epilogue '
-                    'stores into rank 0 HBM over NVLink, no gather pass'}
+    r = {'utterances': n, 'frames': frames, 'no_gather_ms': float(t[0]) * 1e3, 'nccl_gather_ms': float(t[1]) * 1e3,
+         'peer_window_ms': float(t[2]) * 1e3, 'frames_per_s_peer_window': frames / float(t[2]) if frames else None,
+         'note': 'whole sharded corpus run (bucket, ragged generate with 3 batches in flight, collect on rank 0); '
+                 'nccl = exact-size grouped send/recv; peer window = post_proj epilogue stores into rank 0 HBM over '
+                 'NVLink, no gather pass, no collective inside generate'}
+    if err:
+        r['error'] = err
+    return r
+
+
+def multi_gpu_configs_extra(torch, dist, dev, world, rank, pk):
+    """N > 1: BASELINE.json configs[2..4] sharded over the ranks.  Every rank runs its share with NO collective inside
+    the timed work; the per-rank (units, seconds) pairs are reduced afterwards (sum of units / max of seconds)."""
+    from forwardtacotron_b200.utils import batching, synth
+    res, local = {}, {}
+    # cfg3: FastPitch 128 x 300 per rank (utterance-sharded, weak scaling like the headline)
+    try:
+        fp = fastpitch_extra(torch, dev, seed=5 + rank)
+        local['fast_pitch'] = (float(fp['valid_frames']), fp['ms_per_step'] / 1e3)
+    except Exception as e:
+        local['fast_pitch'] = (0.0, 0.0)
+        res['fast_pitch_error'] = str(e)
+    # cfg4: 10 000 clips of 2-10 s sharded over the ranks (strong scaling): 10 000 / N clips here
+    try:
+        st = stft_extra(torch, dev, pk, n_clips=10000 // world, seed=7 + rank, cpu=False)
+        local['stft_mel'] = (float(st['audio_seconds']), st['ms_per_step'] / 1e3)
+        local['stft_mel_e2e'] = (float(st['audio_seconds']), st['e2e']['ms_per_step'] / 1e3)
+    except Exception as e:
+        local['stft_mel'] = local['stft_mel_e2e'] = (0.0, 0.0)
+        res['stft_mel_error'] = str(e)
+    # cfg5: 256 x ~2000-phoneme utterances, length-bucketed into batches of 32, dealt over the ranks, alpha 0.8 / 1.0 / 1.2
+    try:
+        model, _ = synth.synthetic_model('forward_tacotron')
+        model = model.to(dev)
+        g = torch.Generator().manual_seed(11)
+        utts = [torch.randint(1, 135, (int(n),), generator=g).tolist() for n in torch.randint(1900, 2001, (256,), generator=g)]
+        batching.synthesize_corpus(model, utts, alpha=0.8, max_tokens=65536, in_flight=2, gather=False)
+        torch.cuda.synchronize(dev)
+        for alpha in (0.8, 1.0, 1.2):
+            t0 = time.perf_counter()
+            mels = batching.synthesize_corpus(model, utts, alpha=alpha, max_tokens=65536, in_flight=2, gather=False)
+            torch.cuda.synchronize(dev)
+            local[f'long_article_alpha_{alpha}'] = (float(sum(int(m.shape[1]) for m in mels if m is not None)),
+                                                    time.perf_counter() - t0)
+        del model
+    except Exception as e:
+        for alpha in (0.8, 1.0, 1.2):
+            local.setdefault(f'long_article_alpha_{alpha}', (0.0, 0.0))
+        res['long_article_error'] = str(e)
+    keys = sorted(local)
+    units = torch.tensor([local[k][0] for k in keys], dtype=torch.float64, device=dev)
+    secs = torch.tensor([local[k][1] for k in keys], dtype=torch.float64, device=dev)
+    dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+    for k, u, t in zip(keys, units.tolist(), secs.tolist()):
+        res[k] = {'units': u, 'max_seconds_over_ranks': t, 'value': (u / t) if t > 0 else None,
+                  'unit': 'audio-s/s' if k.startswith('stft') else 'frames/s'}
+    res['note'] = (f'configs[2..4] on {world} GPUs: fast_pitch = 128 x 300 per rank (weak); stft_mel = 10 000 clips / '
+                   f'{world} ranks (strong), kernel-only and host-buffer e2e; long_article = 256 utterances sharded '
+                   f'by length bucket (strong), wall clock incl. host bucketing; value = sum(units) / max(seconds)')
+    return res
 
 
 def long_article_extra(torch, dev):
@@ -405,6 +568,16 @@ def run_ours(args):
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = lib.ftb_launch_count() - launches0
+    # the timed region above is the reported one; four more identical regions show the spread (it is ~0.1 s long)
+    repeats = [ms_total / args.steps]
+    for _ in range(4):
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        r0.record()
+        run_steps(args.steps)
+        r1.record()
+        barrier()
+        repeats.append(r0.elapsed_time(r1) / args.steps)
     clocks = sampler.stop() if sampler else None
 
     # ---- per-family kernel durations.  In the timed region kernels of several streams overlap (stage A forks onto
@@ -444,12 +617,22 @@ def run_ours(args):
     else:
         frames_all = float(frames_per_step)
 
-    gather = None
-    if world > 1 and args.gather_extra:  # opt-in: a collective extra must never be able to cost the headline line
-        try:
-            gather = gather_extra(torch, dist, model, dev, world)
-        except Exception as e:  # the headline line must still be printed
-            gather = {'error': str(e)}
+    # ---- latency of ONE generate() with nothing else in flight (the throughput figure keeps S batches in flight)
+    lat_ms = None
+    try:
+        torch.cuda.synchronize(dev)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        model.generate(x)
+        l0.record()
+        for _ in range(5):
+            model.generate(x)
+        l1.record()
+        torch.cuda.synchronize(dev)
+        lat_ms = l0.elapsed_time(l1) / 5
+    except Exception:
+        pass
+
+    line = None
     if rank == 0:
         value = frames_all * args.steps / (ms_total / 1e3)
         e2e_steps = 1 if args.no_extras else args.steps  # --no-extras (profiling runs) times ONE e2e step only
@@ -473,6 +656,9 @@ def run_ours(args):
                        'l2': f'per-step working set {ws_bytes / 1e9:.2f} GB >> 126 MB L2, no explicit flush'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 8,
                     'd2h_bytes_per_step': mel_host.numel() * 4 + B * 4, 'ms_per_step': e2e_ms / e2e_steps},
+            'ms_per_step_repeats': {'all': repeats, 'min': min(repeats), 'median': statistics.median(repeats),
+                                    'note': 'this rank; [0] is the reported region, the others follow it back to back'},
+            'latency_ms_in_flight_1': lat_ms,
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': roofline_of(top, pk),
@@ -482,24 +668,52 @@ def run_ours(args):
             'kernels_note': f'share = fraction of the serialised step ({serial_ms:.3f} ms kernel time); the timed steps '
                             f'overlap stage A / prenet on side streams and keep {S} batches in flight',
         }
-        if gather is not None:
-            line.setdefault('extra', {})['final_gather'] = gather
-        if world == 1 and not args.no_extras:
-            try:
-                line['extra'] = {'stft_mel': stft_extra(torch, dev, pk)}
-            except Exception as e:  # the headline line must still be printed
-                line['extra'] = {'stft_mel': {'error': str(e)}}
-            try:
-                line['extra']['fast_pitch'] = fastpitch_extra(torch, dev)
-            except Exception as e:
-                line['extra']['fast_pitch'] = {'error': str(e)}
-            try:
-                line['extra']['long_article'] = long_article_extra(torch, dev)
-            except Exception as e:
-                line['extra']['long_article'] = {'error': str(e)}
+
+    # ---- extras.  The headline above is complete; a watchdog prints it as it stands if an extra stalls (a collective
+    # that one rank never reaches must not cost the line), then the process exits.
+    import threading
+    printed = threading.Event()
+
+    def emit():
+        if rank == 0 and not printed.is_set():
+            printed.set()
+            print(json.dumps(line), flush=True)
+
+    def watchdog():
+        if rank == 0 and line is not None:
+            line.setdefault('extra', {})['watchdog'] = f'extras exceeded {args.extras_timeout} s; line printed without the unfinished ones'
+        emit()
+        os._exit(0)
+
+    timer = threading.Timer(args.extras_timeout, watchdog)
+    timer.daemon = True
+    if not args.no_extras:
+        timer.start()
+    extra = {}
+    if not args.no_extras:
+        if world > 1:
+            for name, fn in (('final_gather', lambda: sharded_corpus_extra(torch, dist, model, dev, world)),
+                             ('configs', lambda: multi_gpu_configs_extra(torch, dist, dev, world, rank, pk))):
+                try:
+                    r = fn()
+                except Exception as e:
+                    r = {'error': str(e)}
+                if rank == 0 and r is not None:
+                    extra[name] = r
+                    line['extra'] = extra
+        else:
+            for name, fn in (('stft_mel', lambda: stft_extra(torch, dev, pk)),
+                             ('fast_pitch', lambda: fastpitch_extra(torch, dev)),
+                             ('long_article', lambda: long_article_extra(torch, dev))):
+                try:
+                    extra[name] = fn()
+                except Exception as e:  # the headline line must still be printed
+                    extra[name] = {'error': str(e)}
+                line['extra'] = extra
             cb, _ = cpu_generate_rate(3, 1)
             line['cpu_baseline'] = cb
-        print(json.dumps(line), flush=True)
+    timer.cancel()
+    emit()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -515,7 +729,9 @@ def main():
     ap.add_argument('--gemm-mode', type=int, default=0, choices=[0, 2],
                     help='ForwardTacotron operand type: 0 IEEE half (default, holds the absolute tolerance at trained '
                          'magnitude), 2 bf16 (same kernels and rate)')
-    ap.add_argument('--gather-extra', action='store_true', help='N > 1: also time the final gather both ways')
+    ap.add_argument('--extras-timeout', type=float, default=420.0,
+                    help='seconds the extras (other configs, CPU baselines, multi-GPU exchange) may take before the '
+                         'headline line is printed without them')
     ap.add_argument('--no-extras', action='store_true', help='profiling runs: skip the e2e / STFT / CPU legs')
     ap.add_argument('--stft-only', action='store_true', help='profiling runs: only the STFT->mel leg')
     args = ap.parse_args()
