@@ -209,6 +209,15 @@ def roofline_of(fam, pk):
     return out
 
 
+def _one_blas_thread():
+    """One BLAS / OpenMP thread per process: the pool already uses every core (16 workers x 16 BLAS threads thrash)."""
+    try:
+        import threadpoolctl
+        _one_blas_thread.keep = threadpoolctl.threadpool_limits(1)
+    except Exception:
+        os.environ['OMP_NUM_THREADS'] = '1'
+
+
 def _dsp_cpu_clip(args):
     """Pool worker: the oracle's wav_to_mel over one clip (mirrors the reference's per-file pool, preprocess.py:129-139)."""
     from oracle import dsp_oracle
@@ -223,7 +232,13 @@ def stft_cpu_baseline(audio_host, offs, budget_s=12.0):
     import numpy as np
     from oracle import dsp_oracle
     cores = os.cpu_count() or 1
-    clips = [np.asarray(audio_host[int(offs[i]):int(offs[i + 1])]) for i in range(min(len(offs) - 1, 4 * cores))]
+    clips = [np.asarray(audio_host[int(offs[i]):int(offs[i + 1])]) for i in range(min(len(offs) - 1, 16 * cores))]
+    try:
+        import threadpoolctl
+        limit = threadpoolctl.threadpool_limits(1)
+    except Exception:
+        limit = None
+    dsp_oracle.wav_to_mel(clips[0])
     t0 = time.perf_counter()
     n1 = 0
     for c in clips:                                   # single thread: as many clips as fit in ~1/3 of the budget
@@ -233,7 +248,9 @@ def stft_cpu_baseline(audio_host, offs, budget_s=12.0):
             break
     t1 = time.perf_counter() - t0
     secs1 = sum(len(c) for c in clips[:n1]) / 22050.0
-    with mp.get_context('fork').Pool(cores) as pool:
+    if limit is not None:
+        limit.restore_original_limits()
+    with mp.get_context('fork').Pool(cores, initializer=_one_blas_thread) as pool:
         pool.map(_dsp_cpu_clip, clips[:cores])         # warm the workers
         t0 = time.perf_counter()
         pool.map(_dsp_cpu_clip, clips)

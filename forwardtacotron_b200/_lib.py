@@ -103,6 +103,10 @@ SIGNATURES = {
     'ftb_mel_destroy': (None, [_P]),
     'ftb_mel_run': (_I, [_P, _P, _P, _P, _I, _L, _P, _I, _P]),
     'ftb_mel_filterbank': (_I, [_P, _P]),
+    'ftb_mel_to_stft': (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    'ftb_griffinlim_workspace_bytes': (_L, [_I]),
+    'ftb_griffinlim': (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _L, _P]),
+    'ftb_trim_silence': (_I, [_P, _P, _I, _I, _F, _I, _I, _P, _P, _L, _P]),
     'ftb_ft_create': (_I, [C.POINTER(FtConfig), C.POINTER(Tensor), _I, _I, C.POINTER(_P)]),
     'ftb_ft_destroy': (None, [_P]),
     'ftb_ft_workspace_bytes': (_L, [_P, _I, _I, _I]),

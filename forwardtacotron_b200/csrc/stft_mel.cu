@@ -14,76 +14,23 @@
 // is served by L1/L2.  The kernel is bound by instruction issue + shared-memory wavefronts, not by HBM.
 #include <cmath>
 
-#include "common.cuh"
+#include "fft512.cuh"
+#include "mel_handle.cuh"
 
 namespace ftb {
 
 namespace mel {
-constexpr int NFFT = 1024, NC = 512, NBINS = 513, WARPS = 8, MAX_MELS = 128;
-constexpr int NCP = NC + NC / 16;  // padded per-warp FFT buffer (float2): see pad()
 constexpr int VL = 8;              // taps per virtual mel row
 constexpr int PART_OFF = NCP;      // virtual-row partial sums: floats [PART_OFF, 2 NCP) of the warp's buffer
 constexpr int MAX_VR = NCP;
 constexpr int GROUPS = 8;          // 8-frame groups per CTA: amortises the table prologue
 }
 
-struct MelTables {  // device pointers
-  const float2* window;  // [512]  periodic Hann, as (w[2m], w[2m+1])
-  const float2* tw8;     // [8][9]  pass-2 twiddles exp(-2 pi i r k / 64) at [k * 9 + r]
-  const float2* tw64;    // [7][64] pass-3 twiddles exp(-2 pi i r k / 512) at [(r - 1) * 64 + k]
-  const float2* w1024;   // [257]  exp(-2 pi i k / 1024)
-  const float* vr_w;     // [VL][nvrp] tap weights of the virtual rows (0 where a row has fewer taps)
-  const int* vr_start;   // [nvrp] first bin of the virtual row (start + VL <= 513)
-  const int* row_first;  // [n_mels] first virtual row of the mel row
-  const int* row_cnt;    // [n_mels] number of virtual rows
-  int n_mels, nvrp, hop;
-};
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Index into the padded FFT buffer: one float2 of padding after every 16.  A 64-bit shared access is served per
-// half-warp over 16 bank pairs; with this padding pass 1's stride-8 scatter and every unit-stride pattern are
-// conflict-free and pass 2's two 8-wide groups are 2-way (exhaustive search over paddings / XOR swizzles: the only
-// better layout costs an extra LOP3 per access).  Unpadded, pass 1 was 8-way conflicted and shared-memory wavefronts
-// bounded the kernel.
-__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
-
-// 8-point DFT, natural order in and out (decimation in time, 3 radix-2 levels)
-__device__ __forceinline__ void fft8(float2 (&v)[8]) {
-  const float h = 0.70710678118654752440f;
-  const float2 a0 = cadd(v[0], v[4]), a1 = csub(v[0], v[4]), a2 = cadd(v[2], v[6]), a3 = mul_mi(csub(v[2], v[6]));
-  const float2 a4 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]), a6 = cadd(v[3], v[7]), a7 = mul_mi(csub(v[3], v[7]));
-  const float2 b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = csub(a1, a3);
-  const float2 b4 = cadd(a4, a6), b6 = csub(a4, a6), b5 = cadd(a5, a7), b7 = csub(a5, a7);
-  const float2 t5 = make_float2(h * (b5.x + b5.y), h * (b5.y - b5.x));    // b5 * W8   , W8   = (h, -h)
-  const float2 t6 = mul_mi(b6);                                            // b6 * W8^2 = -i
-  const float2 t7 = make_float2(h * (b7.y - b7.x), -h * (b7.x + b7.y));   // b7 * W8^3 , W8^3 = (-h, -h)
-  v[0] = cadd(b0, b4);
-  v[1] = cadd(b1, t5);
-  v[2] = cadd(b2, t6);
-  v[3] = cadd(b3, t7);
-  v[4] = csub(b0, b4);
-  v[5] = csub(b1, t5);
-  v[6] = csub(b2, t6);
-  v[7] = csub(b3, t7);
-}
-
-// np.pad(y, n_fft//2, mode='reflect') index map (period 2(N-1); a single reflection when N > 512)
-__device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t N) {
-  if (N == 1) return 0;
-  const int64_t p = 2 * (N - 1);
-  i %= p;
-  if (i < 0) i += p;
-  return i < N ? i : p - i;
-}
-
 // last c in [0, n_clips) with frame_off[c] <= g: 32 probes per round instead of a dependent bisection chain
 __device__ __forceinline__ int find_clip(const int64_t* __restrict__ frame_off, int n_clips, int64_t g, int lane) {
   int lo = 0, n = n_clips;  // candidates [lo, lo + n); invariant frame_off[lo] <= g
@@ -118,7 +65,7 @@ __global__ void __launch_bounds__(mel::WARPS * 32, 3)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 72; i += WARPS * 32) s_tw8[i] = tb.tw8[i];
   for (int i = tid; i < 448; i += WARPS * 32) s_tw64[i] = tb.tw64[i];
-  for (int i = tid; i < 257; i += WARPS * 32) s_w1024[i] = tb.w1024[i];
+  for (int i = tid; i < 257; i += WARPS * 32) s_w1024[i] = tb.w1024[i];  // bins 0..256 (the mirrored ones by symmetry)
   for (int i = tid; i < NC; i += WARPS * 32) s_win[i] = tb.window[i];
   for (int i = tid; i < VL * tb.nvrp; i += WARPS * 32) s_vrw[i] = tb.vr_w[i];
   for (int i = tid; i < tb.nvrp; i += WARPS * 32) s_vrs[i] = tb.vr_start[i];
@@ -150,76 +97,17 @@ __global__ void __launch_bounds__(mel::WARPS * 32, 3)
     const int64_t nframes = f_next - f_first;
     const float* y = audio + c0;
     const int64_t s0 = f * tb.hop - NFFT / 2;  // first sample of the frame in un-padded coordinates
-    const bool interior = s0 >= 0 && s0 + NFFT <= N;
-
-    // ---- frame -> registers: z[m] = (x[2m], x[2m+1]) for m = lane + 32 jj + 64 r (the order pass 1 wants).
-    // Three warp-uniform paths so the common one is 16 plain 8-byte loads with immediate offsets.
+    // ---- frame -> registers: z[m] = (x[2m], x[2m+1]) for m = lane + 32 jj + 64 r, then the periodic Hann window
     float2 x[2][8];
-    if (interior && (((c0 + s0) & 1) == 0)) {
-      const float2* p2 = reinterpret_cast<const float2*>(y + s0) + lane;
+    load_frame(x, y, c0, s0, N, magbuf, lane);
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-        for (int r = 0; r < 8; ++r) x[jj][r] = __ldg(p2 + 32 * jj + 64 * r);
-    } else if (interior) {  // clip starts on an odd sample: 4-byte loads
-      const float* p1 = y + s0 + 2 * lane;
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-          x[jj][r] = make_float2(__ldg(p1 + 64 * jj + 128 * r), __ldg(p1 + 64 * jj + 128 * r + 1));
-    } else {  // first / last frames of a clip: reflect padding, staged through the warp's buffer
-#pragma unroll 1
-      for (int i = lane; i < NFFT; i += 32) magbuf[i] = __ldg(y + reflect_index(s0 + i, N));
-      __syncwarp();
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-        for (int r = 0; r < 8; ++r) x[jj][r] = buf[lane + 32 * jj + 64 * r];
-      __syncwarp();
-    }
-    // ---- pass 1 (Ns = 1): window, 8-point DFTs without twiddles (k = j % 1 = 0)
-#pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      const int j = lane + 32 * jj;
+    for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const float2 wn = s_win[j + 64 * r];
+        const float2 wn = s_win[lane + 32 * jj + 64 * r];
         x[jj][r] = make_float2(x[jj][r].x * wn.x, x[jj][r].y * wn.y);
       }
-      fft8(x[jj]);
-      const int b1 = 8 * j + (j >> 1);  // pad(8 j + r) = 8 j + (j >> 1) + r
-#pragma unroll
-      for (int r = 0; r < 8; ++r) buf[b1 + r] = x[jj][r];
-    }
-    __syncwarp();
-    // ---- passes 2, 3 (Ns = 8, 64): all reads, then all writes, in place
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int Ns = pass ? 64 : 8;
-      float2 v[2][8];
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j = lane + 32 * jj, k = j % Ns;
-        const int jp = pad(j);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float2 xx = buf[jp + 68 * r];  // pad(j + 64 r)
-          v[jj][r] = r ? cmul(xx, pass ? s_tw64[(r - 1) * 64 + k] : s_tw8[k * 9 + r]) : xx;
-        }
-        fft8(v[jj]);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j = lane + 32 * jj, k = j % Ns;
-        const int j0 = (j / Ns) * Ns * 8 + k;  // a multiple of 64 plus k < Ns
-        const int jp = pad(j0 - k) + pad(k);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) buf[jp + pad(r * Ns)] = v[jj][r];  // = pad(j0 + r Ns): no carries between the terms
-      }
-      __syncwarp();
-    }
+    warp_fft512(x, buf, s_tw8, s_tw64, lane);
     // ---- real-FFT split + magnitude: bins k = lane + 32 t (t < 8) together with 512 - k; k = 256 on lane 0.
     //      X[k] = (e - i w o) / 2 with e = z[k] + conj z[512-k], o = z[k] - conj z[512-k], w = exp(-2 pi i k / 1024);
     //      the mirrored bin has e' = conj e, o' = -conj o, w' = -conj w.
@@ -272,18 +160,6 @@ __global__ void __launch_bounds__(mel::WARPS * 32, 3)
 
 using namespace ftb;
 
-struct ftb_mel_handle {
-  ftb_mel_config cfg;
-  int device = 0;
-  std::vector<void*> owned;
-  std::vector<float> fb_host;  // dense (n_mels, 513)
-  int smem = 0;                // dynamic shared memory of the kernel (tables + per-warp buffers)
-  MelTables tb;
-  ~ftb_mel_handle() {
-    for (void* p : owned) cudaFree(p);
-  }
-};
-
 namespace {
 
 double hz_to_mel(double f) {  // Slaney (librosa htk=False)
@@ -330,6 +206,89 @@ int upload(ftb_mel_handle* h, const std::vector<T>& v, const T** out) {
   return FTB_OK;
 }
 
+// Tables of the inverse path (griffin_lim.cu): A as CSR / CSC, the pseudo-inverse A^T (A A^T)^-1 (the start of the NNLS,
+// librosa.util.nnls: clipped least-squares solution) and the step 1 / lambda_max(A A^T) of the projected-gradient NNLS.
+int build_inverse_tables(ftb_mel_handle* h) {
+  const int nm = h->cfg.num_mels, nb = mel::NBINS;
+  const float* A = h->fb_host.data();
+  std::vector<int> row_ptr(nm + 1, 0), row_col, col_ptr(nb + 1, 0), col_row;
+  std::vector<float> row_val, col_val;
+  for (int i = 0; i < nm; ++i) {
+    for (int k = 0; k < nb; ++k)
+      if (A[(size_t)i * nb + k] != 0.f) row_col.push_back(k), row_val.push_back(A[(size_t)i * nb + k]);
+    row_ptr[i + 1] = (int)row_col.size();
+  }
+  for (int k = 0; k < nb; ++k) {
+    for (int i = 0; i < nm; ++i)
+      if (A[(size_t)i * nb + k] != 0.f) col_row.push_back(i), col_val.push_back(A[(size_t)i * nb + k]);
+    col_ptr[k + 1] = (int)col_row.size();
+  }
+  // G = A A^T (double), Cholesky G = L L^T, G^-1 by solving against the identity, P = A^T G^-1
+  std::vector<double> G((size_t)nm * nm, 0.0), Lc((size_t)nm * nm, 0.0), Ginv((size_t)nm * nm, 0.0);
+  for (int i = 0; i < nm; ++i)
+    for (int j = 0; j < nm; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < nb; ++k) acc += (double)A[(size_t)i * nb + k] * A[(size_t)j * nb + k];
+      G[(size_t)i * nm + j] = acc;
+    }
+  for (int i = 0; i < nm; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double acc = G[(size_t)i * nm + j];
+      for (int k = 0; k < j; ++k) acc -= Lc[(size_t)i * nm + k] * Lc[(size_t)j * nm + k];
+      if (i == j) {
+        FTB_REQUIRE(acc > 0.0, FTB_ERR_UNSUPPORTED, "ftb_mel_create: the mel filterbank has dependent rows (row %d); "
+                    "the inverse path needs a full-rank filterbank", i);
+        Lc[(size_t)i * nm + i] = std::sqrt(acc);
+      } else {
+        Lc[(size_t)i * nm + j] = acc / Lc[(size_t)j * nm + j];
+      }
+    }
+  for (int c = 0; c < nm; ++c) {  // solve L L^T x = e_c
+    std::vector<double> y(nm, 0.0), x(nm, 0.0);
+    for (int i = 0; i < nm; ++i) {
+      double acc = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) acc -= Lc[(size_t)i * nm + k] * y[k];
+      y[i] = acc / Lc[(size_t)i * nm + i];
+    }
+    for (int i = nm - 1; i >= 0; --i) {
+      double acc = y[i];
+      for (int k = i + 1; k < nm; ++k) acc -= Lc[(size_t)k * nm + i] * x[k];
+      x[i] = acc / Lc[(size_t)i * nm + i];
+    }
+    for (int i = 0; i < nm; ++i) Ginv[(size_t)i * nm + c] = x[i];
+  }
+  std::vector<float> pinv((size_t)nb * nm);
+  for (int k = 0; k < nb; ++k)
+    for (int j = 0; j < nm; ++j) {
+      double acc = 0.0;
+      for (int i = 0; i < nm; ++i) acc += (double)A[(size_t)i * nb + k] * Ginv[(size_t)i * nm + j];
+      pinv[(size_t)k * nm + j] = (float)acc;
+    }
+  std::vector<double> v(nm, 1.0), w(nm);  // power iteration for lambda_max(G)
+  double lam = 1.0;
+  for (int it = 0; it < 200; ++it) {
+    double nrm = 0.0;
+    for (int i = 0; i < nm; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < nm; ++j) acc += G[(size_t)i * nm + j] * v[j];
+      w[i] = acc;
+      nrm += acc * acc;
+    }
+    lam = std::sqrt(nrm);
+    for (int i = 0; i < nm; ++i) v[i] = w[i] / lam;
+  }
+  FTB_TRY(upload(h, row_ptr, &h->inv.row_ptr));
+  FTB_TRY(upload(h, row_col, &h->inv.row_col));
+  FTB_TRY(upload(h, row_val, &h->inv.row_val));
+  FTB_TRY(upload(h, col_ptr, &h->inv.col_ptr));
+  FTB_TRY(upload(h, col_row, &h->inv.col_row));
+  FTB_TRY(upload(h, col_val, &h->inv.col_val));
+  FTB_TRY(upload(h, pinv, &h->inv.pinv));
+  h->inv.inv_lipschitz = (float)(1.0 / (lam * 1.01));
+  h->inv.n_mels = nm;
+  return FTB_OK;
+}
+
 }  // namespace
 
 extern "C" int ftb_mel_create(const ftb_mel_config* cfg, int device, ftb_mel_handle** out) {
@@ -345,19 +304,8 @@ extern "C" int ftb_mel_create(const ftb_mel_config* cfg, int device, ftb_mel_han
   h->cfg = *cfg;
   h->device = device;
   auto build = [&]() -> int {
-    const double PI = 3.14159265358979323846;
-    std::vector<float> win(mel::NFFT);
-    for (int n = 0; n < mel::NFFT; ++n) win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / mel::NFFT));
-    std::vector<float2> tw8(8 * 9, make_float2(1.f, 0.f)), tw64(7 * 64), w1024(257), win2(mel::NC);
-    for (int m = 0; m < mel::NC; ++m) win2[m] = make_float2(win[2 * m], win[2 * m + 1]);
-    for (int k = 0; k < 8; ++k)
-      for (int r = 0; r < 8; ++r)
-        tw8[k * 9 + r] = make_float2((float)std::cos(2 * PI * r * k / 64), (float)-std::sin(2 * PI * r * k / 64));
-    for (int r = 1; r < 8; ++r)
-      for (int k = 0; k < 64; ++k)
-        tw64[(r - 1) * 64 + k] = make_float2((float)std::cos(2 * PI * r * k / 512), (float)-std::sin(2 * PI * r * k / 512));
-    for (int k = 0; k < 257; ++k)
-      w1024[k] = make_float2((float)std::cos(2 * PI * k / 1024), (float)-std::sin(2 * PI * k / 1024));
+    const FftTablesHost ft;
+    const std::vector<float2>&win2 = ft.win2, &tw8 = ft.tw8, &tw64 = ft.tw64, &w1024 = ft.w1024;
     h->fb_host = mel_filterbank(cfg->sample_rate, cfg->n_fft, cfg->num_mels, cfg->fmin, cfg->fmax);
     // virtual rows: the support of every mel row cut into pieces of VL taps
     std::vector<int> vstart, rfirst(cfg->num_mels), rcnt(cfg->num_mels);
@@ -395,6 +343,7 @@ extern "C" int ftb_mel_create(const ftb_mel_config* cfg, int device, ftb_mel_han
     h->tb.n_mels = cfg->num_mels;
     h->tb.nvrp = nvrp;
     h->tb.hop = cfg->hop_length;
+    FTB_TRY(build_inverse_tables(h));
     h->smem = (72 + 448 + 258 + mel::NC + mel::WARPS * mel::NCP) * (int)sizeof(float2) +
               (mel::VL * nvrp + nvrp + 2 * cfg->num_mels) * 4;
     FTB_CHECK_CUDA(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));

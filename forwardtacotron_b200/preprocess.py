@@ -1,10 +1,11 @@
 """Mel featurisation of a folder of wavs on the GPU: the step either side of ``DSP.wav_to_mel`` in the reference's
-``preprocess.py`` (:41-76): load -> peak scaling (:70-73) -> ``wav_to_mel`` (:76) -> ``np.save(mel/{id}.npy)`` (:44,
-float32 ``(n_mels, frames)``).  The reference runs one file per ``multiprocessing`` worker; here all clips of a chunk
-go through ONE kernel launch (``DSP.wav_to_mel_batch``).
+``preprocess.py`` (:41-76): load -> start / end silence trimming (:66-67, ``DSP.trim_silence``) -> peak scaling
+(:70-73) -> ``wav_to_mel`` (:76) -> ``np.save(mel/{id}.npy)`` (:44, float32 ``(n_mels, frames)``).  The reference runs
+one file per ``multiprocessing`` worker; here all clips of a chunk go through ONE trim launch and ONE mel launch.
 
-Outside this module (CPU-only upstream, third-party): resampling on load (librosa), silence trimming
-(librosa.effects.trim / webrtcvad), WORLD pitch (:79-80), quantised waveforms for WaveRNN (:83-90), text cleaning.
+Outside this module (CPU-only upstream, third-party): resampling on load (librosa / resampy), the webrtcvad
+long-silence trimmer (:64-65; off in config.yaml), WORLD pitch (:79-80), quantised waveforms for WaveRNN (:83-90),
+text cleaning.
 
     python -m forwardtacotron_b200.preprocess --path wavs/ --out data/ [--config config.yaml]
 """
@@ -41,6 +42,17 @@ def peak_scale(y: np.ndarray, should_peak_norm: bool) -> np.ndarray:
     return y
 
 
+def trim_clips(clips: List[np.ndarray], dsp: DSP) -> List[np.ndarray]:
+    """``DSP.trim_silence`` (preprocess.py:66-67) over a list of clips in one launch."""
+    import torch
+    dev = dsp._default_device()
+    offs = torch.zeros(len(clips) + 1, dtype=torch.int64)
+    offs[1:] = torch.cumsum(torch.tensor([len(c) for c in clips]), 0)
+    flat = torch.from_numpy(np.concatenate(clips).astype(np.float32, copy=False)).pin_memory().to(dev, non_blocking=True)
+    b = dsp.trim_bounds(flat, offs).cpu().tolist()
+    return [c[s:e] for c, (s, e) in zip(clips, b)]
+
+
 def featurize(paths: Iterable[Path], dsp: DSP, out_dir: Path, chunk: int = 256) -> List[Tuple[str, int]]:
     """wav files -> ``out_dir/mel/{stem}.npy``; returns [(id, frames)] like the reference's dataset list
     (preprocess.py:49, 148)."""
@@ -49,7 +61,12 @@ def featurize(paths: Iterable[Path], dsp: DSP, out_dir: Path, chunk: int = 256) 
     done: List[Tuple[str, int]] = []
     for i in range(0, len(paths), chunk):
         part = paths[i:i + chunk]
-        clips = [peak_scale(load_wav(p, dsp.sample_rate), dsp.should_peak_norm) for p in part]
+        clips = [load_wav(p, dsp.sample_rate) for p in part]
+        if dsp.should_trim_long_silences:
+            raise NotImplementedError('trim_long_silences needs webrtcvad (CPU, third-party); set it to false')
+        if dsp.should_trim_start_end_silence:
+            clips = trim_clips(clips, dsp)
+        clips = [peak_scale(y, dsp.should_peak_norm) for y in clips]
         mels = dsp.wav_to_mel_batch(clips)
         for p, m in zip(part, mels):
             m = np.asarray(m, dtype=np.float32)

@@ -8,8 +8,10 @@ framing, Hann window, 1024-point real FFT, magnitude, Slaney mel filterbank and 
 Beyond the reference surface, ``wav_to_mel_batch`` featurises many clips in ONE launch (the reference
 reaches the same thing with a multiprocessing pool over files, preprocess.py:129-139) and
 ``wav_to_mel`` also accepts CUDA tensors so audio already resident in HBM is not copied back and forth.
-The file I/O, silence trimming, VAD, mu-law and Griffin-Lim helpers of the reference class are outside
-the hot path and are not re-implemented here.
+The steps either side of that path are GPU kernels as well (csrc/griffin_lim.cu): ``griffinlim`` (mel -> NNLS linear
+spectrogram -> 32 Griffin-Lim iterations, utils/dsp.py:89-103) and ``trim_silence`` (librosa.effects.trim,
+utils/dsp.py:112-113).  File I/O, the webrtcvad long-silence trimmer and the mu-law helpers of the reference class are
+CPU code outside this package.
 """
 from __future__ import annotations
 
@@ -155,6 +157,86 @@ class DSP:
 
     def wav_to_mel(self, y: Union[np.ndarray, torch.Tensor], normalize=True) -> Union[np.ndarray, torch.Tensor]:
         return self.wav_to_mel_batch([y], normalize)[0]
+
+    # ------------------------------------------------------------------ the inverse path
+    def mel_to_stft(self, mel, denormalize: bool = False, iters: int = 64):
+        """``librosa.feature.inverse.mel_to_stft(M, power=1, ...)``: (n_mels, F) mel magnitudes (log-mels when
+        ``denormalize``) -> (1 + n_fft//2, F) non-negative linear magnitudes.  numpy in -> numpy out."""
+        dev = self._default_device()
+        as_numpy = not isinstance(mel, torch.Tensor)
+        m = torch.as_tensor(np.ascontiguousarray(mel), dtype=torch.float32) if as_numpy else mel.to(torch.float32)
+        m = m.to(dev).contiguous()
+        if m.dim() != 2 or m.shape[0] != self.n_mels:
+            raise ValueError(f'mel must be ({self.n_mels}, frames)')
+        F = int(m.shape[1])
+        S = torch.empty((1 + self.n_fft // 2, F), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ftb_mel_to_stft(self._handle(dev), _lib.ptr(m), F, int(bool(denormalize)), int(iters),
+                                                  _lib.ptr(S), _lib.current_stream(dev)))
+        return S.cpu().numpy() if as_numpy else S
+
+    def griffinlim_from_stft(self, S, phase_u, n_iter: int = 32, momentum: float = 0.99):
+        """``librosa.griffinlim(S, n_iter, hop_length, win_length)`` from the initial phases ``exp(2 pi i phase_u)``
+        (``phase_u``: uniform [0, 1) of S's shape -- upstream draws them from an unseeded RNG)."""
+        dev = self._default_device()
+        as_numpy = not isinstance(S, torch.Tensor)
+        St = torch.as_tensor(np.ascontiguousarray(S), dtype=torch.float32).to(dev).contiguous() if as_numpy \
+            else S.to(dev, torch.float32).contiguous()
+        u = torch.as_tensor(np.ascontiguousarray(phase_u), dtype=torch.float32).to(dev).contiguous() \
+            if not isinstance(phase_u, torch.Tensor) else phase_u.to(dev, torch.float32).contiguous()
+        if St.shape != u.shape or St.dim() != 2 or St.shape[0] != 1 + self.n_fft // 2:
+            raise ValueError('S and phase_u must both be (1 + n_fft//2, frames)')
+        F = int(St.shape[1])
+        if F < 2:
+            raise ValueError('Griffin-Lim needs at least 2 frames')
+        lib = _lib.lib()
+        ws = torch.empty(int(lib.ftb_griffinlim_workspace_bytes(F)), dtype=torch.uint8, device=dev)
+        wav = torch.empty(self.hop_length * (F - 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.ftb_griffinlim(self._handle(dev), _lib.ptr(St), _lib.ptr(u), F, int(n_iter), float(momentum),
+                                          _lib.ptr(wav), _lib.ptr(ws), ws.numel(), _lib.current_stream(dev)))
+        return wav.cpu().numpy() if as_numpy else wav
+
+    def griffinlim(self, mel, n_iter: int = 32, seed=None):
+        """utils/dsp.py:89-103: log-mel (n_mels, F) -> waveform of hop * (F - 1) samples.  ``seed`` fixes the random
+        initial phases (None = fresh ones per call, like upstream)."""
+        dev = self._default_device()
+        S = self.mel_to_stft(mel, denormalize=True)
+        shape = S.shape
+        g = None
+        if seed is not None:
+            g = torch.Generator(device=dev)
+            g.manual_seed(int(seed))
+        u = torch.rand(shape, generator=g, device=dev, dtype=torch.float32)
+        return self.griffinlim_from_stft(S, u if isinstance(S, torch.Tensor) else u.cpu().numpy(), n_iter)
+
+    def trim_bounds(self, audio: torch.Tensor, clip_offsets: torch.Tensor) -> torch.Tensor:
+        """librosa.effects.trim over clips packed back to back on the GPU -> (n_clips, 2) int64 [start, end) per clip."""
+        if not audio.is_cuda:
+            raise RuntimeError('trim_bounds expects audio resident on the GPU')
+        dev = audio.device
+        offs_cpu = clip_offsets.detach().to('cpu', torch.int64)
+        lens = offs_cpu[1:] - offs_cpu[:-1]
+        if len(lens) == 0 or int(lens.min()) < 1:
+            raise ValueError('empty clip')
+        n, mx, hop = len(lens), int(lens.max()), 512
+        offs = offs_cpu.pin_memory().to(dev, non_blocking=True)
+        ws = torch.empty(n * (1 + mx // hop), dtype=torch.float32, device=dev)
+        bounds = torch.empty((n, 2), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ftb_trim_silence(_lib.ptr(audio.to(torch.float32).contiguous()), _lib.ptr(offs), n, mx,
+                                                   float(self.trim_silence_top_db), 2048, hop, _lib.ptr(bounds),
+                                                   _lib.ptr(ws), ws.numel() * 4, _lib.current_stream(dev)))
+        return bounds
+
+    def trim_silence(self, wav):
+        """utils/dsp.py:112-113: cut leading / trailing frames more than ``trim_silence_top_db`` dB below the loudest."""
+        dev = self._default_device()
+        as_numpy = not isinstance(wav, torch.Tensor)
+        t = torch.as_tensor(np.ascontiguousarray(wav), dtype=torch.float32) if as_numpy else wav.to(torch.float32)
+        d = t.to(dev).contiguous()
+        b = self.trim_bounds(d, torch.tensor([0, d.numel()])).cpu()
+        return wav[int(b[0, 0]):int(b[0, 1])]
 
     def normalize(self, mel: np.ndarray) -> np.ndarray:
         mel = np.clip(mel, a_min=1.e-5, a_max=None)

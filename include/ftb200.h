@@ -222,6 +222,28 @@ int ftb_mel_run(ftb_mel_handle* h, const float* audio, const int64_t* clip_offse
 /* Copies the (num_mels, 1 + n_fft/2) f32 filterbank the handle uses to HOST memory. */
 int ftb_mel_filterbank(ftb_mel_handle* h, float* host_out);
 
+/* DSP.griffinlim, utils/dsp.py:89-103 (the step after generate in gen_forward.py:132-134), in its two library calls:
+ * ftb_mel_to_stft = librosa.feature.inverse.mel_to_stft(exp(mel), power=1): mel (n_mels, n_frames) f32 (log-mel when
+ *   denormalize != 0) -> S_out (1 + n_fft/2, n_frames) f32 >= 0 minimising ||A S - M||^2 (non-negative least squares from
+ *   the clipped least-squares start, `iters` accelerated projected-gradient steps; 0 = 64).  The minimiser is not unique;
+ *   the objective reached is at or below the reference's L-BFGS-B result.
+ * ftb_griffinlim = librosa.griffinlim(S, n_iter, hop, win) with momentum (0.99 upstream) and init='random': the
+ *   reference draws the initial phases from an unseeded RNG, so the caller passes them: phase_u (1 + n_fft/2, n_frames)
+ *   f32 uniform in [0, 1), angles0 = exp(2 pi i u).  wav_out: hop * (n_frames - 1) f32 samples (istft with center=True,
+ *   length=None). */
+int ftb_mel_to_stft(ftb_mel_handle* h, const float* mel, int n_frames, int denormalize, int iters, float* S_out,
+                    void* stream);
+int64_t ftb_griffinlim_workspace_bytes(int n_frames);
+int ftb_griffinlim(ftb_mel_handle* h, const float* S, const float* phase_u, int n_frames, int n_iter, float momentum,
+                   float* wav_out, void* workspace, int64_t workspace_bytes, void* stream);
+/* DSP.trim_silence = librosa.effects.trim(wav, top_db, frame_length=2048, hop_length=512), utils/dsp.py:112-113, for
+ * clips packed back to back (clip_offsets as in ftb_mel_run; max_clip_samples = the longest clip): bounds (n_clips, 2)
+ * int64 receives [start, end) of the non-silent region of every clip in samples relative to the clip (0, 0 when every
+ * frame is below the threshold).  workspace: n_clips * (1 + max_clip_samples / hop_length) floats. */
+int ftb_trim_silence(const float* audio, const int64_t* clip_offsets, int n_clips, int max_clip_samples, float top_db,
+                     int frame_length, int hop_length, int64_t* bounds, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Model level: ForwardTacotron.generate, models/forward_tacotron.py:244-330
  * ------------------------------------------------------------------------- */

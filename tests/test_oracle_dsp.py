@@ -47,3 +47,28 @@ def test_unnormalized_and_short_clip():
     lin = dsp_oracle.wav_to_mel(y, normalize=False)
     assert lin.shape == (80, 1 + 700 // 256) and (lin >= 0).all()
     assert np.allclose(np.log(np.clip(lin, 1e-5, None)), dsp_oracle.wav_to_mel(y), atol=1e-6)
+
+
+def test_inverse_path_restatements_are_self_consistent():
+    """istft(stft(y)) == y, stft / istft agree with torch's implementations, NNLS fits its target, trim bounds hold."""
+    import torch
+    from oracle import dsp_oracle as d
+    rng = np.random.default_rng(0)
+    y = (0.1 * rng.standard_normal(22050)).astype(np.float32)
+    S = d.stft(y)
+    yr = d.istft(S)
+    assert len(yr) == 256 * (S.shape[1] - 1) and np.abs(yr - y[:len(yr)]).max() < 1e-6
+    win = torch.hann_window(1024, periodic=True)
+    St = torch.stft(torch.from_numpy(y), 1024, 256, 1024, window=win, center=True, pad_mode='reflect', return_complex=True)
+    assert np.abs(St.numpy() - S).max() < 1e-5
+    yt = torch.istft(St, 1024, 256, 1024, window=win, center=True).numpy()
+    assert np.abs(yt - yr[:len(yt)]).max() < 1e-6
+    M = np.exp(d.wav_to_mel(y)).astype(np.float32)
+    X = d.mel_to_stft(M)
+    A = d.mel_filterbank(22050, 1024, 80, 0, 8000)
+    assert X.min() >= 0 and np.abs(A @ X - M).max() < 1e-2 * M.max()
+    yy = np.concatenate([np.zeros(5000, np.float32), y, np.zeros(7000, np.float32)])
+    cut, (s, e) = d.trim_silence(yy, 60)
+    assert (s, e) == (4096, 28160) and len(cut) == e - s
+    w = d.griffinlim(np.abs(S), np.exp(2j * np.pi * rng.random(S.shape)), n_iter=4)
+    assert w.shape == yr.shape and np.isfinite(w).all()
