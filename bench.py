@@ -388,7 +388,7 @@ def _agree(torch, dist, dev, ok: bool) -> bool:
 
 
 def sharded_corpus_extra(torch, dist, model, dev, world):
-    """N > 1: the path's one exchange step.  A corpus of 96 x world utterances is bucketed,
+    """N > 1: the path's one exchange step.  A corpus of 256 x world utterances is bucketed,
     sharded over the ranks, synthesised (ragged batches, 3 in flight) and collected on rank 0 three ways:
       none        -- no exchange: every rank keeps its results (what the exchange is measured against)
       nccl        -- exact-size grouped ncclSend / ncclRecv to rank 0 (utils/batching.gather_mels)
@@ -397,7 +397,7 @@ def sharded_corpus_extra(torch, dist, model, dev, world):
     from forwardtacotron_b200.utils import batching
     from forwardtacotron_b200.utils.peer_window import PeerWindow
     g = torch.Generator().manual_seed(3)
-    n = 96 * world
+    n = 256 * world
     utts = [torch.randint(1, 135, (int(k),), generator=g).tolist() for k in torch.randint(40, 200, (n,), generator=g)]
     window = PeerWindow(min(8 << 30, (1 << 30) * world))
     res, frames, err = {}, 0, None

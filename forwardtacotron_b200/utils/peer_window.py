@@ -117,10 +117,16 @@ class PeerWindow:
         if self.rank != self.dst:
             return None
         out: List[Optional[torch.Tensor]] = [None] * n_total
-        for meta in metas:
+        for r, meta in enumerate(metas):
+            if not meta:
+                continue
+            # ONE copy per producing rank (the used part of its region), then views: the results survive reset()
+            lo = r * self.region
+            hi = max(off + shape[0] * shape[1] * shape[2] * 4 for off, shape, _, _ in meta)
+            keep = self._view[lo:hi].clone()
             for off, shape, rows, frames in meta:
                 n = shape[0] * shape[1] * shape[2]
-                t = self._view[off:off + n * 4].view(torch.float32).view(*shape)
-                for r, (i, f) in enumerate(zip(rows, frames)):
-                    out[i] = t[r, :, :f].clone()
+                t = keep[off - lo:off - lo + n * 4].view(torch.float32).view(*shape)
+                for row, (i, f) in enumerate(zip(rows, frames)):
+                    out[i] = t[row, :, :f]
         return out
