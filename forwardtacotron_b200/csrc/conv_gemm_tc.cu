@@ -115,7 +115,6 @@ struct alignas(64) TcArgs {
   CUtensorMap map_a;  // (Cin, S, B) bf16, box 64 x box_rows x 1
   TcProb prob[tc::MAXP];
   int nprob, B, S, Cin, cblocks;
-  int cin_valid;  // channels that carry data (the rest of Cin is zero padding in x AND w): all-zero 16-wide k-steps are skipped
   int m_tiles, m_stride, box_rows, bn, total_tiles, pool, highway, fp16;
   int split_in;   // A holds 3 bf16 parts [hi | mid | lo] of an fp32 tensor; K loop = 6 part products (see conv_gemm_group)
   uint32_t amap;  // K segment `seg` (one full pass over taps x channel blocks) reads activation part (amap >> 4 seg) & 15
@@ -276,27 +275,22 @@ template <int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr bool HIGHWAY = MODE == 1, SPLIT = MODE == 2;
   using namespace tc;
-  // The highway epilogue stages BOTH halves (W1 x, W2 x) of a 32-channel group, so it takes two staging buffers per
-  // warp and gives one pipeline stage back (its GEMMs have K = 256 = 4 k-blocks per tile: 3 stages lose nothing).
-  constexpr int NST = HIGHWAY ? 3 : STAGES;
-  constexpr int TILES_BYTES = NST * STAGE_BYTES, STAGING_BYTES = (HIGHWAY ? 2 : 1) * SMEM_STAGING;
-  static_assert(TILES_BYTES + STAGING_BYTES + 1024 + 256 <= SMEM_BYTES, "shared memory layout of this mode");
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B tiles need 1024-byte alignment (offset arithmetic keeps the pointer in the shared space)
   unsigned char* tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  float* staging_all = reinterpret_cast<float*>(tiles + TILES_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TILES_BYTES + STAGING_BYTES);
-  // full[NST], empty[NST], tfull[2], tempty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
+  float* staging_all = reinterpret_cast<float*>(tiles + SMEM_TILES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + SMEM_TILES + SMEM_STAGING);
+  // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const uint32_t tiles_u32 = smem_u32(tiles);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NST), tfull0 = smem_u32(bars + 2 * NST),
-                 tempty0 = smem_u32(bars + 2 * NST + 2);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
+                 tempty0 = smem_u32(bars + 2 * STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map_a) : "memory");
-    for (int i = 0; i < NST; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       mbar_init(full0 + 8 * i, 1);
       mbar_init(empty0 + 8 * i, 1);
     }
@@ -331,8 +325,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         const uint32_t amap = a.amap;
         int j = 0, cb = 0, seg = 0;
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
-          const uint32_t st = it % NST;
-          if (it >= NST) mbar_wait(empty0 + 8 * st, ((it / NST) - 1) & 1);
+          const uint32_t st = it % STAGES;
+          if (it >= STAGES) mbar_wait(empty0 + 8 * st, ((it / STAGES) - 1) & 1);
           const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
           mbar_expect_tx(full0 + 8 * st, tx);
           const int acb = cb + (int)((amap >> (4 * seg)) & 15u) * a.cblocks;
@@ -365,8 +359,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
             const uint32_t d_unit = tmem_base + ub * BN_MAX;
             const int kend = split_unit_end(kb, P.nkb, a.split_d, a.split_ds);
             for (bool first = true; kb < kend; ++kb, ++it, first = false) {
-              const uint32_t st = it % NST;
-              mbar_wait(full0 + 8 * st, (it / NST) & 1);
+              const uint32_t st = it % STAGES;
+              mbar_wait(full0 + 8 * st, (it / STAGES) & 1);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
@@ -383,15 +377,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + buf * BN_MAX;
         for (int kb = 0; kb < P.nkb; ++kb, ++it) {
-          const uint32_t st = it % NST;
-          mbar_wait(full0 + 8 * st, (it / NST) & 1);
+          const uint32_t st = it % STAGES;
+          mbar_wait(full0 + 8 * st, (it / STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
-          // a 64-channel block whose tail is zero padding (postnet: 80 mel channels in 128) needs only its leading k-steps
-          const int nk = min(BK / 16, (a.cin_valid - (kb % a.cblocks) * BK + 15) >> 4);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            if (k < nk) umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty0 + 8 * st);  // frees the smem stage when these MMAs retire
         }
         umma_commit(tfull0 + 8 * buf);  // accumulator complete
@@ -399,8 +391,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
     }
   } else {  // ===== epilogue warps 2..9 =====
     const int ew = warp - 2, q = warp & 3, half = ew >> 2;  // TMEM lane quarter, column half
-    float* stg = staging_all + (half * 4 + q) * (HIGHWAY ? 2 : 1) * 32 * STG_LD;
-    const float* stg_prev = staging_all + (half * 4 + (q > 0 ? q - 1 : 0)) * 32 * STG_LD;  // pool halo row (generic mode)
+    float* stg = staging_all + (half * 4 + q) * 32 * STG_LD;
+    const float* stg_prev = staging_all + (half * 4 + (q > 0 ? q - 1 : 0)) * 32 * STG_LD;  // pool halo row
     const bool has_o32 = a.out_f32 != nullptr, has_o16 = a.out_bf16 != nullptr, has_ot = a.out_t != nullptr;
     const bool has_r32 = a.res_f32 != nullptr, has_r16 = a.res_bf16 != nullptr;
     const bool row_major = has_o32 || has_o16, pool = a.pool != 0;
@@ -475,8 +467,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         continue;
       }
       // operands of the epilogue that do not depend on the accumulator are fetched while the MMAs still run
+      uint4 xin_next[4];
       float res_next[32];
       const bool pre_res = (has_r16 || has_r32) && row_major && !pool && !HIGHWAY;
+#define FTB_LOAD_HW_RES(pr)                                                                                             \
+  if (lane < nrows) {                                                                                                   \
+    const uint4* xr = reinterpret_cast<const uint4*>(a.res_bf16 + (mrow0 + lane) * ldr + (c.n0 >> 1) + (pr) * 32);      \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) xin_next[i] = __ldg(xr + i);                                          \
+  }
 #define FTB_LOAD_RES(ch)                                                                                                \
   {                                                                                                                     \
     const int n_ = c.n0 + (ch) * 32 + lane;                                                                             \
@@ -484,56 +482,49 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
     if (has_r16) load_res_rows<2>(res_next, nullptr, a.res_bf16 + mrow0 * ldr + n_, ldr, nr_, a.fp16 != 0);             \
     else load_res_rows<1>(res_next, a.res_f32 + mrow0 * ldr + n_, nullptr, ldr, nr_, false);                            \
   }
-      // highway: the layer input x (the "residual" of the gate mix) of output channels oc0 + lane, rows of this quarter
-#define FTB_LOAD_HW_RES(pr)                                                                                             \
-  load_res_rows<2>(res_next, nullptr, a.res_bf16 + mrow0 * ldr + (c.n0 >> 1) + (pr) * 32 + lane, ldr, nrows, a.fp16 != 0);
-      if (HIGHWAY && half < (nchunks >> 1)) FTB_LOAD_HW_RES(half)
+      if (HIGHWAY) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xin_next[i] = make_uint4(0, 0, 0, 0);
+        if (half < (nchunks >> 1)) FTB_LOAD_HW_RES(half)
+      }
       if (pre_res && half < nchunks) FTB_LOAD_RES(half)
       mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       bool released = false;
       if (HIGHWAY) {
         // Highway layer (models/common_layers.py:30-35): columns come in groups of 64 = [32 x (W1 x + b1) | 32 x (W2 x + b2)]
-        // of the SAME 32 channels (weights interleaved at pack time).  Both halves are staged through shared memory and
-        // the gate mix y = g relu(x1) + (1 - g) x, g = sigmoid(x2), runs in the TRANSPOSED layout (lane = channel, loop over
-        // rows): the two biases sit in registers, x and y move as coalesced 64-byte rows, and an output costs ~16
-        // instructions instead of the ~37 of the accumulator-layout version (per-element uniform bias loads, a second
-        // pass for the transposed store; profiles/r01_highway_v4.txt: 23.1 M warp instructions per launch).
-        float* stg2 = stg + 32 * STG_LD;
+        // of the SAME 32 channels (weights interleaved at pack time); y = g relu(x1) + (1 - g) x, g = sigmoid(x2),
+        // is formed in the accumulator layout (thread = row), then transposed for the coalesced bf16 store.
         const int npairs = nchunks >> 1;
         for (int pr = half; pr < npairs; pr += 2) {
-          {  // one half at a time: r1 + r2 + the prefetched x rows would not fit the 168-register cap
-            const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX + pr * 64;
-            uint32_t r[32];
-            tmem_ld32(tcol, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t r1[32], r2[32];
+          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX + pr * 64;
+          tmem_ld32(tcol, r1);
+          tmem_ld32(tcol + 32, r2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (pr + 2 >= npairs) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            released = true;
+          }
+          const int nb1 = c.n0 + pr * 64, oc0 = (c.n0 >> 1) + pr * 32;  // GEMM column of x1[0], output channel 0 of the pair
+          uint4 xin[4];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = __uint_as_float(r[i]);
-            tmem_ld32(tcol + 32, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (pr + 2 >= npairs) {
-              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-              if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
-              released = true;
-            }
+          for (int i = 0; i < 4; ++i) xin[i] = xin_next[i];
+          if (pr + 2 < npairs) FTB_LOAD_HW_RES(pr + 2)  // in flight during this pair's gate maths
+          const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xin);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) stg2[lane * STG_LD + i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i) {
+            const float x1 = __uint_as_float(r1[i]) + __ldg(P.bias + nb1 + i);
+            const float x2 = __uint_as_float(r2[i]) + __ldg(P.bias + nb1 + 32 + i);
+            const float g = __fdividef(1.f, 1.f + __expf(-x2));
+            stg[lane * STG_LD + i] = g * fmaxf(x1, 0.f) + (1.f - g) * ld16(xb[i], a.fp16 != 0);
           }
           __syncwarp();
-          const int nb1 = c.n0 + pr * 64, oc = (c.n0 >> 1) + pr * 32 + lane;  // GEMM column of x1[0]; this lane's output channel
-          const float b1 = __ldg(P.bias + nb1 + lane), b2 = __ldg(P.bias + nb1 + 32 + lane);
-          __nv_bfloat16* o16 = a.out_bf16 + mrow0 * ldo + oc;
-          const float *s1 = stg + lane, *s2 = stg2 + lane;
-          const bool f16o = a.fp16 != 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < nrows) {
-              const float x1 = s1[j * STG_LD] + b1, x2 = s2[j * STG_LD] + b2;
-              const float g = __fdividef(1.f, 1.f + __expf(-x2));
-              o16[j * ldo] = cvt16(fmaf(g, fmaxf(x1, 0.f) - res_next[j], res_next[j]), f16o);  // g relu(x1) + (1 - g) x
-            }
-          }
-          if (pr + 2 < npairs) FTB_LOAD_HW_RES(pr + 2)
+          __nv_bfloat16* o16 = a.out_bf16 + mrow0 * ldo + oc0 + lane;
+          const float* sp = stg + lane;
+#pragma unroll 8
+          for (int rr = 0; rr < nrows; ++rr) o16[rr * ldo] = cvt16(sp[rr * STG_LD], a.fp16 != 0);
           __syncwarp();
         }
       }
@@ -667,7 +658,6 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.S = S;
   a.Cin = Cin;
   a.cblocks = Cin / BK;
-  a.cin_valid = (o.cin_valid > 0 && o.cin_valid <= Cin) ? o.cin_valid : Cin;
   a.pool = o.pool ? 1 : 0;
   a.split_in = o.split_in ? 1 : 0;
   a.split_out = o.split_out;

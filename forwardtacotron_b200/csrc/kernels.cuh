@@ -29,7 +29,6 @@ struct TcOut {
   bool split_in = false;  // x is (B,S,3*Cin): bf16 parts hi | mid | lo of an fp32 tensor, weights packed by pack mode 3:
                           // 6 part products with fp32 accumulation = fp32-grade result on the tensor cores
   int split_out = 0;      // > 0: write the 16-bit output as 3 parts, split_out channels apart (ldo >= 3 * split_out)
-  int cin_valid = 0;      // > 0: only the first cin_valid of the Cin channels carry data (zero padding in x and w beyond)
   bool hl_in = false;     // x is (B,S,2*Cin): 16-bit parts hi | lo (rnn_bidir lo_off), weights packed by pack mode 4 / 5
                           // as [hi | hi | lo] along K: hi.hi + lo.hi + hi.lo = a 22-bit (half) / 16-bit (bf16) operand pair
   bool highway = false;  // N = 2C interleaved [32 x1 | 32 x2] groups -> y (C) = sigmoid(x2) relu(x1) + (1 - sigmoid(x2)) res_bf16

@@ -226,7 +226,6 @@ struct ModelBase {
     to.out_scale = out_scale;
     to.fp16 = std::is_same<T, f16>::value;
     to.hl_in = L.hl;
-    to.cin_valid = L.Cin;
     return conv_gemm_group((const bf16*)x, lda, B, S, L.CinP, &it, 1, to, s);
   }
 
@@ -314,7 +313,6 @@ struct ModelBase {
     o.ldo = bank_c;
     o.pool = true;
     o.fp16 = std::is_same<T, f16>::value;
-    o.cin_valid = bank[0].Cin;
     ++launches;
     ProfScope prof(FAM_GEMM_TC, flops, 0.0, s);
     return conv_gemm_group((const bf16*)x, lda, B, S, bank[0].CinP, items.data(), K, o, s);
