@@ -72,6 +72,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// smem tile -> global through the tensor map (clipped at the tensor bounds); completion tracked by bulk groups
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// two floats -> one 32-bit word of 16-bit values (x in the low half); IEEE half saturates like cvt16
+__device__ __forceinline__ uint32_t pack16x2(float x, float y, bool fp16) {
+  if (fp16) return pack_f16x2(fminf(fmaxf(x, -65504.f), 65504.f), fminf(fmaxf(y, -65504.f), 65504.f));
+  return pack_bf16x2(x, y);
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 | LBO(unused)=0 | SBO = 8 rows * 128 B = 1024 (>>4) | version 1 | layout SWIZZLE_128B (2)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -113,6 +128,9 @@ struct alignas(64) TcProb {
 static_assert(sizeof(TcProb) == 192, "TcProb layout");
 struct alignas(64) TcArgs {
   CUtensorMap map_a;  // (Cin, S, B) bf16, box 64 x box_rows x 1
+  // direct epilogue (MODE 3): row-major outputs leave through TMA stores of 32-row x 32-column boxes, (cols, S, B) maps;
+  // the *p maps have 31-row boxes (last quarter of a max-pool tile)
+  CUtensorMap map_o16, map_o16p, map_o32, map_o32p;
   TcProb prob[tc::MAXP];
   int nprob, B, S, Cin, cblocks;
   int m_tiles, m_stride, box_rows, bn, total_tiles, pool, highway, fp16;
@@ -129,7 +147,7 @@ struct alignas(64) TcArgs {
   const float* res_f32;
   const __nv_bfloat16* res_bf16;
 };
-static_assert(sizeof(TcArgs) <= 4000, "kernel parameter space");
+static_assert(sizeof(TcArgs) <= 4096 - 64, "kernel parameter space");
 
 struct TileCoord {
   int p, b, t0, n0;
@@ -466,6 +484,169 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         }
         continue;
       }
+      if (MODE == 3) {
+        // ---- direct epilogue: everything happens in the accumulator layout (thread = output row, 32 consecutive
+        // columns per TMEM read).  Per-column parameters come as uniform 16-byte loads (one L1 transaction per warp),
+        // the residual as the thread's own contiguous 64 / 128 bytes, and a row-major output is packed into a swizzled
+        // 32-row x 32-column shared-memory tile that ONE TMA store sends out (rows beyond S and columns beyond N are
+        // clipped by the tensor map).  The legacy epilogue transposes through shared memory so that lanes walk the
+        // columns and then issues a 2-byte store per element: ~10 instructions per element against ~5 here, and the
+        // K = 256 layers (highways, input projections, pre_highway, proj2) are bound by exactly that.
+        unsigned char* tile = reinterpret_cast<unsigned char*>(staging_all) + (half * 4 + q) * 4096;  // 1024-aligned
+        float* halo = staging_all + 8 * 1024 + half * 4 * 32;                                         // [q][32], pool only
+        const uint32_t tile_u32 = smem_u32(tile);
+        const bool f16o = a.fp16 != 0;
+        const int t_own = trow0 + lane;                     // time index of this thread's accumulator row
+        const int64_t m_own = mrow0 + lane;
+        const bool row_ok = t_own >= 0 && t_own < S;
+        float res[32];
+        auto load_res = [&](int ch) {
+          const int nb = c.n0 + ch * 32;
+          if (has_r16) {
+            uint4 raw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) raw[j] = make_uint4(0, 0, 0, 0);
+            if (row_ok && nb + 32 <= pN) {
+              const uint4* p = reinterpret_cast<const uint4*>(a.res_bf16 + m_own * ldr + nb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) raw[j] = __ldg(p + j);
+            } else if (row_ok) {
+              __nv_bfloat16* rb = reinterpret_cast<__nv_bfloat16*>(raw);
+              for (int i = 0; i < 32; ++i)
+                if (nb + i < pN) rb[i] = a.res_bf16[m_own * ldr + nb + i];
+            }
+            const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(raw);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) res[i] = ld16(rb[i], f16o);
+          } else if (has_r32) {
+            if (row_ok && nb + 32 <= pN) {
+              const float4* p = reinterpret_cast<const float4*>(a.res_f32 + m_own * ldr + nb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 v4 = __ldg(p + j);
+                res[4 * j] = v4.x, res[4 * j + 1] = v4.y, res[4 * j + 2] = v4.z, res[4 * j + 3] = v4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) res[i] = (row_ok && nb + i < pN) ? a.res_f32[m_own * ldr + nb + i] : 0.f;
+            }
+          }
+        };
+        const bool any_res = has_r16 || has_r32;
+        if (any_res && half < nchunks) load_res(half);
+        mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        bool released = false;
+        for (int ch = half; ch < nchunks; ch += 2) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX + ch * 32, r);
+          const int nb = c.n0 + ch * 32;  // first output column of the chunk
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ch + 2 >= nchunks) {  // last TMEM read of this warp for this tile: hand the buffer back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            released = true;
+          }
+          // ---- value transform, 4 columns at a time (uniform parameter loads)
+          float v[32];
+          const bool full = nb + 32 <= pN;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = b4;
+            if (full) {
+              if (P.bias) b4 = __ldg(reinterpret_cast<const float4*>(P.bias + nb) + j);
+              if (P.scale) s4 = __ldg(reinterpret_cast<const float4*>(P.scale + nb) + j), h4 = __ldg(reinterpret_cast<const float4*>(P.shift + nb) + j);
+            } else {
+              float* bb = &b4.x; float* ss = &s4.x; float* hh = &h4.x;
+              for (int e = 0; e < 4; ++e) {
+                const int n = nb + 4 * j + e;
+                if (n < pN) {
+                  if (P.bias) bb[e] = __ldg(P.bias + n);
+                  if (P.scale) ss[e] = __ldg(P.scale + n), hh[e] = __ldg(P.shift + n);
+                }
+              }
+            }
+            v[4 * j] = fmaf(fmaxf(__uint_as_float(r[4 * j]) + b4.x, relu_lo), s4.x, h4.x);
+            v[4 * j + 1] = fmaf(fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, relu_lo), s4.y, h4.y);
+            v[4 * j + 2] = fmaf(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, relu_lo), s4.z, h4.z);
+            v[4 * j + 3] = fmaf(fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, relu_lo), s4.w, h4.w);
+          }
+          int row_coord = trow0;       // first row of the TMA box
+          bool last_q_pool = false;
+          if (pool) {
+            // out[t + 1] = max(v[t], v[t + 1]): this thread supplies v[t] and takes v[t + 1] from the lane above (the
+            // first row of the next quarter through the halo buffer); a halo row t = -1 counts as -inf.  The tile's
+            // 128 accumulator rows yield 127 outputs: the last quarter stores 31 rows.
+            if (t_own < 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
+            }
+            if (lane == 0 && q > 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(halo + q * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // the 4 quarters of this column half
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float nx = __shfl_down_sync(0xffffffffu, v[i], 1);
+              if (lane == 31) nx = q < 3 ? halo[(q + 1) * 32 + i] : -INFINITY;
+              v[i] = fmaxf(v[i], nx);
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // halo rows consumed before the next chunk writes them
+            row_coord = trow0 + 1;
+            last_q_pool = q == 3;
+          } else if (any_res) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += res[i];
+            if (ch + 2 < nchunks) load_res(ch + 2);  // in flight while this chunk is packed and stored
+          }
+          if (out_scale != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= out_scale;
+          }
+          if (has_ot) {  // (B,N,S) output: lanes walk t (coalesced along the time axis)
+            if (row_ok) {
+              float* ot = a.out_t + ((int64_t)c.b * a.n_total + nb) * S + t_own;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (nb + i < pN) ot[(int64_t)i * S] = v[i];
+            }
+          }
+          if (has_o32) {  // 32 rows x 128 B, SWIZZLE_128B: 16-byte chunk j of row r sits at chunk position j ^ (r & 7)
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(tile + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(last_q_pool ? &a.map_o32p : &a.map_o32, tile_u32, P.n_offset + nb, row_coord, c.b);
+              tma_store_commit();
+            }
+          }
+          if (has_o16) {  // 32 rows x 64 B, SWIZZLE_64B: chunk j of row r sits at chunk position j ^ ((r >> 1) & 3)
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(tile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pack16x2(v[8 * j], v[8 * j + 1], f16o), pack16x2(v[8 * j + 2], v[8 * j + 3], f16o),
+                             pack16x2(v[8 * j + 4], v[8 * j + 5], f16o), pack16x2(v[8 * j + 6], v[8 * j + 7], f16o));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(last_q_pool ? &a.map_o16p : &a.map_o16, tile_u32, P.n_offset + nb, row_coord, c.b);
+              tma_store_commit();
+            }
+          }
+        }
+        if (!released) {  // no chunk for this warp in this tile
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+        }
+        continue;
+      }
       // operands of the epilogue that do not depend on the accumulator are fetched while the MMAs still run
       uint4 xin_next[4];
       float res_next[32];
@@ -594,6 +775,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
       }
     }
   }
+  if (MODE == 3 && warp >= 2 && lane == 0) tma_store_wait_all();  // the staging tiles are read until the stores complete
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -620,13 +802,13 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box) {
+                    const cuuint32_t* box, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   FTB_REQUIRE(fn, FTB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t elem_strides[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
-                  elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, elem_strides,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FTB_REQUIRE(r == CUDA_SUCCESS, FTB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return FTB_OK;
 }
@@ -731,8 +913,38 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
     tiles += P.n_tiles * a.m_tiles * B;
   }
   a.total_tiles = tiles;
+  // ---- direct epilogue (MODE 3): needs 16-byte aligned rows / parameter vectors; anything else takes the legacy one
+  static const int force_legacy = getenv("FTB_EPI_LEGACY") ? atoi(getenv("FTB_EPI_LEGACY")) : 0;
+  bool direct = !force_legacy && !o.highway && !o.split_in && !o.split_out;
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (o.out_bf16) direct = direct && o.ldo % 8 == 0 && al16(o.out_bf16);
+  if (o.out_f32) direct = direct && o.ldo % 4 == 0 && al16(o.out_f32);
+  if (o.res_bf16) direct = direct && o.ldr % 8 == 0 && al16(o.res_bf16);
+  if (o.res_f32) direct = direct && o.ldr % 4 == 0 && al16(o.res_f32);
+  int out_cols = 0;
+  for (int i = 0; i < n_items; ++i) {
+    direct = direct && al16(items[i].bias) && al16(items[i].scale) && al16(items[i].shift) && items[i].n_offset % 4 == 0;
+    out_cols = std::max(out_cols, items[i].n_offset + items[i].N);
+  }
+  if (direct && (o.out_bf16 || o.out_f32)) {
+    FTB_REQUIRE(out_cols <= o.ldo, FTB_ERR_INVALID, "conv_gemm_bf16: ldo=%d is smaller than n_offset + N = %d", o.ldo, out_cols);
+    for (int e = 0; e < 2; ++e) {
+      void* base = e ? (void*)o.out_f32 : (void*)o.out_bf16;
+      if (!base) continue;
+      const int esz = e ? 4 : 2;
+      cuuint64_t dims[3] = {(cuuint64_t)out_cols, (cuuint64_t)S, (cuuint64_t)B};
+      cuuint64_t strides[2] = {(cuuint64_t)o.ldo * esz, (cuuint64_t)S * o.ldo * esz};
+      for (int pv = 0; pv < (o.pool ? 2 : 1); ++pv) {
+        cuuint32_t box[3] = {32, (cuuint32_t)(pv ? 31 : 32), 1};
+        CUtensorMap* m = e ? (pv ? &a.map_o32p : &a.map_o32) : (pv ? &a.map_o16p : &a.map_o16);
+        FTB_TRY(make_map(m, base, 3, dims, strides, box, e ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                         e ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
+      }
+    }
+  }
   static bool configured = false;
   if (!configured) {
+    FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -741,6 +953,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   const int grid = std::min(tiles, sm_count());
   if (o.highway) conv_gemm_tc_kernel<1><<<grid, THREADS, SMEM_BYTES, s>>>(a);
   else if (o.split_in) conv_gemm_tc_kernel<2><<<grid, THREADS, SMEM_BYTES, s>>>(a);
+  else if (direct) conv_gemm_tc_kernel<3><<<grid, THREADS, SMEM_BYTES, s>>>(a);
   else conv_gemm_tc_kernel<0><<<grid, THREADS, SMEM_BYTES, s>>>(a);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
