@@ -34,6 +34,7 @@ namespace tc {
 constexpr int BM = 128, BK = 64, STAGES = 4, BN_MAX = 256, MAXP = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN_MAX * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;  // 16K + 32K
 constexpr int EPI_WARPS = 8, STG_LD = 33;
+constexpr int EPI_WARPS_DIRECT = 12;  // direct epilogue: 4 TMEM lane quarters x 3 column groups (<= 144 registers)
 constexpr int SPLIT_BN = 128;  // split-precision mode: tile width (two 32-column chunks per epilogue warp stay in registers)
 constexpr int SMEM_TILES = STAGES * STAGE_BYTES;                  // 196608
 constexpr int SMEM_STAGING = EPI_WARPS * 32 * STG_LD * 4;         // 33792
@@ -79,12 +80,16 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// two floats -> one 32-bit word of 16-bit values (x in the low half); IEEE half saturates like cvt16
+// two floats -> one 32-bit word of 16-bit values (x in the low half); IEEE half saturates like cvt16 (one F2FP.SATFINITE)
 __device__ __forceinline__ uint32_t pack16x2(float x, float y, bool fp16) {
-  if (fp16) return pack_f16x2(fminf(fmaxf(x, -65504.f), 65504.f), fminf(fmaxf(y, -65504.f), 65504.f));
-  return pack_bf16x2(x, y);
+  uint32_t r;
+  if (fp16)
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+  return r;
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -128,12 +133,14 @@ struct alignas(64) TcProb {
 static_assert(sizeof(TcProb) == 192, "TcProb layout");
 struct alignas(64) TcArgs {
   CUtensorMap map_a;  // (Cin, S, B) bf16, box 64 x box_rows x 1
-  // direct epilogue (MODE 3): row-major outputs leave through TMA stores of 32-row x 32-column boxes, (cols, S, B) maps;
+  // direct epilogue (MODE 3): row-major outputs leave through TMA stores of 32-row x 64-byte boxes, (cols, S, B) maps;
   // the *p maps have 31-row boxes (last quarter of a max-pool tile)
   CUtensorMap map_o16, map_o16p, map_o32, map_o32p;
   TcProb prob[tc::MAXP];
   int nprob, B, S, Cin, cblocks;
   int m_tiles, m_stride, box_rows, bn, total_tiles, pool, highway, fp16;
+  int dbg_skip_epi;  // developer experiment (FTB_DBG_SKIP_EPI=1): the direct epilogue only releases the accumulator, which
+                     // times the TMA / MMA side alone (K = 256, N = 512 at frame rate: 19.6 us against 41.8 us with the epilogue)
   int split_in;   // A holds 3 bf16 parts [hi | mid | lo] of an fp32 tensor; K loop = 6 part products (see conv_gemm_group)
   uint32_t amap;  // K segment `seg` (one full pass over taps x channel blocks) reads activation part (amap >> 4 seg) & 15
   int split_d;    // split-precision mode: k-blocks per TMEM accumulation unit inside the hi.hi product ...
@@ -290,7 +297,8 @@ __device__ __forceinline__ int split_unit_end(int kb, int nkb, int d, int ds) {
 // precision.  Separate instantiations because the kernel sits at its register cap (10 warps -> 3 per scheduler ->
 // 168 registers per thread): every mode only carries its own epilogue state.
 template <int MODE>
-__global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(MODE == 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : tc::THREADS, 1)
+    conv_gemm_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr bool HIGHWAY = MODE == 1, SPLIT = MODE == 2;
   using namespace tc;
   extern __shared__ unsigned char smem_dyn[];
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, EPI_WARPS);
+      mbar_init(tempty0 + 8 * i, MODE == 3 ? EPI_WARPS_DIRECT : EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -417,7 +425,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
     const int64_t ldo = a.ldo, ldr = a.ldr;
     const float out_scale = a.out_scale;
     const int S = a.S;
-    uint32_t tl = 0, un = 0;
+    uint32_t tl = 0, un = 0, nstore = 0;  // nstore: TMA stores issued by this warp (direct epilogue: staging tile parity)
+    int st_off[4];  // direct epilogue: byte offset of this thread's four 16-byte chunks in a 32 x 64 B SWIZZLE_64B tile
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st_off[j] = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tl) {
       const TileCoord c = decode_tile(a, tile);
       const TcProb& P = a.prob[c.p];
@@ -492,9 +503,25 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
         // clipped by the tensor map).  The legacy epilogue transposes through shared memory so that lanes walk the
         // columns and then issues a 2-byte store per element: ~10 instructions per element against ~5 here, and the
         // K = 256 layers (highways, input projections, pre_highway, proj2) are bound by exactly that.
-        unsigned char* tile = reinterpret_cast<unsigned char*>(staging_all) + (half * 4 + q) * 4096;  // 1024-aligned
-        float* halo = staging_all + 8 * 1024 + half * 4 * 32;                                         // [q][32], pool only
-        const uint32_t tile_u32 = smem_u32(tile);
+        const float *p_bias = P.bias, *p_scale = P.scale, *p_shift = P.shift;
+        const int n_off = P.n_offset;
+        // staging area: one 2 KB store tile per warp | the tile's per-column parameters (two sets, by tile parity) |
+        // the pool halo rows
+        constexpr int NCG = EPI_WARPS_DIRECT / 4;  // column groups: warp (q, cgp) takes chunks cgp, cgp + NCG, ...
+        const int cgp = ew >> 2;
+        unsigned char* tile = reinterpret_cast<unsigned char*>(staging_all) + (cgp * 4 + q) * 2048;  // 32 rows x 64 B
+        float* spar = staging_all + EPI_WARPS_DIRECT * 512 + (tl & 1) * 768;  // bias | scale | shift of this tile, 256 each
+        float* halo = staging_all + EPI_WARPS_DIRECT * 512 + 2 * 768 + cgp * 4 * 32;  // [q][32] per column group, pool only
+        {  // 256 epilogue threads load the tile's 3 x bn parameters; a missing vector becomes 0 / 1 / 0
+          const int et = ew * 32 + lane, n = c.n0 + et;
+          const bool nok = et < a.bn && n < pN;
+          if (et < 256) {
+            spar[et] = (nok && p_bias) ? __ldg(p_bias + n) : 0.f;
+            spar[256 + et] = (nok && p_scale) ? __ldg(p_scale + n) : 1.f;
+            spar[512 + et] = (nok && p_scale) ? __ldg(p_shift + n) : 0.f;
+          }
+          asm volatile("bar.sync 5, %0;" ::"n"(32 * EPI_WARPS_DIRECT) : "memory");  // double-buffered by tile parity: one barrier per tile
+        }
         const bool f16o = a.fp16 != 0;
         const int t_own = trow0 + lane;                     // time index of this thread's accumulator row
         const int64_t m_own = mrow0 + lane;
@@ -533,43 +560,40 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
           }
         };
         const bool any_res = has_r16 || has_r32;
-        if (any_res && half < nchunks) load_res(half);
+        if (any_res && cgp < nchunks) load_res(cgp);
         mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         bool released = false;
-        for (int ch = half; ch < nchunks; ch += 2) {
+        if (a.dbg_skip_epi == 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+          continue;
+        }
+        for (int ch = cgp; ch < nchunks; ch += NCG) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX + ch * 32, r);
           const int nb = c.n0 + ch * 32;  // first output column of the chunk
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (ch + 2 >= nchunks) {  // last TMEM read of this warp for this tile: hand the buffer back
+          if (ch + NCG >= nchunks) {  // last TMEM read of this warp for this tile: hand the buffer back
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
             released = true;
           }
-          // ---- value transform, 4 columns at a time (uniform parameter loads)
+          // ---- value transform, 4 columns at a time: the per-column parameters are broadcast 16-byte shared-memory
+          // loads (staged once per tile; as uniform global loads their latency cost 10 % of the K = 256 layers)
           float v[32];
-          const bool full = nb + 32 <= pN;
+          {
+            const float4* bp = reinterpret_cast<const float4*>(spar + ch * 32);  // broadcast shared-memory loads
+            const float4* sp = bp + 64;
+            const float4* hp = bp + 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = b4;
-            if (full) {
-              if (P.bias) b4 = __ldg(reinterpret_cast<const float4*>(P.bias + nb) + j);
-              if (P.scale) s4 = __ldg(reinterpret_cast<const float4*>(P.scale + nb) + j), h4 = __ldg(reinterpret_cast<const float4*>(P.shift + nb) + j);
-            } else {
-              float* bb = &b4.x; float* ss = &s4.x; float* hh = &h4.x;
-              for (int e = 0; e < 4; ++e) {
-                const int n = nb + 4 * j + e;
-                if (n < pN) {
-                  if (P.bias) bb[e] = __ldg(P.bias + n);
-                  if (P.scale) ss[e] = __ldg(P.scale + n), hh[e] = __ldg(P.shift + n);
-                }
-              }
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = bp[j], s4 = sp[j], h4 = hp[j];
+              v[4 * j] = fmaf(fmaxf(__uint_as_float(r[4 * j]) + b4.x, relu_lo), s4.x, h4.x);
+              v[4 * j + 1] = fmaf(fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, relu_lo), s4.y, h4.y);
+              v[4 * j + 2] = fmaf(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, relu_lo), s4.z, h4.z);
+              v[4 * j + 3] = fmaf(fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, relu_lo), s4.w, h4.w);
             }
-            v[4 * j] = fmaf(fmaxf(__uint_as_float(r[4 * j]) + b4.x, relu_lo), s4.x, h4.x);
-            v[4 * j + 1] = fmaf(fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, relu_lo), s4.y, h4.y);
-            v[4 * j + 2] = fmaf(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, relu_lo), s4.z, h4.z);
-            v[4 * j + 3] = fmaf(fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, relu_lo), s4.w, h4.w);
           }
           int row_coord = trow0;       // first row of the TMA box
           bool last_q_pool = false;
@@ -585,20 +609,20 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
 #pragma unroll
               for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(halo + q * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // the 4 quarters of this column half
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + cgp) : "memory");  // the 4 quarters of this column group
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               float nx = __shfl_down_sync(0xffffffffu, v[i], 1);
               if (lane == 31) nx = q < 3 ? halo[(q + 1) * 32 + i] : -INFINITY;
               v[i] = fmaxf(v[i], nx);
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // halo rows consumed before the next chunk writes them
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + cgp) : "memory");  // halo rows consumed before the next chunk writes them
             row_coord = trow0 + 1;
             last_q_pool = q == 3;
           } else if (any_res) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += res[i];
-            if (ch + 2 < nchunks) load_res(ch + 2);  // in flight while this chunk is packed and stored
+            if (ch + NCG < nchunks) load_res(ch + NCG);  // in flight while this chunk is packed and stored
           }
           if (out_scale != 1.f) {
 #pragma unroll
@@ -612,33 +636,45 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_gemm_tc_kernel(const __gr
                 if (nb + i < pN) ot[(int64_t)i * S] = v[i];
             }
           }
-          if (has_o32) {  // 32 rows x 128 B, SWIZZLE_128B: 16-byte chunk j of row r sits at chunk position j ^ (r & 7)
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
+          // Row-major outputs: one 32 rows x 64 B staging tile per warp (SWIZZLE_64B: 16-byte chunk j of row r sits at
+          // chunk position j ^ ((r >> 1) & 3)); the previous store has long finished reading it when the next chunk is
+          // ready (a second tile per warp measured no gain).  16-bit: one tile = the 32 columns of the chunk; fp32: two
+          // tiles of 16 columns.
+          if (has_o32) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(tile + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(last_q_pool ? &a.map_o32p : &a.map_o32, tile_u32, P.n_offset + nb, row_coord, c.b);
-              tma_store_commit();
+            for (int hcol = 0; hcol < 2; ++hcol) {
+              unsigned char* tb = tile;
+              if (lane == 0) tma_store_wait_read1();
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(tb + st_off[j]) =
+                    make_float4(v[16 * hcol + 4 * j], v[16 * hcol + 4 * j + 1], v[16 * hcol + 4 * j + 2], v[16 * hcol + 4 * j + 3]);
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(last_q_pool ? &a.map_o32p : &a.map_o32, smem_u32(tb), n_off + nb + 16 * hcol, row_coord, c.b);
+                tma_store_commit();
+              }
+              ++nstore;
             }
           }
-          if (has_o16) {  // 32 rows x 64 B, SWIZZLE_64B: chunk j of row r sits at chunk position j ^ ((r >> 1) & 3)
-            if (lane == 0) tma_store_wait_read();
+          if (has_o16) {
+            unsigned char* tb = tile;
+            if (lane == 0) tma_store_wait_read1();
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(tile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+              *reinterpret_cast<uint4*>(tb + st_off[j]) =
                   make_uint4(pack16x2(v[8 * j], v[8 * j + 1], f16o), pack16x2(v[8 * j + 2], v[8 * j + 3], f16o),
                              pack16x2(v[8 * j + 4], v[8 * j + 5], f16o), pack16x2(v[8 * j + 6], v[8 * j + 7], f16o));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(last_q_pool ? &a.map_o16p : &a.map_o16, tile_u32, P.n_offset + nb, row_coord, c.b);
+              tma_store_3d(last_q_pool ? &a.map_o16p : &a.map_o16, smem_u32(tb), n_off + nb, row_coord, c.b);
               tma_store_commit();
             }
+            ++nstore;
           }
         }
         if (!released) {  // no chunk for this warp in this tile
@@ -841,6 +877,8 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   a.Cin = Cin;
   a.cblocks = Cin / BK;
   a.pool = o.pool ? 1 : 0;
+  static const int dbg_skip = getenv("FTB_DBG_SKIP_EPI") ? atoi(getenv("FTB_DBG_SKIP_EPI")) : 0;
+  a.dbg_skip_epi = dbg_skip;
   a.split_in = o.split_in ? 1 : 0;
   a.split_out = o.split_out;
   a.amap = o.split_in ? 0x001102u : o.hl_in ? 0x010u : 0u;
@@ -935,10 +973,10 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
       cuuint64_t dims[3] = {(cuuint64_t)out_cols, (cuuint64_t)S, (cuuint64_t)B};
       cuuint64_t strides[2] = {(cuuint64_t)o.ldo * esz, (cuuint64_t)S * o.ldo * esz};
       for (int pv = 0; pv < (o.pool ? 2 : 1); ++pv) {
-        cuuint32_t box[3] = {32, (cuuint32_t)(pv ? 31 : 32), 1};
+        cuuint32_t box[3] = {(cuuint32_t)(e ? 16 : 32), (cuuint32_t)(pv ? 31 : 32), 1};  // 64-byte rows either way
         CUtensorMap* m = e ? (pv ? &a.map_o32p : &a.map_o32) : (pv ? &a.map_o16p : &a.map_o16);
         FTB_TRY(make_map(m, base, 3, dims, strides, box, e ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                         e ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
+                         CU_TENSOR_MAP_SWIZZLE_64B));
       }
     }
   }
@@ -953,7 +991,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   const int grid = std::min(tiles, sm_count());
   if (o.highway) conv_gemm_tc_kernel<1><<<grid, THREADS, SMEM_BYTES, s>>>(a);
   else if (o.split_in) conv_gemm_tc_kernel<2><<<grid, THREADS, SMEM_BYTES, s>>>(a);
-  else if (direct) conv_gemm_tc_kernel<3><<<grid, THREADS, SMEM_BYTES, s>>>(a);
+  else if (direct) conv_gemm_tc_kernel<3><<<grid, 32 * (2 + EPI_WARPS_DIRECT), SMEM_BYTES, s>>>(a);
   else conv_gemm_tc_kernel<0><<<grid, THREADS, SMEM_BYTES, s>>>(a);
   FTB_CHECK_LAUNCH();
   return FTB_OK;
