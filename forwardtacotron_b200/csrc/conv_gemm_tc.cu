@@ -27,6 +27,7 @@
 
 #include "epilogue.cuh"
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace ftb {
 
@@ -49,76 +50,6 @@ __host__ __device__ constexpr uint32_t idesc_16(int n, bool fp16) {
 }
 }  // namespace tc
 
-
-// ---- PTX wrappers -------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_or_trap(bar, parity); }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-// smem tile -> global through the tensor map (clipped at the tensor bounds); completion tracked by bulk groups
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// two floats -> one 32-bit word of 16-bit values (x in the low half); IEEE half saturates like cvt16 (one F2FP.SATFINITE)
-__device__ __forceinline__ uint32_t pack16x2(float x, float y, bool fp16) {
-  uint32_t r;
-  if (fp16)
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
-  else
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
-  return r;
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start>>4 | LBO(unused)=0 | SBO = 8 rows * 128 B = 1024 (>>4) | version 1 | layout SWIZZLE_128B (2)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
-      "%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
 
 // One conv / linear of a launch; all problems of a launch share the activation tensor and outputs.
 struct alignas(64) TcProb {
@@ -734,8 +665,7 @@ __global__ void __launch_bounds__(MODE == 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
           for (int i = 0; i < 32; ++i) {
             const float x1 = __uint_as_float(r1[i]) + __ldg(P.bias + nb1 + i);
             const float x2 = __uint_as_float(r2[i]) + __ldg(P.bias + nb1 + 32 + i);
-            const float g = __fdividef(1.f, 1.f + __expf(-x2));
-            stg[lane * STG_LD + i] = g * fmaxf(x1, 0.f) + (1.f - g) * ld16(xb[i], a.fp16 != 0);
+            stg[lane * STG_LD + i] = highway_mix_value(x1, x2, ld16(xb[i], a.fp16 != 0));
           }
           __syncwarp();
           __nv_bfloat16* o16 = a.out_bf16 + mrow0 * ldo + oc0 + lane;
@@ -821,34 +751,6 @@ __global__ void __launch_bounds__(MODE == 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
 }
 
 // ---- host side ------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
-  EncodeTiledFn fn = get_encode_fn();
-  FTB_REQUIRE(fn, FTB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint32_t elem_strides[3] = {1, 1, 1};
-  CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, elem_strides,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FTB_REQUIRE(r == CUDA_SUCCESS, FTB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return FTB_OK;
-}
-
 int tc_tile_n(int N) { return N % 256 == 0 ? 256 : (N > 64 ? 128 : 64); }
 
 // x (B,S,lda) bf16; items[i] is one conv over x.  All items must agree on the tile width tc_tile_n(N).
@@ -1082,8 +984,9 @@ namespace ftb {
 FTB_DEFINE_TIMEOUT_READER(gemm_tc_timeouts)
 int rnn_tc_timeouts();   // rnn_tc.cu
 int rnn_mma_timeouts();  // rnn_mma.cu
+int tail_tc_timeouts();  // cbhg_tail.cu
 }  // namespace ftb
 extern "C" int ftb_tc_timeout_count(void) {
-  const int a = ftb::gemm_tc_timeouts(), b = ftb::rnn_tc_timeouts(), c = ftb::rnn_mma_timeouts();
-  return (a < 0 || b < 0 || c < 0) ? -1 : a + b + c;  // -1: the context is gone (a kernel trapped)
+  const int a = ftb::gemm_tc_timeouts(), b = ftb::rnn_tc_timeouts(), c = ftb::rnn_mma_timeouts(), d = ftb::tail_tc_timeouts();
+  return (a < 0 || b < 0 || c < 0 || d < 0) ? -1 : a + b + c + d;  // -1: the context is gone (a kernel trapped)
 }

@@ -57,6 +57,7 @@ struct ftb_ft_handle : ftb::ModelBase {
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   int opt_overlap_prenet = 0, opt_serialize = 0;
   int opt_dur_simt = getenv("FTB_DUR_SIMT") ? atoi(getenv("FTB_DUR_SIMT")) : 0;  // 1: duration predictor on the fp32 SIMT kernel
+  int opt_unfused_tail = getenv("FTB_UNFUSED_TAIL") ? atoi(getenv("FTB_UNFUSED_TAIL")) : 0;  // 1: CBHG tail layer by layer
   char* pre_buf = nullptr;
   int64_t pre_cap = 0;
   const int64_t* pre_tok = nullptr;
@@ -271,6 +272,22 @@ static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int 
   FTB_ZERO_TAIL(w.p1, S, W.p0 * sizeof(T));
   if (w.ld2 != W.p1) FTB_CHECK_CUDA(cudaMemsetAsync(w.p2, 0, (size_t)M * w.ld2 * sizeof(T), s));
   FTB_TRY(h->gemm<T>(W.proj2, w.p1, W.p0, B, S, act_out(w.p2, w.ld2), x, ldx, 1.f, s));  // + residual
+  if (!std::is_same<T, float>::value && !h->opt_unfused_tail && W.nhw <= 4 && W.ch == 256 && W.pre_hw.CinP <= 256) {
+    // pre_highway -> highways -> GRU input projection in one persistent kernel, activations resident in shared memory
+    const bf16* whw[4];
+    const float* bhw[4];
+    for (int i = 0; i < W.nhw; ++i) whw[i] = W.hw[i].w16, bhw[i] = W.hw[i].bias;
+    {
+      ++h->launches;
+      ProfScope prof(FAM_GEMM_TC, 2.0 * M * ((double)W.ch * W.pre_hw.Cin + W.nhw * 2.0 * W.ch * W.ch + 6.0 * W.ch * W.ch), 0.0, s);
+      FTB_TRY(cbhg_tail((const bf16*)w.p2, w.ld2, M, W.pre_hw.w16, W.pre_hw.CinP, whw, bhw, W.nhw, W.rnn.in.w16, W.rnn.in.bias,
+                        6 * W.ch, w.xg, std::is_same<T, f16>::value, s));
+    }
+    FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, out_kind<T>(), s, nullptr, out_ld, out_lo, lens));
+    h->launches += 1;
+    A.reset(mark);
+    return FTB_OK;
+  }
   FTB_TRY(h->gemm<T>(W.pre_hw, w.p2, w.ld2, B, S, act_out(w.ha, W.ch), nullptr, 0, 1.f, s));
   T *cur = w.ha, *nxt = w.hb;
   for (int i = 0; i < W.nhw; ++i) {
@@ -536,6 +553,10 @@ extern "C" int ftb_ft_set_option(ftb_ft_handle* h, int option, int value) {
   }
   if (option == FTB_OPT_SERIALIZE) {
     h->opt_serialize = value != 0;
+    return FTB_OK;
+  }
+  if (option == FTB_OPT_UNFUSED_TAIL) {
+    h->opt_unfused_tail = value != 0;
     return FTB_OK;
   }
   set_error("ftb_ft_set_option: unknown option %d", option);

@@ -37,6 +37,12 @@ int tc_tile_n(int N);
 int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, const TcItem* items, int n_items,
                     const TcOut& o, cudaStream_t s);
 
+// cbhg_tail.cu: pre_highway -> nhw highway layers -> GRU input projection of a CBHG in one persistent kernel.
+// p2 (M, ld2) 16-bit -> xg (M, n_in) fp32; weights K-major 16-bit, highway rows / biases interleaved [32 W1 | 32 W2].
+int cbhg_tail(const __nv_bfloat16* p2, int ld2, int64_t M, const __nv_bfloat16* w_pre, int kp, const __nv_bfloat16* const* w_hw,
+              const float* const* b_hw, int nhw, const __nv_bfloat16* w_in, const float* b_in, int n_in, float* xg, bool fp16,
+              cudaStream_t s);
+
 // rnn_small.cu / rnn_cluster.cu
 // xrow (optional, H=512 LSTM): (B,S) int32 row of xg feeding frame (b,t) (default b*S + t).  ldo: out row stride
 // (default 2H); lo_off > 0: the 16-bit rounding remainder h - hi is written lo_off elements after hi.

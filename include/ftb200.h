@@ -295,6 +295,11 @@ int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, int T, float 
  * is carried as three bf16 parts (hi + mid + lo = the fp32 value), six part products accumulate in fp32.  1 = use the
  * fp32 SIMT GEMM instead (the all-fp32 gemm_mode 1 always does). */
 #define FTB_OPT_DUR_SIMT 3
+/* FTB_OPT_UNFUSED_TAIL (default 0; env FTB_UNFUSED_TAIL): 1 = run pre_highway, the highway layers and the GRU input
+ * projection of each CBHG (models/common_layers.py:113-118) as one tcgen05 launch per layer instead of the fused
+ * persistent kernel that keeps the activations in shared memory across all of them (csrc/cbhg_tail.cu).  Both paths
+ * produce the same bits; the option exists for that comparison and for profiling. */
+#define FTB_OPT_UNFUSED_TAIL 4
 int ftb_ft_set_option(ftb_ft_handle* h, int option, int value);
 
 /* Between the stages the Python callbacks pitch_function / energy_function run

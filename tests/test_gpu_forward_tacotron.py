@@ -132,6 +132,29 @@ def test_prenet_overlap_and_serialised_paths_agree():
         assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
 
 
+@pytest.mark.parametrize('gemm_mode', [0, 2])
+@pytest.mark.parametrize('B,T', [(5, 70), (1, 3), (3, 129), (16, 200)])
+def test_fused_cbhg_tail_equals_the_layer_by_layer_path(gemm_mode, B, T):
+    """pre_highway -> 4 highways -> GRU input projection (models/common_layers.py:113-118) run as ONE persistent kernel
+    with the activations resident in shared memory (csrc/cbhg_tail.cu).  FTB_OPT_UNFUSED_TAIL runs one launch per
+    layer.  Same MMA K order, same epilogue expressions, same 16-bit rounding points -> bit-identical outputs, for both
+    CBHGs (prenet: 256 input channels at phoneme rate; postnet: 80 -> 128 padded channels at frame rate, row counts
+    that are not a multiple of the 128-row tile)."""
+    from forwardtacotron_b200 import _lib
+    model, _ = cuda_model('forward_tacotron', gemm_mode)
+    x = synth.synthetic_tokens(B, T, seed=21, ragged=B > 1).cuda()
+    a = model.generate(x)
+    _lib.check(_lib.lib().ftb_ft_set_option(model._handle, _lib.FTB_OPT_UNFUSED_TAIL, 1))
+    try:
+        b = model.generate(x)
+    finally:
+        _lib.check(_lib.lib().ftb_ft_set_option(model._handle, _lib.FTB_OPT_UNFUSED_TAIL, 0))
+    assert int(a['mel_len'].max()) > 0
+    for k in ('mel', 'mel_post', 'dur', 'pitch', 'energy', 'mel_len'):
+        assert torch.equal(a[k], b[k]), (k, float((a[k].float() - b[k].float()).abs().max()))
+    assert _lib.lib().ftb_tc_timeout_count() == 0
+
+
 def test_long_utterances_against_oracle():
     """cfg5-like shape scaled to what the CPU oracle finishes in seconds: T = 900 phonemes -> L ~ 5.5 k frames."""
     model, _ = cuda_model('forward_tacotron', 0)
