@@ -161,6 +161,16 @@ static int build_cbhg(ftb_ft_handle* h, CbhgW& W, const std::string& p, int K, i
     }
   }
   FTB_TRY(h->make_rnn(W.rnn, p + ".rnn", ch, ch, false, w32, w16));
+  if (w16) {  // the fused tail kernel streams its weights k-block by k-block
+    auto tail_copy = [&](Layer& L) -> int {
+      L.w16t = h->dalloc<bf16>((int64_t)L.N * L.CinP);
+      FTB_REQUIRE(L.w16t, FTB_ERR_CUDA, "out of device memory");
+      return cbhg_tail_pack(L.w16, L.w16t, L.N, L.CinP, h->prep);
+    };
+    FTB_TRY(tail_copy(W.pre_hw));
+    for (int i = 0; i < nhw; ++i) FTB_TRY(tail_copy(W.hw[i]));
+    FTB_TRY(tail_copy(W.rnn.in));
+  }
   return FTB_OK;
 }
 
@@ -276,11 +286,11 @@ static int run_cbhg(ftb_ft_handle* h, CbhgW& W, const T* x, int ldx, int B, int 
     // pre_highway -> highways -> GRU input projection in one persistent kernel, activations resident in shared memory
     const bf16* whw[4];
     const float* bhw[4];
-    for (int i = 0; i < W.nhw; ++i) whw[i] = W.hw[i].w16, bhw[i] = W.hw[i].bias;
+    for (int i = 0; i < W.nhw; ++i) whw[i] = W.hw[i].w16t, bhw[i] = W.hw[i].bias;
     {
       ++h->launches;
       ProfScope prof(FAM_GEMM_TC, 2.0 * M * ((double)W.ch * W.pre_hw.Cin + W.nhw * 2.0 * W.ch * W.ch + 6.0 * W.ch * W.ch), 0.0, s);
-      FTB_TRY(cbhg_tail((const bf16*)w.p2, w.ld2, M, W.pre_hw.w16, W.pre_hw.CinP, whw, bhw, W.nhw, W.rnn.in.w16, W.rnn.in.bias,
+      FTB_TRY(cbhg_tail((const bf16*)w.p2, w.ld2, M, W.pre_hw.w16t, W.pre_hw.CinP, whw, bhw, W.nhw, W.rnn.in.w16t, W.rnn.in.bias,
                         6 * W.ch, w.xg, std::is_same<T, f16>::value, s));
     }
     FTB_TRY(rnn_bidir(w.xg, W.rnn.w_hh, W.rnn.b_hn, out, B, S, W.ch, 0, out_kind<T>(), s, nullptr, out_ld, out_lo, lens));

@@ -38,7 +38,9 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
                     const TcOut& o, cudaStream_t s);
 
 // cbhg_tail.cu: pre_highway -> nhw highway layers -> GRU input projection of a CBHG in one persistent kernel.
-// p2 (M, ld2) 16-bit -> xg (M, n_in) fp32; weights K-major 16-bit, highway rows / biases interleaved [32 W1 | 32 W2].
+// p2 (M, ld2) 16-bit -> xg (M, n_in) fp32; weights 16-bit in cbhg_tail_pack order, highway rows / biases interleaved
+// [32 W1 | 32 W2].
+int cbhg_tail_pack(const __nv_bfloat16* w, __nv_bfloat16* out, int N, int K, cudaStream_t s);  // (N,K) -> [K/64][N][64]
 int cbhg_tail(const __nv_bfloat16* p2, int ld2, int64_t M, const __nv_bfloat16* w_pre, int kp, const __nv_bfloat16* const* w_hw,
               const float* const* b_hw, int nhw, const __nv_bfloat16* w_in, const float* b_in, int n_in, float* xg, bool fp16,
               cudaStream_t s);

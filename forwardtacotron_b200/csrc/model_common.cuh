@@ -18,6 +18,7 @@ struct Layer {
   float* w32 = nullptr;
   bf16* w16 = nullptr;
   bf16* w16s = nullptr;  // split-precision copy (ftb_pack_conv_weight mode 3): (N, 6, k, CinP) bf16
+  bf16* w16t = nullptr;  // k-block-major copy for the fused CBHG tail kernel (cbhg_tail_pack)
   float* bias = nullptr;
   float* scale = nullptr;
   float* shift = nullptr;

@@ -83,11 +83,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 
-// Highway gate mix (models/common_layers.py:30-35): y = g relu(x1) + (1 - g) x, g = sigmoid(x2).  Explicit rounding
-// steps (no compiler-chosen FMA contraction) so every kernel that forms it produces the same bits.
+// Highway gate mix (models/common_layers.py:30-35): y = g relu(x1) + (1 - g) x, g = sigmoid(x2), in the tensor-core
+// epilogues.  The gate is one MUFU (tanh.approx.f32, max relative error 2^-11 -> |dg| <= 2.5e-4, the size of the 16-bit
+// rounding the result gets anyway): with exp + reciprocal the fused CBHG tail kernel is bound by the SFU pipe (2 MUFU per
+// output at 16 lanes/clk/SM = the time of the layer's MMAs).  Written as x + g (relu(x1) - x) with explicit rounding
+// steps (no compiler-chosen contraction) so every kernel that forms it produces the same bits.
 __device__ __forceinline__ float highway_mix_value(float x1, float x2, float x) {
-  const float g = __fdividef(1.f, 1.f + __expf(-x2));
-  return __fmaf_rn(g, fmaxf(x1, 0.f), __fmul_rn(__fsub_rn(1.f, g), x));
+  const float g = __fmaf_rn(tanh_mufu(__fmul_rn(0.5f, x2)), 0.5f, 0.5f);
+  return __fmaf_rn(g, __fsub_rn(fmaxf(x1, 0.f), x), x);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
