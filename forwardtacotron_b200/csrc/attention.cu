@@ -6,6 +6,8 @@
 // an online softmax, so the S x S score matrix never reaches HBM.  fp32 arithmetic throughout (the
 // duration predictor needs fp32-accurate attention; the bf16 instantiation only changes the I/O type).
 // Round-1 kernel: SIMT FFMA inner products; the tcgen05 version is the next optimisation step.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace ftb {
@@ -384,12 +386,20 @@ static int launch_attention_tc(const void* qkv, const int64_t* tokens, void* ctx
   return FTB_OK;
 }
 
+int attention_umma(const void* qkv, const int64_t* tokens_for_mask, void* ctx, int B, int S, int E, int heads, bool fp16,
+                   cudaStream_t s);  // attention_umma.cu
+
+// impl: 0 = tcgen05 / TMEM kernel (attention_umma.cu, the default), 1 = the mma.sync kernel above (FTB_ATTN_LEGACY=1)
 template <bool FP16>
-int attention_tc(const void* qkv, const int64_t* tokens_for_mask, void* ctx, int B, int S, int E, int heads, cudaStream_t s) {
+int attention_tc(const void* qkv, const int64_t* tokens_for_mask, void* ctx, int B, int S, int E, int heads, cudaStream_t s,
+                 int impl = -1) {
   FTB_REQUIRE(qkv && ctx && B > 0 && S > 0 && heads > 0 && E % heads == 0, FTB_ERR_INVALID, "attention: bad arguments");
   FTB_REQUIRE(B <= 65535 && heads <= 65535 && E % 8 == 0, FTB_ERR_INVALID, "attention: grid too large / E not a multiple of 8");
   const int hd = E / heads;
   ProfScope prof(FAM_ATTENTION, 4.0 * B * heads * (double)S * S * hd, 0.0, s);
+  static const int legacy = getenv("FTB_ATTN_LEGACY") ? atoi(getenv("FTB_ATTN_LEGACY")) : 0;
+  if (impl < 0) impl = legacy;
+  if (impl == 0 && (hd == 64 || hd == 128)) return attention_umma(qkv, tokens_for_mask, ctx, B, S, E, heads, FP16, s);
   if (hd == 64) return launch_attention_tc<64, FP16>(qkv, tokens_for_mask, ctx, B, S, E, heads, s);
   if (hd == 128) return launch_attention_tc<128, FP16>(qkv, tokens_for_mask, ctx, B, S, E, heads, s);
   set_error("attention: head dim %d not built (64, 128)", hd);
@@ -406,3 +416,11 @@ int attention<__nv_bfloat16>(const __nv_bfloat16* qkv, const int64_t* m, __nv_bf
 }
 
 }  // namespace ftb
+
+// 16-bit attention core on its own (tests, profiling): qkv (B,S,3E) -> ctx (B,S,E); tokens (B,S) int64 or NULL
+extern "C" int ftb_attention_16(const void* qkv, const int64_t* tokens, void* ctx, int B, int S, int E, int heads, int fp16,
+                                int impl, void* stream) {
+  FTB_REQUIRE(impl == 0 || impl == 1, FTB_ERR_INVALID, "ftb_attention_16: impl must be 0 (tcgen05) or 1 (mma.sync)");
+  return fp16 ? ftb::attention_tc<true>(qkv, tokens, ctx, B, S, E, heads, (cudaStream_t)stream, impl)
+              : ftb::attention_tc<false>(qkv, tokens, ctx, B, S, E, heads, (cudaStream_t)stream, impl);
+}

@@ -985,8 +985,10 @@ FTB_DEFINE_TIMEOUT_READER(gemm_tc_timeouts)
 int rnn_tc_timeouts();   // rnn_tc.cu
 int rnn_mma_timeouts();  // rnn_mma.cu
 int tail_tc_timeouts();  // cbhg_tail.cu
+int attn_tc_timeouts();  // attention_umma.cu
 }  // namespace ftb
 extern "C" int ftb_tc_timeout_count(void) {
-  const int a = ftb::gemm_tc_timeouts(), b = ftb::rnn_tc_timeouts(), c = ftb::rnn_mma_timeouts(), d = ftb::tail_tc_timeouts();
-  return (a < 0 || b < 0 || c < 0 || d < 0) ? -1 : a + b + c + d;  // -1: the context is gone (a kernel trapped)
+  const int a = ftb::gemm_tc_timeouts(), b = ftb::rnn_tc_timeouts(), c = ftb::rnn_mma_timeouts(), d = ftb::tail_tc_timeouts(),
+            e = ftb::attn_tc_timeouts();
+  return (a < 0 || b < 0 || c < 0 || d < 0 || e < 0) ? -1 : a + b + c + d + e;  // -1: the context is gone (a kernel trapped)
 }

@@ -346,6 +346,14 @@ int ftb_ft_last_launch_count(const ftb_ft_handle* h);
 /* ------------------------------------------------------------------------- *
  * Model level: FastPitch.generate, models/fast_pitch.py:286-340
  * ------------------------------------------------------------------------- */
+/* The 16-bit multi-head attention core of FastPitch's FFT blocks on its own (nn.MultiheadAttention inside
+ * models/fast_pitch.py:64,80-82): ctx (B,S,E) = softmax(q k^T / sqrt(hd) + key_padding_mask) v on the packed projection
+ * qkv (B,S,3E) = [q | k | v], heads split along E (hd = E / heads in {64, 128}).  tokens: (B,S) int64 ids, keys with id
+ * 0 are masked; or NULL.  fp16: the 16-bit type is IEEE half (else bfloat16).  impl 0 = the tcgen05 / TMEM kernel the
+ * models use, 1 = the mma.sync kernel it replaced (kept for comparison). */
+int ftb_attention_16(const void* qkv, const int64_t* tokens, void* ctx, int B, int S, int E, int heads, int fp16, int impl,
+                     void* stream);
+
 typedef struct ftb_fp_config { /* keys of config.yaml fast_pitch.model + num_chars, n_mels */
   int32_t num_chars, n_mels;
   int32_t durpred_d_model, durpred_n_heads, durpred_layers, durpred_d_fft;
