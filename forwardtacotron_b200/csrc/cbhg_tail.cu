@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) cbhg_tail_kernel(const __gri
   auto layer_ncol = [&](int l) { return l == 0 ? CH : (l <= a.nhw ? 2 * CH : a.in_units * UN); };  // output columns
   auto tile_of = [&](int tk, int s) { return 2 * (pair0 + (2 * tk + s) * npairs_step) + (int)crank; };  // this CTA's 128 rows
   // The three roles walk the same schedule (tail_period), period by period; period n0 only drains slot 1's projection.
-  TailGrp grp[16];
+  TailGrp grp[2 * (2 * tail::MAX_HW + 2)];  // per phase: pre, nhw highway groups, up to nhw projection slices, a load marker
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       uint32_t it = 0, gp = 0;

@@ -133,13 +133,14 @@ def test_prenet_overlap_and_serialised_paths_agree():
 
 
 @pytest.mark.parametrize('gemm_mode', [0, 2])
-@pytest.mark.parametrize('B,T', [(5, 70), (1, 3), (3, 129), (16, 200)])
+@pytest.mark.parametrize('B,T', [(5, 70), (1, 3), (3, 129), (16, 200), (64, 200)])
 def test_fused_cbhg_tail_equals_the_layer_by_layer_path(gemm_mode, B, T):
     """pre_highway -> 4 highways -> GRU input projection (models/common_layers.py:113-118) run as ONE persistent kernel
     with the activations resident in shared memory (csrc/cbhg_tail.cu).  FTB_OPT_UNFUSED_TAIL runs one launch per
     layer.  Same MMA K order, same epilogue expressions, same 16-bit rounding points -> bit-identical outputs, for both
     CBHGs (prenet: 256 input channels at phoneme rate; postnet: 80 -> 128 padded channels at frame rate, row counts
-    that are not a multiple of the 128-row tile)."""
+    that are not a multiple of the 128-row tile).  64 x 200 is the cfg2 shape: every CTA pair works through several
+    tiles per slot there (reloads of the input rows, the drain period of the unit schedule)."""
     from forwardtacotron_b200 import _lib
     model, _ = cuda_model('forward_tacotron', gemm_mode)
     x = synth.synthetic_tokens(B, T, seed=21, ragged=B > 1).cuda()
