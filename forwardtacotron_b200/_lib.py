@@ -127,7 +127,6 @@ SIGNATURES = {
     'ftb_fp_synthesize': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _L, _P]),
     'ftb_fp_forward_eval': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),
     'ftb_fp_last_launch_count': (_I, [_P]),
-    'ftb_fp_set_option': (_I, [_P, _I, _I]),
     'ftb_attention_16': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
 }
 STRUCT_IDS = {0: Tensor, 1: ConvDesc, 2: MelConfig, 3: FtConfig, 4: FpConfig}

@@ -399,7 +399,7 @@ int attention_tc(const void* qkv, const int64_t* tokens_for_mask, void* ctx, int
   ProfScope prof(FAM_ATTENTION, 4.0 * B * heads * (double)S * S * hd, 0.0, s);
   static const int legacy = getenv("FTB_ATTN_LEGACY") ? atoi(getenv("FTB_ATTN_LEGACY")) : 0;
   if (impl < 0) impl = legacy;
-  if (impl == 0 && (hd == 64 || hd == 128) && S <= 8000) return attention_umma(qkv, tokens_for_mask, ctx, B, S, E, heads, FP16, s);
+  if (impl == 0 && (hd == 64 || hd == 128)) return attention_umma(qkv, tokens_for_mask, ctx, B, S, E, heads, FP16, s);
   if (hd == 64) return launch_attention_tc<64, FP16>(qkv, tokens_for_mask, ctx, B, S, E, heads, s);
   if (hd == 128) return launch_attention_tc<128, FP16>(qkv, tokens_for_mask, ctx, B, S, E, heads, s);
   set_error("attention: head dim %d not built (64, 128)", hd);

@@ -27,7 +27,6 @@ namespace ftb {
 namespace au {
 constexpr int BQ = 128, BKV = 128, NSB = 3, THREADS = 192;
 constexpr int BOX = 128 * 64 * 2;  // one TMA box: 128 rows x 64 columns, 16 KB
-constexpr int MAX_KEYS = 8192;       // the additive key mask of the whole sequence sits in shared memory (32 KB)
 constexpr float RESCALE_STEP = 8.f;  // log2 domain: rescale O only when the row maximum grows by more than 2^8
 }  // namespace au
 
@@ -84,7 +83,7 @@ __global__ void __launch_bounds__(au::THREADS, 1) attention_umma_kernel(const __
   using namespace au;
   constexpr int KB = HD / 64;  // 64-column boxes per Q / K / V tile
   constexpr int TILE = KB * BOX;
-  constexpr int OFF_K = TILE, OFF_V = OFF_K + 2 * TILE, OFF_MSK = OFF_V + 2 * TILE, OFF_BAR = OFF_MSK + MAX_KEYS * 4;
+  constexpr int OFF_K = TILE, OFF_V = OFF_K + 2 * TILE, OFF_MSK = OFF_V + 2 * TILE, OFF_BAR = OFF_MSK + 2 * BKV * 4;
   constexpr uint32_t O_COL = NSB * 128;  // O accumulator behind the three score buffers
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -184,33 +183,25 @@ __global__ void __launch_bounds__(au::THREADS, 1) attention_umma_kernel(const __
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const float scale = a.scale_log2;
     float m_ref = -INFINITY, l = 0.f;
-    // additive key-padding mask of every key (also masks the zero-filled keys beyond S), once: a per-tile fetch put a
-    // global-memory round trip at the head of every tile
-    for (int key = ts; key < nt * BKV; key += 128)
-      msk[key] = (key >= S || (a.tokens && a.tokens[(int64_t)b * S + key] == 0)) ? -INFINITY : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int j = 0; j < nt; ++j) {
-      const float* mk = msk + j * BKV;
+      {  // key-padding mask of this tile (also masks the zero-filled keys beyond S)
+        const int key = j * BKV + ts;
+        msk[(j & 1) * BKV + ts] = (key >= S || (a.tokens && a.tokens[(int64_t)b * S + key] == 0)) ? -INFINITY : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float* mk = msk + (j & 1) * BKV;
       const uint32_t tS = lane_base + (uint32_t)(j % NSB) * 128u;
       mbar_wait(s_full0 + 8 * (j % NSB), (j / NSB) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // ---- pass 1: row maximum of the scaled, masked scores (log2 domain)
       float mx = -INFINITY;
-      {
-        uint32_t ra[32], rb[32];  // the next chunk's TMEM load is in flight while this one is reduced
-        tmem_ld32(tS, ra);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + c * 32, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < 4; c += 2) {
-          tmem_ld32(tS + (c + 1) * 32, rb);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(ra[i]), scale, mk[c * 32 + i]));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (c + 2 < 4) tmem_ld32(tS + (c + 2) * 32, ra);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(rb[i]), scale, mk[(c + 1) * 32 + i]));
-          if (c + 2 < 4) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        }
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(r[i]), scale, mk[c * 32 + i]));
       }
       // ---- a row whose maximum outgrows its reference by more than 2^8 moves the reference and rescales l and O
       const bool need = mx > m_ref + RESCALE_STEP;  // (-inf reference: any live key)
@@ -288,7 +279,7 @@ template <int HD, bool FP16>
 static int launch_attention_umma(const void* qkv, const int64_t* tokens, void* ctx, int B, int S, int E, int heads, cudaStream_t s) {
   using namespace au;
   constexpr int KB = HD / 64, TILE = KB * BOX;
-  constexpr int SMEM = 5 * TILE + MAX_KEYS * 4 + 160 + 1024;
+  constexpr int SMEM = 5 * TILE + 2 * BKV * 4 + 160 + 1024;
   static_assert(SMEM <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   AttnArgs a;
   memset(&a, 0, sizeof(a));
@@ -319,7 +310,6 @@ static int launch_attention_umma(const void* qkv, const int64_t* tokens, void* c
 int attention_umma(const void* qkv, const int64_t* tokens_for_mask, void* ctx, int B, int S, int E, int heads, bool fp16,
                    cudaStream_t s) {
   FTB_REQUIRE(qkv && ctx && B > 0 && S > 0 && heads > 0 && E % heads == 0, FTB_ERR_INVALID, "attention: bad arguments");
-  FTB_REQUIRE(S <= au::MAX_KEYS - au::BKV, FTB_ERR_UNSUPPORTED, "attention: more than %d keys", au::MAX_KEYS - au::BKV);
   FTB_REQUIRE(B <= 65535 && heads <= 65535 && E % 8 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)ctx & 15) == 0,
               FTB_ERR_INVALID, "attention: grid too large / unaligned operands");
   const int hd = E / heads;

@@ -44,25 +44,14 @@ struct ftb_fp_handle : ftb::ModelBase {
   // 10x ForwardTacotron's); half has 11 bits at the same tensor-core rate and these activations are LayerNorm-bounded
   // (stores saturate at +-65504), so half is the default and bf16 the opt-in.
   // stage A: the three independent predictors run on three side streams (fork / join with events), like ft_model.cu
-  // With FTB_OPT_OVERLAP_PRENET the prenet transformer of stage B (it depends on the tokens only) is started in
-  // stage A as well, on a fourth stream into handle-owned memory: the predictors are small kernels on 38 k rows (the
-  // fp32-grade duration predictor takes ~2 ms alone) and leave most SMs idle.
-  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
-  int opt_overlap_prenet = 0;
-  char* pre_buf = nullptr;
-  int64_t pre_cap = 0;
-  const int64_t* pre_tok = nullptr;
-  int pre_B = 0, pre_T = 0;
-  bool pre_valid = false;
-  void* pre_x = nullptr;
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   ~ftb_fp_handle() {
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 3; ++i) {
       if (side[i]) cudaStreamSynchronize(side[i]), cudaStreamDestroy(side[i]);
       if (ev_join[i]) cudaEventDestroy(ev_join[i]);
     }
     if (ev_fork) cudaEventDestroy(ev_fork);
-    if (pre_buf) cudaFree(pre_buf);
   }
   bool half_mode() const { return cfg.gemm_mode == 0 || cfg.gemm_mode == 2; }
   bool is_fp16() const { return cfg.gemm_mode == 0; }
@@ -247,14 +236,8 @@ static int run_fp_synthesize(ftb_fp_handle* h, const int64_t* tok, const int32_t
   T* up = A.take<T>(ML * E);
   float* x32 = std::is_same<T, float>::value ? nullptr : A.take<float>(std::max(MT, ML) * E);
   FTB_REQUIRE(!A.overflow, FTB_ERR_WORKSPACE, "workspace too small for synthesize");
-  if (!post_mask && h->pre_valid && h->pre_tok == tok && h->pre_B == B && h->pre_T == Tn) {
-    FTB_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_join[3], 0));  // prenet already computed (or in flight) on side stream 3
-    x = (T*)h->pre_x;
-  } else {
-    FTB_TRY(embed<T>(tok, h->embedding, x, MT, E, E, c.num_chars, s));
-    FTB_TRY(run_transformer<T>(h, h->prenet, x, x32, tok, B, Tn, A, s));
-  }
-  h->pre_valid = false;
+  FTB_TRY(embed<T>(tok, h->embedding, x, MT, E, E, c.num_chars, s));
+  FTB_TRY(run_transformer<T>(h, h->prenet, x, x32, tok, B, Tn, A, s));
   FTB_TRY(cond_add<T>(x, pitch, energy, h->pitch_w, h->pitch_b, h->energy_w, h->energy_b, c.pitch_strength,
                       c.energy_strength, B, Tn, E, s));
   FTB_TRY(ftb_length_expand(x, cum, up, B, Tn, L, E, (int)sizeof(T), s));
@@ -263,39 +246,6 @@ static int run_fp_synthesize(ftb_fp_handle* h, const int64_t* tok, const int32_t
   o.t = mel;
   FTB_TRY(h->gemm<T>(h->lin, up, E, B, L, o, nullptr, 0, 1.f, s));
   h->launches += 3;
-  return FTB_OK;
-}
-
-// starts embedding + prenet transformer on side stream 3 into handle-owned memory (FTB_OPT_OVERLAP_PRENET)
-template <typename T>
-static int prefetch_fp_prenet(ftb_fp_handle* h, const int64_t* tok, int B, int Tn) {
-  const int E = h->cfg.d_model;
-  const int64_t MT = (int64_t)B * Tn;
-  Arena M(nullptr, 0);
-  M.take<T>(MT * E);
-  M.take<float>(MT * E);
-  plan_tr<T>(M, h->prenet, B, Tn);
-  const int64_t need = M.mark() + 4096;
-  if (need > h->pre_cap) {
-    FTB_CHECK_CUDA(cudaStreamSynchronize(h->side[3]));
-    if (h->pre_buf) FTB_CHECK_CUDA(cudaFree(h->pre_buf));
-    h->pre_buf = nullptr;
-    h->pre_cap = 0;
-    FTB_CHECK_CUDA(cudaMalloc((void**)&h->pre_buf, (size_t)need));
-    h->pre_cap = need;
-  }
-  Arena A(h->pre_buf, h->pre_cap);
-  T* x = A.take<T>(MT * E);
-  float* x32 = std::is_same<T, float>::value ? nullptr : A.take<float>(MT * E);
-  cudaStream_t s3 = h->side[3];
-  FTB_TRY(embed<T>(tok, h->embedding, x, MT, E, E, h->cfg.num_chars, s3));
-  FTB_TRY(run_transformer<T>(h, h->prenet, x, x32, tok, B, Tn, A, s3));
-  h->launches += 1;
-  h->pre_x = x;
-  h->pre_tok = tok;
-  h->pre_B = B;
-  h->pre_T = Tn;
-  h->pre_valid = true;
   return FTB_OK;
 }
 
@@ -379,7 +329,7 @@ extern "C" int ftb_fp_create(const ftb_fp_config* cfg, const ftb_tensor* tensors
     const bool w16 = h->half_mode(), w32 = !w16;
     FTB_TRY(h->make_conv(h->lin, "lin.weight", c.n_mels, c.d_model, 1, 0, false, "", "lin.bias", w32, w16));
     FTB_CHECK_CUDA(cudaStreamSynchronize(h->prep));
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 3; ++i) {
       FTB_CHECK_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
       FTB_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
     }
@@ -432,27 +382,8 @@ extern "C" int ftb_fp_predict(ftb_fp_handle* h, const int64_t* tokens, int B, in
     FTB_CHECK_CUDA(cudaEventRecord(h->ev_join[i], si));
     off += bytes[i];
   }
-  if (h->opt_overlap_prenet) {  // the caller's stream does NOT wait for it here: ftb_fp_synthesize does
-    FTB_CHECK_CUDA(cudaStreamWaitEvent(h->side[3], h->ev_fork, 0));
-    if (h->half_mode())
-      FTB_TRY(h->is_fp16() ? prefetch_fp_prenet<f16>(h, tokens, B, T) : prefetch_fp_prenet<bf16>(h, tokens, B, T));
-    else
-      FTB_TRY(prefetch_fp_prenet<float>(h, tokens, B, T));
-    FTB_CHECK_CUDA(cudaEventRecord(h->ev_join[3], h->side[3]));
-  }
   for (int i = 0; i < 3; ++i) FTB_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_join[i], 0));  // join
   return FTB_OK;
-}
-
-extern "C" int ftb_fp_set_option(ftb_fp_handle* h, int option, int value) {
-  FTB_REQUIRE(h, FTB_ERR_INVALID, "ftb_fp_set_option: null handle");
-  if (option == FTB_OPT_OVERLAP_PRENET) {
-    h->opt_overlap_prenet = value != 0;
-    if (!value) h->pre_valid = false;
-    return FTB_OK;
-  }
-  set_error("ftb_fp_set_option: unknown option %d", option);
-  return FTB_ERR_INVALID;
 }
 
 extern "C" int ftb_fp_synthesize(ftb_fp_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,

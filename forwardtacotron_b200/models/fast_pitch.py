@@ -188,19 +188,10 @@ class FastPitch(NativeModel):
                  mel_post_alloc=None) -> Dict[str, torch.Tensor]:
         self.eval()
         with torch.no_grad():
-            x = self._check_tokens(x)
-            h = self._get_handle(x.device)
-            lib = _lib.lib()
-            # stage B's prenet depends on the tokens only: let stage A start it on a side stream (x is not touched
-            # between the two calls)
-            _lib.check(lib.ftb_fp_set_option(h, _lib.FTB_OPT_OVERLAP_PRENET, 1))
-            try:
-                dur_hat, pitch_hat, energy_hat = self.predict(x, alpha)
-                pitch_hat = pitch_function(pitch_hat)
-                energy_hat = energy_function(energy_hat)
-                return self.synthesize(x, dur_hat, pitch_hat, energy_hat, mel_post_alloc)
-            finally:
-                _lib.check(lib.ftb_fp_set_option(h, _lib.FTB_OPT_OVERLAP_PRENET, 0))
+            dur_hat, pitch_hat, energy_hat = self.predict(x, alpha)
+            pitch_hat = pitch_function(pitch_hat)
+            energy_hat = energy_function(energy_hat)
+            return self.synthesize(x, dur_hat, pitch_hat, energy_hat, mel_post_alloc)
 
     def forward(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Teacher-forced forward in EVAL mode (models/fast_pitch.py:243-283): predictors and prenet with the token

@@ -374,11 +374,6 @@ int64_t ftb_fp_workspace_bytes(const ftb_fp_handle* h, int B, int T, int L);
 int ftb_fp_predict(ftb_fp_handle* h, const int64_t* tokens, int B, int T, float alpha, float* dur, float* pitch,
                    float* energy, void* workspace, int64_t workspace_bytes, void* stream);
 /* mel (B, n_mels, L) f32; the reference returns the same tensor as 'mel' and 'mel_post'. */
-/* FTB_OPT_OVERLAP_PRENET (default 0), as for ftb_ft_set_option: ftb_fp_predict also starts the prenet transformer of
- * stage B -- it depends on the tokens only -- on a side stream into handle-owned memory; the next ftb_fp_synthesize with
- * the same tokens pointer / shape picks the result up.  The tokens must not change between the two calls. */
-int ftb_fp_set_option(ftb_fp_handle* h, int option, int value);
-
 int ftb_fp_synthesize(ftb_fp_handle* h, const int64_t* tokens, const int32_t* cum, const float* pitch,
                       const float* energy, int B, int T, int L, float* mel, void* workspace,
                       int64_t workspace_bytes, void* stream);
