@@ -364,8 +364,8 @@ def fastpitch_extra(torch, dev, seed=5):
     res = {'metric': 'mel_frames_per_s', 'value': frames / (ms / 1e3), 'unit': 'frames/s', 'ms_per_step': ms,
            'workload': 'FastPitch.generate batch 128 x 300 phonemes, pitch*1.2 / energy+0.1 callbacks',
            'mel_frames_padded_L': int(out['mel'].shape[-1]), 'valid_frames': frames,
-           'numerics': 'IEEE-half tcgen05 GEMMs + tensor-core flash attention, fp32 accumulate / residual stream / '
-                       'LayerNorm; duration predictor fp32-grade (DESIGN.md 2)'}
+           'numerics': 'IEEE-half tcgen05 GEMMs (LayerNorm fused into the out_proj / conv2 epilogues) + tcgen05 / TMEM '
+                       'attention, fp32 accumulate / residual stream / LayerNorm; duration predictor fp32-grade (DESIGN.md 2)'}
     try:  # per-family kernel time of one more call (events around every launch)
         lib.ftb_profile_enable(1)
         model.generate(x, pitch_function=pf, energy_function=ef)

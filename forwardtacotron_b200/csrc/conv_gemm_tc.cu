@@ -225,10 +225,10 @@ __device__ __forceinline__ int split_unit_end(int kb, int nkb, int d, int ds) {
 }
 
 // MODE: 0 generic epilogue (bias / ReLU / BN affine / residual / pool / transposed output), 1 highway, 2 split
-// precision.  Separate instantiations because the kernel sits at its register cap (10 warps -> 3 per scheduler ->
+// precision, 3 direct epilogue (TMA stores), 4 direct epilogue with a fused LayerNorm over the N = 256 output row.  Separate instantiations because the kernel sits at its register cap (10 warps -> 3 per scheduler ->
 // 168 registers per thread): every mode only carries its own epilogue state.
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : tc::THREADS, 1)
+__global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : tc::THREADS, 1)
     conv_gemm_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr bool HIGHWAY = MODE == 1, SPLIT = MODE == 2;
   using namespace tc;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(MODE == 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, MODE == 3 ? EPI_WARPS_DIRECT : EPI_WARPS);
+      mbar_init(tempty0 + 8 * i, MODE >= 3 ? EPI_WARPS_DIRECT : EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(MODE == 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
         }
         continue;
       }
-      if (MODE == 3) {
+      if (MODE >= 3) {
         // ---- direct epilogue: everything happens in the accumulator layout (thread = output row, 32 consecutive
         // columns per TMEM read).  Per-column parameters come as uniform 16-byte loads (one L1 transaction per warp),
         // the residual as the thread's own contiguous 64 / 128 bytes, and a row-major output is packed into a swizzled
@@ -457,6 +457,127 @@ __global__ void __launch_bounds__(MODE == 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
         const int t_own = trow0 + lane;                     // time index of this thread's accumulator row
         const int64_t m_own = mrow0 + lane;
         const bool row_ok = t_own >= 0 && t_own < S;
+        if (MODE == 4) {
+          // ---- fused LayerNorm (models/fast_pitch.py:70-71,84,91: x = norm(x + sublayer(x)), post-LN): the tile is the
+          // whole 256-column row, so the epilogue normalises it before anything leaves the SM.  v = acc + bias + residual
+          // goes BACK into the accumulator (tcgen05.st), the row statistics are formed in two passes like torch's
+          // (mean, then sum of squared deviations) with the three column-group warps of a lane quarter exchanging their
+          // partial sums through shared memory, and y = (v - mean) rstd gamma + beta leaves as fp32 (the residual
+          // stream, in place over the residual rows this thread just read) and as the 16-bit operand of the next GEMM.
+          // partial sums [3 column groups][128 rows] in the pool's halo area (the pool never runs together with the LayerNorm)
+          float* lnbase = reinterpret_cast<float*>(staging_all) + EPI_WARPS_DIRECT * 512 + 2 * 768;
+          float* lnq = lnbase + cgp * 128;
+          const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX;
+          const int row = q * 32 + lane;
+          mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          float s1 = 0.f;
+          for (int ch = cgp; ch < nchunks; ch += NCG) {
+            uint32_t r[32];
+            tmem_ld32(tbase + ch * 32, r);
+            const int nb = c.n0 + ch * 32;
+            float rs[32];
+            if (row_ok) {
+              const float4* p = reinterpret_cast<const float4*>(a.res_f32 + m_own * ldr + nb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 v4 = __ldg(p + j);
+                rs[4 * j] = v4.x, rs[4 * j + 1] = v4.y, rs[4 * j + 2] = v4.z, rs[4 * j + 3] = v4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) rs[i] = 0.f;
+            }
+            const float* bp = spar + ch * 32;
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = __uint_as_float(r[i]) + bp[i] + rs[i];
+              s1 += v;
+              r[i] = __float_as_uint(v);
+            }
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"
+                "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(tbase + ch * 32),
+                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+                "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+                "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                : "memory");
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          lnq[row] = s1;
+          asm volatile("bar.sync %0, 96;" ::"r"(8 + q) : "memory");  // the three column-group warps of this lane quarter
+          const float mean = (lnbase[row] + lnbase[128 + row] + lnbase[256 + row]) * (1.f / 256.f);
+          asm volatile("bar.sync %0, 96;" ::"r"(8 + q) : "memory");
+          float s2 = 0.f;
+          for (int ch = cgp; ch < nchunks; ch += NCG) {
+            uint32_t r[32];
+            tmem_ld32(tbase + ch * 32, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float d = __uint_as_float(r[i]) - mean;
+              s2 = fmaf(d, d, s2);
+            }
+          }
+          lnq[row] = s2;
+          asm volatile("bar.sync %0, 96;" ::"r"(8 + q) : "memory");
+          const float rstd = 1.f / sqrtf((lnbase[row] + lnbase[128 + row] + lnbase[256 + row]) * (1.f / 256.f) + 1e-5f);
+          asm volatile("bar.sync %0, 96;" ::"r"(8 + q) : "memory");  // partials consumed before the next tile overwrites them
+          bool released = false;
+          for (int ch = cgp; ch < nchunks; ch += NCG) {
+            uint32_t r[32];
+            tmem_ld32(tbase + ch * 32, r);
+            const int nb = c.n0 + ch * 32;
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ch + NCG >= nchunks) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+              released = true;
+            }
+            float v[32];
+            const float* gp = spar + 256 + ch * 32;
+            const float* hp = spar + 512 + ch * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf((__uint_as_float(r[i]) - mean) * rstd, gp[i], hp[i]);
+#pragma unroll
+            for (int hcol = 0; hcol < 2; ++hcol) {  // fp32 residual stream
+              if (lane == 0) tma_store_wait_read1();
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(tile + st_off[j]) =
+                    make_float4(v[16 * hcol + 4 * j], v[16 * hcol + 4 * j + 1], v[16 * hcol + 4 * j + 2], v[16 * hcol + 4 * j + 3]);
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&a.map_o32, smem_u32(tile), n_off + nb + 16 * hcol, trow0, c.b);
+                tma_store_commit();
+              }
+            }
+            {  // 16-bit operand of the next GEMM
+              if (lane == 0) tma_store_wait_read1();
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(tile + st_off[j]) =
+                    make_uint4(pack16x2(v[8 * j], v[8 * j + 1], f16o), pack16x2(v[8 * j + 2], v[8 * j + 3], f16o),
+                               pack16x2(v[8 * j + 4], v[8 * j + 5], f16o), pack16x2(v[8 * j + 6], v[8 * j + 7], f16o));
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&a.map_o16, smem_u32(tile), n_off + nb, trow0, c.b);
+                tma_store_commit();
+              }
+            }
+          }
+          if (!released) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+          }
+          continue;
+        }
         float res[32];
         auto load_res = [&](int ch) {
           const int nb = c.n0 + ch * 32;
@@ -741,7 +862,7 @@ __global__ void __launch_bounds__(MODE == 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
       }
     }
   }
-  if (MODE == 3 && warp >= 2 && lane == 0) tma_store_wait_all();  // the staging tiles are read until the stores complete
+  if (MODE >= 3 && warp >= 2 && lane == 0) tma_store_wait_all();  // the staging tiles are read until the stores complete
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -856,6 +977,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   // ---- direct epilogue (MODE 3): needs 16-byte aligned rows / parameter vectors; anything else takes the legacy one
   static const int force_legacy = getenv("FTB_EPI_LEGACY") ? atoi(getenv("FTB_EPI_LEGACY")) : 0;
   bool direct = !force_legacy && !o.highway && !o.split_in && !o.split_out;
+  const bool ln = o.ln_gamma != nullptr;
   auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
   if (o.out_bf16) direct = direct && o.ldo % 8 == 0 && al16(o.out_bf16);
   if (o.out_f32) direct = direct && o.ldo % 4 == 0 && al16(o.out_f32);
@@ -882,8 +1004,17 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
       }
     }
   }
+  if (ln) {  // fused LayerNorm: the tile must hold whole rows and the direct epilogue's alignment rules must hold
+    FTB_REQUIRE(direct && n_items == 1 && items[0].N == BN_MAX && a.bn == BN_MAX && o.out_f32 && o.out_bf16 && o.res_f32 &&
+                    !o.res_bf16 && !o.pool && !o.out_t && !o.hl_in && o.ln_beta && items[0].bias && !items[0].scale &&
+                    !items[0].relu && a.out_scale == 1.f && ((uintptr_t)o.ln_gamma & 15) == 0 && ((uintptr_t)o.ln_beta & 15) == 0,
+                FTB_ERR_UNSUPPORTED, "conv_gemm_bf16: the fused LayerNorm needs N = 256, bias, fp32 residual, fp32 + 16-bit outputs");
+    a.prob[0].scale = o.ln_gamma;  // staged like the BN affine, applied after the normalisation
+    a.prob[0].shift = o.ln_beta;
+  }
   static bool configured = false;
   if (!configured) {
+    FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -893,6 +1024,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   const int grid = std::min(tiles, sm_count());
   if (o.highway) conv_gemm_tc_kernel<1><<<grid, THREADS, SMEM_BYTES, s>>>(a);
   else if (o.split_in) conv_gemm_tc_kernel<2><<<grid, THREADS, SMEM_BYTES, s>>>(a);
+  else if (ln) conv_gemm_tc_kernel<4><<<grid, 32 * (2 + EPI_WARPS_DIRECT), SMEM_BYTES, s>>>(a);
   else if (direct) conv_gemm_tc_kernel<3><<<grid, 32 * (2 + EPI_WARPS_DIRECT), SMEM_BYTES, s>>>(a);
   else conv_gemm_tc_kernel<0><<<grid, THREADS, SMEM_BYTES, s>>>(a);
   FTB_CHECK_LAUNCH();

@@ -55,6 +55,7 @@ struct ftb_fp_handle : ftb::ModelBase {
   }
   bool half_mode() const { return cfg.gemm_mode == 0 || cfg.gemm_mode == 2; }
   bool is_fp16() const { return cfg.gemm_mode == 0; }
+  int opt_unfused_ln = getenv("FTB_UNFUSED_LN") ? atoi(getenv("FTB_UNFUSED_LN")) : 0;  // 1: stand-alone LayerNorm launches
 };
 
 namespace ftb {
@@ -144,6 +145,18 @@ static int run_transformer(ftb_fp_handle* h, TransformerW& W, T* x, float* x32_b
   for (FftBlockW& L : W.layers) {
     FTB_TRY(h->gemm<T>(L.qkv, x, E, B, S, act_out(w.qkv, 3 * E), nullptr, 0, 1.f, s));
     FTB_TRY(attention<T>(w.qkv, mask_tokens, w.ctx, B, S, E, W.heads, s));
+    // E = 256 = one GEMM tile: the post-LN residual blocks x = norm(x + sublayer(x)) (models/fast_pitch.py:84,91) run
+    // inside the out_proj / conv2 epilogues -- the fp32 stream is updated in place, the 16-bit operand copy comes with it
+    const bool fuse_ln = !kF32 && E == 256 && L.conv2.k == 1 && !h->opt_unfused_ln;
+    if (fuse_ln) {
+      Out xo = act_out(x, E);
+      xo.f32 = x32;
+      FTB_TRY(h->gemm<T>(L.out_proj, w.ctx, E, B, S, xo, nullptr, E, 1.f, s, x32, L.n1w, L.n1b));
+      FTB_TRY(h->gemm<T>(L.conv1, x, E, B, S, act_out(w.f1, W.dfft), nullptr, 0, 1.f, s));  // + bias, ReLU
+      FTB_TRY(h->gemm<T>(L.conv2, w.f1, W.dfft, B, S, xo, nullptr, E, 1.f, s, x32, L.n2w, L.n2b));
+      h->launches += 1;
+      continue;
+    }
     FTB_TRY(h->gemm<T>(L.out_proj, w.ctx, E, B, S, a32, nullptr, E, 1.f, s, x32));  // + bias + residual (fp32)
     FTB_TRY(layernorm(w.a32, L.n1w, L.n1b, x32, x16, x16_fp16, M, E, s));
     FTB_TRY(h->gemm<T>(L.conv1, x, E, B, S, act_out(w.f1, W.dfft), nullptr, 0, 1.f, s));  // + bias, ReLU

@@ -31,6 +31,8 @@ struct TcOut {
   int split_out = 0;      // > 0: write the 16-bit output as 3 parts, split_out channels apart (ldo >= 3 * split_out)
   bool hl_in = false;     // x is (B,S,2*Cin): 16-bit parts hi | lo (rnn_bidir lo_off), weights packed by pack mode 4 / 5
                           // as [hi | hi | lo] along K: hi.hi + lo.hi + hi.lo = a 22-bit (half) / 16-bit (bf16) operand pair
+  const float* ln_gamma = nullptr;  // fused LayerNorm over the N = 256 output row (after bias + fp32 residual): weight ...
+  const float* ln_beta = nullptr;   // ... and bias; needs out_f32 AND out_bf16 (the fp32 stream and the next GEMM's operand)
   bool highway = false;  // N = 2C interleaved [32 x1 | 32 x2] groups -> y (C) = sigmoid(x2) relu(x1) + (1 - sigmoid(x2)) res_bf16
 };
 int tc_tile_n(int N);

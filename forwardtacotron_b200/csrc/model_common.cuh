@@ -176,7 +176,7 @@ struct ModelBase {
   // y = epilogue(conv(x)) with the kernel matching T: float -> fp32 SIMT, bf16 -> tcgen05
   template <typename T>
   int gemm(const Layer& L, const T* x, int lda, int B, int S, Out o, const T* residual, int ldr, float out_scale,
-           cudaStream_t s, const float* residual32 = nullptr) {
+           cudaStream_t s, const float* residual32 = nullptr, const float* ln_gamma = nullptr, const float* ln_beta = nullptr) {
     ftb_conv_desc d;
     memset(&d, 0, sizeof(d));
     d.B = B;
@@ -227,6 +227,8 @@ struct ModelBase {
     to.out_scale = out_scale;
     to.fp16 = std::is_same<T, f16>::value;
     to.hl_in = L.hl;
+    to.ln_gamma = ln_gamma;
+    to.ln_beta = ln_beta;
     return conv_gemm_group((const bf16*)x, lda, B, S, L.CinP, &it, 1, to, s);
   }
 

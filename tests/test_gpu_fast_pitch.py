@@ -86,3 +86,25 @@ def test_teacher_forced_forward_against_reference_fixture(gemm_mode):
     model.train()
     with pytest.raises(NotImplementedError):
         model(batch)
+
+
+def test_fused_layernorm_epilogue_matches_the_standalone_layernorm(monkeypatch):
+    """x = norm(x + sublayer(x)) (models/fast_pitch.py:84,91) runs inside the out_proj / conv2 GEMM epilogues (d_model 256
+    = one tile: the row is complete in tensor memory).  FTB_UNFUSED_LN=1 (read when a native handle is created) keeps the
+    stand-alone LayerNorm launches.  Same two-pass statistics in fp32, different summation order -> equal to a few ulp of
+    the 16-bit operand copy, far inside the parity budget; and both inside the budget against the oracle."""
+    x = synth.synthetic_tokens(4, 130, seed=3)
+    fused, _ = cuda_model('fast_pitch', 0)
+    a = fused.generate(x.cuda())
+    monkeypatch.setenv('FTB_UNFUSED_LN', '1')
+    plain, _ = cuda_model('fast_pitch', 0)
+    b = plain.generate(x.cuda())
+    monkeypatch.delenv('FTB_UNFUSED_LN')
+    assert torch.equal(rounded(a['dur']), rounded(b['dur']))
+    d = (a['mel'] - b['mel']).abs()
+    print('fused vs stand-alone LayerNorm: max-abs', float(d.max()), 'mean-abs', float(d.mean()))
+    assert float(d.max()) < 5e-3 and float(d.mean()) < 5e-4
+    want = mo.fp_generate(cpu_state_dict(fused), x)
+    assert_close(a['mel'], want['mel'], what='fused LayerNorm vs oracle')
+    from forwardtacotron_b200 import _lib
+    assert _lib.lib().ftb_tc_timeout_count() == 0
