@@ -27,13 +27,16 @@ __global__ void __launch_bounds__(att::THREADS)
     attention_kernel(const T* __restrict__ qkv, const int64_t* __restrict__ tokens, T* __restrict__ ctx, int S, int E,
                      float scale) {
   using namespace att;
-  constexpr int KLD = HD + 1, PLD = BKV + 1, OC = HD / 16;  // OC output columns per thread
-  extern __shared__ float sm[];
-  float* Qs = sm;                 // [BQ][HD]
-  float* Ks = Qs + BQ * HD;       // [BKV][KLD]
-  float* Vs = Ks + BKV * KLD;     // [BKV][HD]
-  float* Ps = Vs + BKV * HD;      // [BQ][PLD]
-  float* msk = Ps + BQ * PLD;     // [BKV] additive mask (0 or -inf)
+  // Q, K and P sit TRANSPOSED in shared memory ([d][row] / [key][row], rows padded to TLD): the four rows a thread
+  // multiplies are then one 16-byte load (a broadcast for Q and P, conflict-free for K) instead of four scalar ones --
+  // the inner products were bound by shared-memory instructions (8 loads per 16 FMAs, now 2).
+  constexpr int TLD = BQ + 4, OC = HD / 16;  // OC output columns per thread
+  extern __shared__ __align__(16) float sm[];
+  float* Qt = sm;                 // [HD][TLD]   Q^T, pre-scaled
+  float* Kt = Qt + HD * TLD;      // [HD][TLD]   K^T
+  float* Vs = Kt + HD * TLD;      // [BKV][HD]
+  float* Pt = Vs + BKV * HD;      // [BKV][TLD]  P^T
+  float* msk = Pt + BKV * TLD;    // [BKV] additive mask (0 or -inf)
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(att::THREADS)
 
   for (int i = tid; i < BQ * HD; i += THREADS) {
     const int r = i / HD, d = i % HD;
-    Qs[i] = (q0 + r < S) ? ActIO<T>::load(base + (int64_t)(q0 + r) * row_stride + d) * scale : 0.f;
+    Qt[d * TLD + r] = (q0 + r < S) ? ActIO<T>::load(base + (int64_t)(q0 + r) * row_stride + d) * scale : 0.f;
   }
   float m_run[4], l_run[4], o[4][OC];
 #pragma unroll
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(att::THREADS)
       const int r = i / HD, d = i % HD;
       const bool ok = k0 + r < S;
       const T* p = base + (int64_t)(k0 + r) * row_stride + d;
-      Ks[r * KLD + d] = ok ? ActIO<T>::load(p + E) : 0.f;
+      Kt[d * TLD + r] = ok ? ActIO<T>::load(p + E) : 0.f;
       Vs[r * HD + d] = ok ? ActIO<T>::load(p + 2 * E) : 0.f;
     }
     if (tid < BKV) {
@@ -76,11 +79,9 @@ __global__ void __launch_bounds__(att::THREADS)
       for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
 #pragma unroll 4
     for (int d = 0; d < HD; ++d) {
-      float qv[4], kv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) qv[i] = Qs[(ty * 4 + i) * HD + d];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) kv[j] = Ks[(tx * 4 + j) * KLD + d];
+      const float4 q4 = *reinterpret_cast<const float4*>(Qt + d * TLD + ty * 4);
+      const float4 k4 = *reinterpret_cast<const float4*>(Kt + d * TLD + tx * 4);
+      const float qv[4] = {q4.x, q4.y, q4.z, q4.w}, kv[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(att::THREADS)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float p = expf(s[i][j] - m_use);
-        Ps[(ty * 4 + i) * PLD + tx * 4 + j] = p;
+        Pt[(tx * 4 + j) * TLD + ty * 4 + i] = p;
         sum += p;
       }
 #pragma unroll
@@ -118,11 +119,14 @@ __global__ void __launch_bounds__(att::THREADS)
     // O += P V : rows ty*4.., cols tx*OC..
 #pragma unroll 2
     for (int j = 0; j < BKV; ++j) {
-      float pv[4], vv[OC];
+      const float4 p4 = *reinterpret_cast<const float4*>(Pt + j * TLD + ty * 4);
+      const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+      float vv[OC];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) pv[i] = Ps[(ty * 4 + i) * PLD + j];
-#pragma unroll
-      for (int c = 0; c < OC; ++c) vv[c] = Vs[j * HD + tx * OC + c];
+      for (int c = 0; c < OC; c += 4) {
+        const float4 v4 = *reinterpret_cast<const float4*>(Vs + j * HD + tx * OC + c);
+        vv[c] = v4.x, vv[c + 1] = v4.y, vv[c + 2] = v4.z, vv[c + 3] = v4.w;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -144,7 +148,7 @@ template <typename T, int HD>
 static int launch_attention(const T* qkv, const int64_t* tokens, T* ctx, int B, int S, int E, int heads,
                             cudaStream_t s) {
   using namespace att;
-  const size_t smem = sizeof(float) * (BQ * HD + BKV * (HD + 1) + BKV * HD + BQ * (BKV + 1) + BKV);
+  const size_t smem = sizeof(float) * (2 * HD * (BQ + 4) + BKV * HD + BKV * (BQ + 4) + BKV);
   static bool configured = false;
   if (!configured) {
     FTB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

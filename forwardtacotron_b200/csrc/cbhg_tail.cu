@@ -69,48 +69,6 @@ __device__ long long* g_tail_dbg = nullptr;
     if (dbg && (unit) < 128) dbg[(unit) * 8 + (slot)] = clock64();         \
   } while (0)
 
-namespace tail {
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the EVEN CTA of the pair (cute::Sm100MmaPeerBitMask)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// TMA load issued by either CTA of the pair into its OWN shared memory, completing bytes on the LEADER's barrier
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_local, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar_local & PEER_MASK), "r"(c0), "r"(c1)
-      : "memory");
-}
-// D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] . B[smem, 64 of the 128 n-rows per CTA]; issued by the leader only
-__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the barrier at this offset in BOTH CTAs once every MMA issued so far has retired
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar_local) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_local & PEER_MASK) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar_local, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar_local), "r"(cta));
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
-}
-}  // namespace tail
-
 struct alignas(64) TailArgs {
   CUtensorMap map_x;                     // (ld2, M) 16-bit, box 64 x 128
   CUtensorMap map_w[tail::MAX_HW + 2];   // weights in k-block-major order (cbhg_tail_pack): (64, K/64 * N), box 64 x UN/2

@@ -89,15 +89,20 @@ static_assert(sizeof(TcArgs) <= 4096 - 64, "kernel parameter space");
 
 struct TileCoord {
   int p, b, t0, n0;
+  bool valid;  // pair mode: the odd CTA's tile of the last pair of a problem may not exist (b == B: loads zero-fill, stores clip)
 };
-__device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile) {
+// pair > 0: `tile` counts PAIR tiles (two consecutive row tiles with the same weights); crank picks this CTA's one
+__device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile, int pair = 0, int crank = 0) {
   int p = 0;
   while (p + 1 < a.nprob && tile >= a.prob[p + 1].tile_begin) ++p;
   const int local = tile - a.prob[p].tile_begin;
-  const int nt = local % a.prob[p].n_tiles, rest = local / a.prob[p].n_tiles;
+  const int nt = local % a.prob[p].n_tiles;
+  int rest = local / a.prob[p].n_tiles;
+  if (pair) rest = 2 * rest + crank;
   TileCoord c;
   c.p = p;
   c.b = rest / a.m_tiles;
+  c.valid = c.b < a.B;
   c.t0 = (rest % a.m_tiles) * a.m_stride - a.pool;
   c.n0 = nt * a.bn;
   return c;
@@ -227,10 +232,20 @@ __device__ __forceinline__ int split_unit_end(int kb, int nkb, int d, int ds) {
 // MODE: 0 generic epilogue (bias / ReLU / BN affine / residual / pool / transposed output), 1 highway, 2 split
 // precision, 3 direct epilogue (TMA stores), 4 direct epilogue with a fused LayerNorm over the N = 256 output row.  Separate instantiations because the kernel sits at its register cap (10 warps -> 3 per scheduler ->
 // 168 registers per thread): every mode only carries its own epilogue state.
-template <int MODE>
+// PAIR: two CTAs of a cluster work as one tcgen05 cta_group::2 unit on two consecutive row tiles of the same weights:
+// M = 256 (each CTA keeps its own activation tile and its own 128 accumulator rows), and each CTA loads only half of
+// every weight tile.  A 128-row tile streams 16 KB of activations and 32 KB of weights per k-block of ~660 clk of MMAs
+// -- 73 B/clk/SM, more than L2 delivers to 148 SMs at once (the conv bank and the K = 256 layers were bound by it); the
+// pair brings it to 48 B/clk.  The leader CTA issues the MMAs; loads of both CTAs complete on the leader's barriers,
+// commits are multicast, the peer's epilogue warps release accumulators on the leader's barrier.
+template <int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : tc::THREADS, 1)
     conv_gemm_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr bool HIGHWAY = MODE == 1, SPLIT = MODE == 2;
+  static_assert(!PAIR || MODE >= 3, "CTA pairs are built for the direct epilogues");
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
+  const bool leader = crank == 0;
+  const int cta0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, cta_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   using namespace tc;
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B tiles need 1024-byte alignment (offset arithmetic keeps the pointer in the shared space)
@@ -253,27 +268,34 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, MODE >= 3 ? EPI_WARPS_DIRECT : EPI_WARPS);
+      mbar_init(tempty0 + 8 * i, (MODE >= 3 ? EPI_WARPS_DIRECT : EPI_WARPS) * (PAIR ? 2 : 1));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // one full warp allocates (and later frees) the accumulator columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      const uint32_t tx = (uint32_t)(a.box_rows * BK * 2 + a.bn * BK * 2);
+      // bytes that complete a stage: one CTA's A + B tiles, or (pair) both CTAs' A tiles + the two halves of the B tile
+      const uint32_t tx = (uint32_t)((PAIR ? 2 : 1) * a.box_rows * BK * 2 + a.bn * BK * 2);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const TileCoord c = decode_tile(a, tile);
+      for (int tile = cta0; tile < a.total_tiles; tile += cta_step) {
+        const TileCoord c = decode_tile(a, tile, PAIR, crank);
         const TcProb& P = a.prob[c.p];
         // K order = (part product, tap, 64-channel block); the packed weights follow it, so their K offset is kb * BK.
         // split_in: product `seg` reads activation part (amap >> 4 seg) & 15 -- smallest products first:
@@ -285,10 +307,15 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
           const uint32_t st = it % STAGES;
           if (it >= STAGES) mbar_wait(empty0 + 8 * st, ((it / STAGES) - 1) & 1);
           const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
-          mbar_expect_tx(full0 + 8 * st, tx);
+          if (!PAIR || leader) mbar_expect_tx(full0 + 8 * st, tx);
           const int acb = cb + (int)((amap >> (4 * seg)) & 15u) * a.cblocks;
-          tma_load_3d(sa, &a.map_a, full0 + 8 * st, acb * BK, c.t0 + j - P.pad_left, c.b);
-          tma_load_2d(sb, &P.map_w, full0 + 8 * st, kb * BK, c.n0);
+          if (PAIR) {
+            tma_load_3d_pair(sa, &a.map_a, full0 + 8 * st, acb * BK, c.t0 + j - P.pad_left, c.b);
+            tma_load_2d_pair(sb, &P.map_w, full0 + 8 * st, kb * BK, c.n0 + crank * (a.bn >> 1));  // this CTA's half of the rows
+          } else {
+            tma_load_3d(sa, &a.map_a, full0 + 8 * st, acb * BK, c.t0 + j - P.pad_left, c.b);
+            tma_load_2d(sb, &P.map_w, full0 + 8 * st, kb * BK, c.n0);
+          }
           if (++cb == a.cblocks) {
             cb = 0;
             if (++j == P.ktaps) j = 0, ++seg;
@@ -297,12 +324,12 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
+    if (lane == 0 && leader) {  // ===== MMA issuer (of the pair) =====
       uint32_t it = 0, tl = 0, un = 0;  // un: accumulation units issued (split-precision mode)
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tl) {
-        const TileCoord c = decode_tile(a, tile);
+      for (int tile = cta0; tile < a.total_tiles; tile += cta_step, ++tl) {
+        const TileCoord c = decode_tile(a, tile, PAIR, crank);
         const TcProb& P = a.prob[c.p];
-        const uint32_t idesc = P.idesc;
+        const uint32_t idesc = PAIR ? ((P.idesc & ~(31u << 24)) | ((uint32_t)(256 >> 4) << 24)) : P.idesc;  // pair: M = 256
         if (SPLIT) {
           // Split-precision mode: the tensor core adds into the fp32 accumulator with truncation, a bias that grows with
           // the length of the accumulation chain (measured: 80 K-steps put the duration predictor 5x further from an
@@ -339,11 +366,15 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = tiles_u32 + st * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty0 + 8 * st);  // frees the smem stage when these MMAs retire
+          for (int k = 0; k < BK / 16; ++k) {
+            if (PAIR) umma_pair(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if (PAIR) umma_commit_pair(empty0 + 8 * st);
+          else umma_commit(empty0 + 8 * st);  // frees the smem stage when these MMAs retire
         }
-        umma_commit(tfull0 + 8 * buf);  // accumulator complete
+        if (PAIR) umma_commit_pair(tfull0 + 8 * buf);
+        else umma_commit(tfull0 + 8 * buf);  // accumulator complete
       }
     }
   } else {  // ===== epilogue warps 2..9 =====
@@ -360,8 +391,8 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
     int st_off[4];  // direct epilogue: byte offset of this thread's four 16-byte chunks in a 32 x 64 B SWIZZLE_64B tile
 #pragma unroll
     for (int j = 0; j < 4; ++j) st_off[j] = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tl) {
-      const TileCoord c = decode_tile(a, tile);
+    for (int tile = cta0; tile < a.total_tiles; tile += cta_step, ++tl) {
+      const TileCoord c = decode_tile(a, tile, PAIR, crank);
       const TcProb& P = a.prob[c.p];
       const uint32_t buf = tl & 1;
       const int pN = P.N;
@@ -456,7 +487,7 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
         const bool f16o = a.fp16 != 0;
         const int t_own = trow0 + lane;                     // time index of this thread's accumulator row
         const int64_t m_own = mrow0 + lane;
-        const bool row_ok = t_own >= 0 && t_own < S;
+        const bool row_ok = c.valid && t_own >= 0 && t_own < S;
         if (MODE == 4) {
           // ---- fused LayerNorm (models/fast_pitch.py:70-71,84,91: x = norm(x + sublayer(x)), post-LN): the tile is the
           // whole 256-column row, so the epilogue normalises it before anything leaves the SM.  v = acc + bias + residual
@@ -533,7 +564,7 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (ch + NCG >= nchunks) {
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-              if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+              if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * buf); else mbar_arrive(tempty0 + 8 * buf); }
               released = true;
             }
             float v[32];
@@ -574,7 +605,7 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
           }
           if (!released) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * buf); else mbar_arrive(tempty0 + 8 * buf); }
           }
           continue;
         }
@@ -618,7 +649,7 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
         bool released = false;
         if (a.dbg_skip_epi == 1) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * buf); else mbar_arrive(tempty0 + 8 * buf); }
           continue;
         }
         for (int ch = cgp; ch < nchunks; ch += NCG) {
@@ -628,7 +659,7 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (ch + NCG >= nchunks) {  // last TMEM read of this warp for this tile: hand the buffer back
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * buf); else mbar_arrive(tempty0 + 8 * buf); }
             released = true;
           }
           // ---- value transform, 4 columns at a time: the per-column parameters are broadcast 16-byte shared-memory
@@ -731,7 +762,7 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
         }
         if (!released) {  // no chunk for this warp in this tile
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * buf); else mbar_arrive(tempty0 + 8 * buf); }
         }
         continue;
       }
@@ -864,10 +895,12 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
   }
   if (MODE >= 3 && warp >= 2 && lane == 0) tma_store_wait_all();  // the staging tiles are read until the stores complete
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA frees its TMEM or exits while the pair may still address it
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -943,6 +976,32 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)a.box_rows, 1};
     FTB_TRY(make_map(&a.map_a, x, 3, dims, strides, box));
   }
+  // ---- direct epilogue (MODE 3): needs 16-byte aligned rows / parameter vectors; anything else takes the legacy one
+  static const int force_legacy = getenv("FTB_EPI_LEGACY") ? atoi(getenv("FTB_EPI_LEGACY")) : 0;
+  bool direct = !force_legacy && !o.highway && !o.split_in && !o.split_out;
+  const bool ln = o.ln_gamma != nullptr;
+  static const int pair_env = getenv("FTB_GEMM_PAIR") ? atoi(getenv("FTB_GEMM_PAIR")) : 1;
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (o.out_bf16) direct = direct && o.ldo % 8 == 0 && al16(o.out_bf16);
+  if (o.out_f32) direct = direct && o.ldo % 4 == 0 && al16(o.out_f32);
+  if (o.res_bf16) direct = direct && o.ldr % 8 == 0 && al16(o.res_bf16);
+  if (o.res_f32) direct = direct && o.ldr % 4 == 0 && al16(o.res_f32);
+  int out_cols = 0;
+  for (int i = 0; i < n_items; ++i) {
+    direct = direct && al16(items[i].bias) && al16(items[i].scale) && al16(items[i].shift) && items[i].n_offset % 4 == 0;
+    out_cols = std::max(out_cols, items[i].n_offset + items[i].N);
+  }
+  // CTA pairs: direct epilogues with 256-wide tiles whose N is a whole number of tiles (each CTA loads a 128-row half
+  // of every weight tile), and enough row tiles for two CTAs
+  bool pair = pair_env != 0 && direct && a.bn == BN_MAX && sm_count() >= 2;
+  int64_t pair_tiles = 0;
+  for (int i = 0; i < n_items; ++i) {
+    pair = pair && items[i].N % BN_MAX == 0;
+    pair_tiles += (int64_t)cdiv(items[i].N, BN_MAX) * cdiv((int64_t)a.m_tiles * B, 2);
+  }
+  // ... and only when every cluster works through several pair tiles: on the phoneme-rate predictor GEMMs (one tile per
+  // CTA) the pair only adds its cluster set-up (measured 11 -> 12.6 us); on the frame-rate FastPitch GEMMs it gives 4 %
+  pair = pair && pair_tiles >= (pair_env > 1 ? 1 : 2 * (sm_count() / 2));
   // heaviest problems first: with the static round-robin schedule this is longest-processing-time-first
   int order[MAXP];
   for (int i = 0; i < n_items; ++i) order[i] = i;
@@ -956,7 +1015,7 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
     const int ktot = nseg * it.ktaps * Cin;
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)it.N};  // rows >= N of the last tile are zero-filled by TMA
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)a.bn};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(pair ? a.bn / 2 : a.bn)};
     FTB_TRY(make_map(&P.map_w, it.w, 2, dims, strides, box));
     P.bias = it.bias;
     P.scale = it.scale;
@@ -971,23 +1030,9 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
     P.nkb = nseg * it.ktaps * a.cblocks;
     P.tile_begin = tiles;
     P.idesc = idesc_16(it.N >= a.bn ? a.bn : (int)align_up(it.N, 16), o.fp16);
-    tiles += P.n_tiles * a.m_tiles * B;
+    tiles += pair ? P.n_tiles * cdiv((int64_t)a.m_tiles * B, 2) : P.n_tiles * a.m_tiles * B;  // pair: pair tiles
   }
   a.total_tiles = tiles;
-  // ---- direct epilogue (MODE 3): needs 16-byte aligned rows / parameter vectors; anything else takes the legacy one
-  static const int force_legacy = getenv("FTB_EPI_LEGACY") ? atoi(getenv("FTB_EPI_LEGACY")) : 0;
-  bool direct = !force_legacy && !o.highway && !o.split_in && !o.split_out;
-  const bool ln = o.ln_gamma != nullptr;
-  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-  if (o.out_bf16) direct = direct && o.ldo % 8 == 0 && al16(o.out_bf16);
-  if (o.out_f32) direct = direct && o.ldo % 4 == 0 && al16(o.out_f32);
-  if (o.res_bf16) direct = direct && o.ldr % 8 == 0 && al16(o.res_bf16);
-  if (o.res_f32) direct = direct && o.ldr % 4 == 0 && al16(o.res_f32);
-  int out_cols = 0;
-  for (int i = 0; i < n_items; ++i) {
-    direct = direct && al16(items[i].bias) && al16(items[i].scale) && al16(items[i].shift) && items[i].n_offset % 4 == 0;
-    out_cols = std::max(out_cols, items[i].n_offset + items[i].N);
-  }
   if (direct && (o.out_bf16 || o.out_f32)) {
     FTB_REQUIRE(out_cols <= o.ldo, FTB_ERR_INVALID, "conv_gemm_bf16: ldo=%d is smaller than n_offset + N = %d", o.ldo, out_cols);
     for (int e = 0; e < 2; ++e) {
@@ -1016,10 +1061,30 @@ int conv_gemm_group(const __nv_bfloat16* x, int lda, int B, int S, int Cin, cons
   if (!configured) {
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FTB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
+  }
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * std::min(tiles, sm_count() / 2));
+    cfg.blockDim = dim3(32 * (2 + EPI_WARPS_DIRECT));
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (ln) FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<4, true>, a));
+    else FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<3, true>, a));
+    count_launch();
+    return FTB_OK;
   }
   const int grid = std::min(tiles, sm_count());
   if (o.highway) conv_gemm_tc_kernel<1><<<grid, THREADS, SMEM_BYTES, s>>>(a);
