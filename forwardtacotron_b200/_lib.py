@@ -18,6 +18,7 @@ FTB_OPT_OVERLAP_PRENET = 1
 FTB_OPT_SERIALIZE = 2
 FTB_OPT_DUR_SIMT = 3
 FTB_OPT_UNFUSED_TAIL = 4
+FTB_OPT_LSTM_MIN_CHUNK = 5
 FTB_TUNE_LSTM_MIN_CHUNK = 1
 FTB_TUNE_GRU_MIN_CHUNK = 2
 

@@ -57,6 +57,7 @@ struct ftb_ft_handle : ftb::ModelBase {
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   int opt_overlap_prenet = 0, opt_serialize = 0;
   int opt_dur_simt = getenv("FTB_DUR_SIMT") ? atoi(getenv("FTB_DUR_SIMT")) : 0;  // 1: duration predictor on the fp32 SIMT kernel
+  int opt_lstm_min_chunk = 0;  // FTB_OPT_LSTM_MIN_CHUNK: utterances per decoder-LSTM cluster for this handle (0: ftb_tune default)
   int opt_unfused_tail = getenv("FTB_UNFUSED_TAIL") ? atoi(getenv("FTB_UNFUSED_TAIL")) : 0;  // 1: CBHG tail layer by layer
   char* pre_buf = nullptr;
   int64_t pre_cap = 0;
@@ -364,7 +365,7 @@ static int run_synthesize(ftb_ft_handle* h, const int64_t* tok, const int32_t* c
   FTB_TRY(length_index(cum, fidx, B, Tn, L, (int)MT, s));
   // mel_lens: packed sequences (teacher-forced forward in eval mode; ragged batches) -- rows stop at mel_lens[b]
   FTB_TRY(rnn_bidir(xg, h->lstm.w_hh, nullptr, dec, B, L, RH, 1, out_kind<T>(), s, fidx, dec_ld, HP == 2 ? 2 * RH : 0,
-                    mel_lens, pad_value));
+                    mel_lens, pad_value, h->opt_lstm_min_chunk));
   if (melP != NM) FTB_CHECK_CUDA(cudaMemsetAsync(mel_cl, 0, (size_t)ML * melP * sizeof(T), s));
   Out o = act_out(mel_cl, melP);
   o.t = mel;  // 'mel' (B,80,L) and the channel-last copy the postnet reads, from one epilogue
@@ -567,6 +568,11 @@ extern "C" int ftb_ft_set_option(ftb_ft_handle* h, int option, int value) {
   }
   if (option == FTB_OPT_UNFUSED_TAIL) {
     h->opt_unfused_tail = value != 0;
+    return FTB_OK;
+  }
+  if (option == FTB_OPT_LSTM_MIN_CHUNK) {
+    FTB_REQUIRE(value == 0 || (value >= 8 && value <= 32), FTB_ERR_INVALID, "FTB_OPT_LSTM_MIN_CHUNK: 0 or 8..32");
+    h->opt_lstm_min_chunk = value;
     return FTB_OK;
   }
   set_error("ftb_ft_set_option: unknown option %d", option);

@@ -54,7 +54,8 @@ int cbhg_tail(const __nv_bfloat16* p2, int ld2, int64_t M, const __nv_bfloat16* 
 // output pad_value (LSTM; 0 elsewhere) beyond them, the reverse direction starts at the last valid step.
 int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
               int out_bf16, cudaStream_t s, const int32_t* xrow = nullptr, int ldo = 0, int lo_off = 0,
-              const int32_t* lens = nullptr, float pad_value = 0.f);
+              const int32_t* lens = nullptr, float pad_value = 0.f, int min_chunk = 0);  // min_chunk > 0: smallest number of
+              // utterances per LSTM cluster for THIS call (0 = the process-wide ftb_tune setting)
 
 // length_regulator.cu: idx (B,L) int32 <- row of the phoneme-rate tensor that frame (b, j) repeats: b*T + t with
 // cum[b,t-1] <= j < cum[b,t], or pad_row for the zero-padded tail j >= cum[b,T-1]

@@ -122,11 +122,11 @@ static int launch_gru_small(const float* xg, const float* w_hh, const float* b_h
 
 int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
                 int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens,
-                float pad_value);  // rnn_tc.cu
+                float pad_value, int min_chunk);  // rnn_tc.cu
 
 int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
               int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens,
-              float pad_value) {
+              float pad_value, int min_chunk) {
   FTB_REQUIRE(xg && w_hh && out && B > 0 && S > 0, FTB_ERR_INVALID, "rnn_bidir: bad arguments");
   FTB_REQUIRE(ldo == 0 || ldo >= 2 * H + (lo_off ? 2 * H : 0), FTB_ERR_INVALID, "rnn_bidir: output row stride %d too small", ldo);
   FTB_REQUIRE(lo_off == 0 || lo_off >= 2 * H, FTB_ERR_INVALID, "rnn_bidir: the remainder part must not overlap the 2H main part");
@@ -139,7 +139,7 @@ int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, 
     return H == 64 ? launch_gru_small<64>(xg, w_hh, b_hn, out, B, S, out_bf16, s, lens)
                    : launch_gru_small<128>(xg, w_hh, b_hn, out, B, S, out_bf16, s, lens);
   }
-  return rnn_cluster(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, s, xrow, ldo, lo_off, lens, pad_value);
+  return rnn_cluster(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, s, xrow, ldo, lo_off, lens, pad_value, min_chunk);
 }
 
 }  // namespace ftb

@@ -472,15 +472,19 @@ static std::atomic<int> g_lstm_min_chunk{getenv("FTB_LSTM_MIN_CHUNK") ? atoi(get
 
 template <int G, int H, int CL>
 static int dispatch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
-                           cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens, float pad_value) {
+                           cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens, float pad_value,
+                           int min_chunk_call) {
   int m8 = 0, m16 = 0, m32 = 0;
   FTB_TRY((launch_rnn_tc<G, H, CL, 16, 4, 8>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 8, s, &m8)));
   FTB_TRY((launch_rnn_tc<G, H, CL, 16, 8, 16>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 16, s, &m16)));
   FTB_TRY((launch_rnn_tc<G, H, CL, 32, 8, 32>(nullptr, nullptr, nullptr, nullptr, B, S, 0, 32, s, &m32)));
+  static const int force = getenv("FTB_LSTM_FORCE_CHUNK") ? atoi(getenv("FTB_LSTM_FORCE_CHUNK")) : 0;  // developer knob
+  if (force == 16) return launch_rnn_tc<G, H, CL, 16, 8, 16>(xg, w_hh, b_hn, out, B, S, out_bf16, 16, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
+  if (force == 24 || force == 32) return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, force, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
   // 8 utterances: only the first column group of a 16-wide MMA carries data, 1 pair per gate thread
   if (2 * cdiv(B, 8) <= m8) return launch_rnn_tc<G, H, CL, 16, 4, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, 8, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
   if (2 * cdiv(B, 16) <= m16) return launch_rnn_tc<G, H, CL, 16, 8, 16>(xg, w_hh, b_hn, out, B, S, out_bf16, 16, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
-  const int min_chunk = g_lstm_min_chunk.load(std::memory_order_relaxed);
+  const int min_chunk = min_chunk_call > 0 ? min_chunk_call : g_lstm_min_chunk.load(std::memory_order_relaxed);
   if (min_chunk <= 24 && 2 * cdiv(B, 24) <= m32) return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 24, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
   return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 32, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
 }
@@ -491,10 +495,11 @@ int rnn_gru256_mma(const float* xg, const float* w_hh, const float* b_hn, void* 
 // lens (optional, (B) int32): row b is a sequence of lens[b] steps (pack_padded_sequence semantics): state zero and output
 // pad_value beyond it, the reverse direction starts at its last valid step.
 int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
-                int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens, float pad_value) {
+                int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens, float pad_value,
+                int min_chunk) {
   FTB_REQUIRE(!lo_off || out_bf16, FTB_ERR_INVALID, "rnn_bidir: the hi/lo output pair exists for 16-bit outputs only");
   FTB_REQUIRE((int64_t)B * S < (1ll << 31), FTB_ERR_INVALID, "rnn_bidir: B*S overflows the int32 row index");
-  if (is_lstm && H == 512) return dispatch_rnn_tc<4, 512, 16>(xg, w_hh, nullptr, out, B, S, out_bf16, s, xrow, ldo, lo_off, lens, pad_value);
+  if (is_lstm && H == 512) return dispatch_rnn_tc<4, 512, 16>(xg, w_hh, nullptr, out, B, S, out_bf16, s, xrow, ldo, lo_off, lens, pad_value, min_chunk);
   FTB_REQUIRE(!xrow, FTB_ERR_UNSUPPORTED, "rnn_bidir: the row-indexed input exists for the H=512 LSTM only");
   FTB_REQUIRE(pad_value == 0.f, FTB_ERR_UNSUPPORTED, "rnn_bidir: a non-zero pad value exists for the H=512 LSTM only");
   if (!is_lstm && H == 256) return rnn_gru256_mma(xg, w_hh, b_hn, out, B, S, out_bf16, s, ldo, lo_off, lens);

@@ -177,10 +177,12 @@ class NativeModel(nn.Module):
             _lib.check(getattr(lib, self._create_fn)(C.byref(cfg), table, len(table), device.index or 0,
                                                      C.byref(out)))
         self._lanes[key] = {'handle': out, 'keep': (table, keep, cfg), 'ws': None}
-        if len(self._lanes) == 2:
+        if len(self._lanes) >= 2 and hasattr(lib, 'ftb_ft_set_option') and self._create_fn == 'ftb_ft_create':
             # a second stream means batches in flight: trade a little single-call latency of the decoder LSTM for
-            # fewer SMs held during its recurrence (include/ftb200.h, FTB_TUNE_LSTM_MIN_CHUNK)
-            _lib.check(lib.ftb_tune(_lib.FTB_TUNE_LSTM_MIN_CHUNK, 32))
+            # fewer SMs held during its recurrence -- an option of THIS model's handles, not a process-wide setting
+            # (include/ftb200.h, FTB_OPT_LSTM_MIN_CHUNK)
+            for lane in self._lanes.values():
+                _lib.check(lib.ftb_ft_set_option(lane['handle'], _lib.FTB_OPT_LSTM_MIN_CHUNK, 32))
         return out
 
     def lane_streams(self, device, n: int):

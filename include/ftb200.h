@@ -300,6 +300,10 @@ int ftb_ft_predict(ftb_ft_handle* h, const int64_t* tokens, int B, int T, float 
  * persistent kernel that keeps the activations in shared memory across all of them (csrc/cbhg_tail.cu).  Both paths
  * produce the same bits; the option exists for that comparison and for profiling. */
 #define FTB_OPT_UNFUSED_TAIL 4
+/* FTB_OPT_LSTM_MIN_CHUNK (default 0 = the process-wide ftb_tune(FTB_TUNE_LSTM_MIN_CHUNK) value): smallest number of
+ * utterances per decoder-LSTM cluster for launches of THIS handle.  32 = throughput setting for several batches in
+ * flight (4 instead of 6 clusters hold 64 instead of 96 SMs for the whole recurrence; one call alone +12 %). */
+#define FTB_OPT_LSTM_MIN_CHUNK 5
 int ftb_ft_set_option(ftb_ft_handle* h, int option, int value);
 
 /* Between the stages the Python callbacks pitch_function / energy_function run

@@ -73,15 +73,20 @@ def rnn(sd: SD, p: str, x: torch.Tensor, kind: str) -> torch.Tensor:
     models/forward_tacotron.py:39,53,165-168,321."""
     w_hh = sd[f'{p}.weight_hh_l0']
     key = (id(w_hh), p, kind)
-    mod = _RNN_CACHE.get(key)
-    if mod is None:
+    hit = _RNN_CACHE.get(key)
+    # The entry keeps the tensor it was built from: an id() alone is reused by Python once the old tensor is collected,
+    # and a state_dict of the same shape would then silently get the previous weights (seen as a rare, exactly repeating
+    # "kernel" mismatch in tests/test_gpu_rnn.py).
+    if hit is None or hit[0] is not w_hh:
         cls = torch.nn.GRU if kind == 'gru' else torch.nn.LSTM
         mod = cls(sd[f'{p}.weight_ih_l0'].shape[1], w_hh.shape[1], batch_first=True, bidirectional=True)
         mod.load_state_dict({k[len(p) + 1:]: v for k, v in sd.items() if k.startswith(p + '.')})
         mod.eval()
-        _RNN_CACHE[key] = mod
+        if len(_RNN_CACHE) >= 64:
+            _RNN_CACHE.pop(next(iter(_RNN_CACHE)))
+        _RNN_CACHE[key] = hit = (w_hh, mod)
     with torch.no_grad():
-        return mod(x)[0]
+        return hit[1](x)[0]
 
 
 def length_regulate(x: torch.Tensor, dur: torch.Tensor) -> torch.Tensor:

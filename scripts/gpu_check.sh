@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for f in ${TESTS:-test_gpu_length_regulator test_gpu_conv_gemm test_gpu_rnn test_gpu_dsp test_gpu_forward_tacotron test_gpu_fast_pitch test_gpu_full_size test_gpu_multi}; do
+for f in ${TESTS:-test_gpu_length_regulator test_gpu_conv_gemm test_gpu_rnn test_gpu_dsp test_gpu_forward_tacotron test_gpu_fast_pitch test_gpu_attention test_gpu_full_size test_gpu_multi}; do
   echo "=== $f"
   timeout ${TEST_TIMEOUT:-420} python -m pytest tests/$f.py -q -m gpu -x -s --tb=short > gpurun_out/$f.log 2>&1
   echo "exit $?" | tee -a gpurun_out/$f.log

@@ -61,7 +61,15 @@ def test_cluster_rnn(H, lstm, B, S):
     # W_hh and the h operand of the recurrent matmul are bf16 (fp32 accumulate, fp32 state)
     mx = float((got - want).abs().max())
     mn = float((got - want).abs().mean())
-    assert mx < 1e-2 and mn < 1e-3, (mx, mn)
+    if not (mx < 1e-2 and mn < 1e-3):   # diagnostics: where, and does a second launch agree?
+        d = (got - want).abs()
+        again = run_kernel(sd, x, H, lstm)
+        info = {'utterances': (d.amax(dim=(1, 2)) > 1e-2).nonzero().flatten().tolist(),
+                'steps': (d.amax(dim=(0, 2)) > 1e-2).nonzero().flatten().tolist()[:8],
+                'fwd_max': float(d[:, :, :H].max()), 'bwd_max': float(d[:, :, H:].max()),
+                'second_launch_max_err': float((again - want).abs().max()),
+                'timeouts': _lib.lib().ftb_tc_timeout_count()}
+        raise AssertionError((mx, mn, info))
     got16 = run_kernel(sd, x, H, lstm, out_bf16=True)
     assert float((got16 - got).abs().max()) < 8e-3
     # output type 2: IEEE-half output AND IEEE-half recurrent operands (3 more significand bits than bf16)
