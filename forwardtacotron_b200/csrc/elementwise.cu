@@ -232,6 +232,36 @@ __global__ void posenc_add_kernel(T* __restrict__ x, const float* __restrict__ p
   }
 }
 
+// 16-bit activations: x32 = float(x) + scale * pe[:S] and the 16-bit copy x = cast(x32) in ONE pass, 8 channels per
+// thread (16-byte loads / stores).  Replaces to_f32 + posenc_add + cast_rows: three scalar passes over the frame-rate
+// tensor (443 us at cfg3) for one (read 2 B, write 6 B per element).
+template <typename T>
+__global__ void posenc_dual_kernel(T* __restrict__ x, float* __restrict__ x32, const float* __restrict__ pe,
+                                   const float* __restrict__ scale, int64_t rows, int S, int E8) {
+  const float sc = scale[0];
+  const int64_t total = rows * E8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % E8);
+    const int t = (int)((i / E8) % S);
+    uint4 raw = reinterpret_cast<const uint4*>(x)[i];
+    const T* xv = reinterpret_cast<const T*>(&raw);
+    const float4* pp = reinterpret_cast<const float4*>(pe + ((int64_t)t * E8 + c8) * 8);
+    const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+    const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    float v[8];
+    T o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = fmaf(sc, pv[k], ActIO<T>::load(xv + k));
+      ActIO<T>::store(o + k, v[k]);
+    }
+    float4* dst = reinterpret_cast<float4*>(x32 + i * 8);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    reinterpret_cast<uint4*>(x)[i] = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
 // ---- one-time weight preparation ------------------------------------------------------------
 // BN eval -> scale/shift (common_layers.py:52): scale = w / sqrt(var + 1e-5), shift = b - mean*scale
 __global__ void bn_fold_kernel(const float* w, const float* b, const float* mean, const float* var, float* scale,
@@ -377,6 +407,17 @@ int posenc_add(T* x, const float* pe, const float* scale, int B, int S, int E, c
   FTB_CHECK_LAUNCH();
   return FTB_OK;
 }
+template <typename T>
+int posenc_dual(T* x, float* x32, const float* pe, const float* scale, int B, int S, int E, cudaStream_t s) {
+  FTB_REQUIRE(E % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)x32 & 15) == 0 && ((uintptr_t)pe & 15) == 0, FTB_ERR_INVALID,
+              "posenc_dual: E must be a multiple of 8 and the buffers 16-byte aligned");
+  ProfScope prof(FAM_ELEMENTWISE, 0.0, 0.0, s);
+  posenc_dual_kernel<T><<<ew_blocks((int64_t)B * S * E / 8), 256, 0, s>>>(x, x32, pe, scale, (int64_t)B * S, S, E / 8);
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+template int posenc_dual<__nv_bfloat16>(__nv_bfloat16*, float*, const float*, const float*, int, int, int, cudaStream_t);
+template int posenc_dual<__half>(__half*, float*, const float*, const float*, int, int, int, cudaStream_t);
 template int posenc_add<float>(float*, const float*, const float*, int, int, int, cudaStream_t);
 template int posenc_add<__nv_bfloat16>(__nv_bfloat16*, const float*, const float*, int, int, int, cudaStream_t);
 

@@ -136,9 +136,16 @@ static int run_transformer(ftb_fp_handle* h, TransformerW& W, T* x, float* x32_b
   float* x32 = kF32 ? (float*)x : x32_buf;  // caller-owned fp32 stream (B,S,E) in bf16 mode
   void* x16 = kF32 ? nullptr : (void*)x;
   const int x16_fp16 = std::is_same<T, f16>::value;
-  if (!kF32) FTB_TRY(to_f32<T>(x, x32, M * E, s));
-  FTB_TRY(posenc_add<float>(x32, W.pe, W.scale, B, S, E, s));
-  if (!kF32) FTB_TRY(cast_rows<T>(x32, x, M, E, E, E, s));
+  if constexpr (kF32) {
+    FTB_TRY(posenc_add<float>(x32, W.pe, W.scale, B, S, E, s));
+  } else if (E % 8 == 0) {
+    FTB_TRY(posenc_dual<T>(x, x32, W.pe, W.scale, B, S, E, s));  // fp32 stream + 16-bit operand copy in one pass
+    h->launches -= 2;
+  } else {
+    FTB_TRY(to_f32<T>(x, x32, M * E, s));
+    FTB_TRY(posenc_add<float>(x32, W.pe, W.scale, B, S, E, s));
+    FTB_TRY(cast_rows<T>(x32, x, M, E, E, E, s));
+  }
   Out a32;
   a32.f32 = w.a32;
   a32.ldo = E;

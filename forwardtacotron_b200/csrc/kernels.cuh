@@ -85,6 +85,9 @@ int layernorm(const float* x, const float* gamma, const float* beta, float* y32,
               int C, cudaStream_t s);
 template <typename T>
 int posenc_add(T* x, const float* pe, const float* scale, int B, int S, int E, cudaStream_t s);
+// 16-bit x in place + the fp32 stream: x32 = float(x) + scale * pe[:S], x = cast(x32)
+template <typename T>
+int posenc_dual(T* x, float* x32, const float* pe, const float* scale, int B, int S, int E, cudaStream_t s);
 int bn_fold(const float* w, const float* b, const float* mean, const float* var, float* scale, float* shift, int C,
             cudaStream_t s);
 int rnn_bias(const float* b_ih, const float* b_hh, float* out, int n, int fold, cudaStream_t s);
