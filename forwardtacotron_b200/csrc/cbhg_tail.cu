@@ -31,7 +31,9 @@
 // Arithmetic is the same as the per-layer path (conv_gemm_tc.cu modes 1 and 3): same MMA K order, same epilogue
 // expressions, same 16-bit rounding points, so the two paths agree bit for bit (tests/test_gpu_forward_tacotron.py).
 // Measured (cfg2, B200): postnet tail 370 us as six launches -> 281 us (single CTA per tile, 128-column units) ->
-// ~230 us; prenet 117 -> 62 -> ~40 us.
+// 220-244 us; prenet (one tile per CTA, no second slot to interleave) 117 -> 62 -> 59 us.  What is left: the epilogue
+// warps are one serial resource for the highway gate maths (MUFU / issue bound, ~2.5 k clk per 256-column unit against
+// ~2.7 k of MMAs) AND the projection's store drain (TMA stores of 32 x 64 B boxes, ~26 B/clk/SM).
 #include <algorithm>
 #include <cstdlib>
 
