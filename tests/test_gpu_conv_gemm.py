@@ -98,6 +98,24 @@ def test_conv_gemm(B, S, Cin, N, k, relu, bn, bias, res, bf16):
     assert _lib.lib().ftb_tc_timeout_count() == 0
 
 
+@pytest.mark.parametrize('res', [False, True])
+def test_tc_cta_pair_mode(res):
+    """A launch big enough for the CTA-pair path (tcgen05 cta_group::2: two row tiles per MMA, the weight tile split over
+    the two CTAs): 7 x 21 = 147 row tiles -- an ODD count, so the last pair has a row tile that does not exist (its loads
+    zero-fill, its stores clip, its residual reads are skipped) -- times two 256-wide column tiles = 148 pair tiles."""
+    g = torch.Generator().manual_seed(11)
+    B, S, Cin, N, k = 7, 2600, 128, 512, 3
+    x = (torch.randn(B, S, Cin, generator=g) * 0.5).bfloat16().float()
+    w = (torch.randn(N, Cin, k, generator=g) / (Cin * k) ** 0.5).bfloat16().float()
+    bvec = torch.randn(N, generator=g) * 0.1
+    r = torch.randn(B, S, N, generator=g).bfloat16().float() if res else None
+    want = reference(x, w, k, True, None, None, bvec, r, 1.0)
+    got, got_t = run_kernel(x, w, k, True, None, None, bvec, r, 1.0, True, want_t=True)
+    assert float((got - want).abs().max()) < 3e-3
+    assert float((got_t - want.transpose(1, 2)).abs().max()) < 3e-3
+    assert _lib.lib().ftb_tc_timeout_count() == 0
+
+
 def test_tc_large_k_and_batch():
     """conv_project1-like: K = 3*4096, several M and N tiles."""
     g = torch.Generator().manual_seed(0)
