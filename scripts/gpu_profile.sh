@@ -42,12 +42,10 @@ $CMD > gpurun_out/plain_stft.log 2>&1 && cap stft stft_mel 3 1
 CMD="python scripts/fp_profile.py"
 # FastPitch.generate (cfg3), per generate: prenet + postnet = 8 x attention_umma_kernel<128>, 8 x <64> (pitch / energy),
 # 4 x fp32 SIMT attention (duration predictor); the frame- and phoneme-rate transformer GEMMs run as CTA pairs:
-# 16 x conv_gemm_tc_kernel<3, true> (qkv, conv1) and 16 x <4, true> (out_proj / conv2 with the fused LayerNorm)
+# 16 x conv_gemm_tc_kernel<3, true> (qkv, conv1) and 16 x <4, true> (out_proj / conv2 with the fused LayerNorm): those and
+# the LayerNorm launches are captured by scripts/gpu_profile_fp.sh (launch counts are taken from a first pass)
 $CMD > gpurun_out/plain_fp.log 2>&1 && {
   capm attn attention_umma_kernelILi128E 20 1
   cap attnf32 attention_kernel 8 1
-  cap layernorm layernorm_kernel 90 2
-  capm fpgemm conv_gemm_tc_kernelILi3ELb1E 56 2
-  capm fpgemmln conv_gemm_tc_kernelILi4ELb1E 56 2
 }
 ls -la gpurun_out | grep $TAG; du -sh gpurun_out
