@@ -500,25 +500,30 @@ __global__ void __launch_bounds__(MODE >= 3 ? 32 * (2 + tc::EPI_WARPS_DIRECT) : 
           float* lnq = lnbase + cgp * 128;
           const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN_MAX;
           const int row = q * 32 + lane;
+          // the residual rows do not depend on the accumulator: the first chunk's are fetched while the MMAs still run,
+          // the next chunk's while this one is reduced
+          float4 rs4[8];
+          auto load_ln_res = [&](int ch) {
+            if (row_ok && ch < nchunks) {
+              const float4* p = reinterpret_cast<const float4*>(a.res_f32 + m_own * ldr + c.n0 + ch * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rs4[j] = __ldg(p + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rs4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          };
+          load_ln_res(cgp);
           mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           float s1 = 0.f;
           for (int ch = cgp; ch < nchunks; ch += NCG) {
             uint32_t r[32];
             tmem_ld32(tbase + ch * 32, r);
-            const int nb = c.n0 + ch * 32;
             float rs[32];
-            if (row_ok) {
-              const float4* p = reinterpret_cast<const float4*>(a.res_f32 + m_own * ldr + nb);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 v4 = __ldg(p + j);
-                rs[4 * j] = v4.x, rs[4 * j + 1] = v4.y, rs[4 * j + 2] = v4.z, rs[4 * j + 3] = v4.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) rs[i] = 0.f;
-            }
+            for (int j = 0; j < 8; ++j) rs[4 * j] = rs4[j].x, rs[4 * j + 1] = rs4[j].y, rs[4 * j + 2] = rs4[j].z, rs[4 * j + 3] = rs4[j].w;
+            load_ln_res(ch + NCG);
             const float* bp = spar + ch * 32;
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
