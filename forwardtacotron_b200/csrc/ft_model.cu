@@ -94,7 +94,8 @@ static int build_series(ftb_ft_handle* h, SeriesW& P, const std::string& p, int 
     const std::string c = p + ".convs." + std::to_string(i);
     FTB_TRY(h->make_conv(P.conv[i], c + ".conv.weight", C, i ? C : E, 5, 2, true, c + ".bnorm", "", w32, w16, split));
   }
-  FTB_REQUIRE(H == 64 || H == 128, FTB_ERR_UNSUPPORTED, "%s.rnn: hidden size %d not built (64, 128)", p.c_str(), H);
+  // 64 / 128: the register-resident kernel; any other multiple of 4: the generic recurrence (rnn_small.cu, slow)
+  FTB_REQUIRE(H % 4 == 0 && H >= 4 && H <= 2048, FTB_ERR_UNSUPPORTED, "%s.rnn: hidden size %d (multiples of 4 up to 2048)", p.c_str(), H);
   FTB_TRY(h->make_rnn(P.rnn, p + ".rnn", C, H, false, w32, w16, split));
   FTB_TRY(h->get(p + ".lin.weight", {1, 2 * H}, &P.lin_w));
   FTB_TRY(h->get(p + ".lin.bias", {1}, &P.lin_b));
@@ -110,7 +111,8 @@ static int build_cbhg(ftb_ft_handle* h, CbhgW& W, const std::string& p, int K, i
   W.p1 = p1;
   W.nhw = nhw;
   const bool w16 = h->bf16_mode(), w32 = !w16;
-  FTB_REQUIRE(ch == 256, FTB_ERR_UNSUPPORTED, "%s: CBHG channels %d not built (GRU kernel is H=256)", p.c_str(), ch);
+  // 256 channels (config.yaml): fused tail kernel + cluster GRU; other multiples of 64: layer-by-layer tail, generic GRU
+  FTB_REQUIRE(ch % 64 == 0 && ch <= 2048, FTB_ERR_UNSUPPORTED, "%s: CBHG channels %d must be a multiple of 64", p.c_str(), ch);
   FTB_REQUIRE(p1 == Cin, FTB_ERR_INVALID, "%s: residual needs proj_channels[1] == in_channels", p.c_str());
   W.bank.resize(K);
   for (int i = 0; i < K; ++i) {
@@ -483,7 +485,8 @@ extern "C" int ftb_ft_create(const ftb_ft_config* cfg, const ftb_tensor* tensors
   for (int i = 0; i < n_tensors; ++i) h->sd[tensors[i].name] = tensors[i];
   const ftb_ft_config& c = h->cfg;
   auto build = [&]() -> int {
-    FTB_REQUIRE(c.rnn_dims == 512, FTB_ERR_UNSUPPORTED, "rnn_dims %d not built (LSTM kernel is H=512)", c.rnn_dims);
+    // 512 (config.yaml): the tcgen05 cluster LSTM; other multiples of 32: the generic recurrence (slow)
+    FTB_REQUIRE(c.rnn_dims % 32 == 0 && c.rnn_dims <= 2048, FTB_ERR_UNSUPPORTED, "rnn_dims %d must be a multiple of 32", c.rnn_dims);
     FTB_REQUIRE(c.embed_dims % 64 == 0 && c.series_embed_dims % 64 == 0, FTB_ERR_UNSUPPORTED,
                 "embedding dims must be multiples of 64");
     FTB_TRY(build_series(h, h->series[0], "dur_pred", c.series_embed_dims, c.durpred_conv_dims, c.durpred_rnn_dims, true));

@@ -120,6 +120,89 @@ static int launch_gru_small(const float* xg, const float* w_hh, const float* b_h
   return FTB_OK;
 }
 
+// ---- any other hidden size: correct, not fast ------------------------------------------------------------------
+// The specialised kernels cover the reference's config.yaml (predictor GRUs 64 / 128, CBHG GRUs 256, decoder LSTM 512).
+// A checkpoint trained with other sizes still has to run: this kernel takes any H (multiple of 4, G*H*4 + H*4 bytes of
+// shared memory), exact fp32, one CTA per (utterance, direction).  Every step streams the direction's whole W_hh from
+// L2 (a warp per gate row, lanes along k), so it is one to two orders of magnitude slower per step than the
+// specialised kernels -- a compatibility path on the GPU, not a CPU fallback.  Same semantics as the others: optional
+// frame -> row index for the input pre-activations, hi / lo output pair, per-row lengths (packed sequences).
+template <int G>
+__global__ void __launch_bounds__(512) rnn_generic_kernel(const float* __restrict__ xg, const float* __restrict__ w_hh,
+                                                          const float* __restrict__ b_hn, void* __restrict__ out, int S, int H,
+                                                          int out_kind, const int32_t* __restrict__ xrow, int ldo, int lo_off,
+                                                          const int32_t* __restrict__ lens, float pad_value) {
+  extern __shared__ __align__(16) float sm_g[];
+  float* h = sm_g;       // [H]
+  float* pre = h + H;    // [G*H]  W_hh h
+  const int b = blockIdx.x, dir = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int len = lens ? min(max(__ldg(lens + b), 0), S) : S;
+  const float* W = w_hh + (int64_t)dir * G * H * H;
+  for (int u = tid; u < H; u += blockDim.x) h[u] = 0.f;
+  // cell state of unit u lives in the thread that owns it: units tid, tid + blockDim, ...  (at most 4 per thread: H <= 2048)
+  float cst[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+  for (int s = 0; s < S; ++s) {
+    const int t = dir ? S - 1 - s : s;
+    const bool live = t < len;
+    for (int r = warp; r < G * H; r += nw) {  // pre[r] = W[r, :] . h
+      const float4* wr = reinterpret_cast<const float4*>(W + (int64_t)r * H);
+      float acc = 0.f;
+      for (int k = lane; k < H / 4; k += 32) {
+        const float4 w4 = __ldg(wr + k);
+        const float4 h4 = *reinterpret_cast<const float4*>(h + 4 * k);
+        acc = fmaf(w4.x, h4.x, fmaf(w4.y, h4.y, fmaf(w4.z, h4.z, fmaf(w4.w, h4.w, acc))));
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) pre[r] = acc;
+    }
+    __syncthreads();
+    const int64_t f = (int64_t)b * S + t;
+    const int64_t row = xrow ? (int64_t)__ldg(xrow + f) : f;
+    const float* x = xg + row * (2 * G * H) + (int64_t)dir * G * H;
+    int ci = 0;
+    for (int u = tid; u < H; u += blockDim.x, ++ci) {
+      float hn;
+      if (G == 4) {  // LSTM, gate order i, f, g, o; biases folded into xg
+        const float gi = sigmoidf_(x[u] + pre[u]), gf = sigmoidf_(x[H + u] + pre[H + u]);
+        const float gg = tanhf_(x[2 * H + u] + pre[2 * H + u]), go = sigmoidf_(x[3 * H + u] + pre[3 * H + u]);
+        cst[ci & 3] = gf * cst[ci & 3] + gi * gg;
+        hn = go * tanhf_(cst[ci & 3]);
+      } else {  // GRU, gate order r, z, n; b_hn stays inside r * (.)
+        const float gr = sigmoidf_(x[u] + pre[u]), gz = sigmoidf_(x[H + u] + pre[H + u]);
+        const float gn = tanhf_(x[2 * H + u] + gr * (pre[2 * H + u] + b_hn[dir * H + u]));
+        hn = (1.f - gz) * gn + gz * h[u];
+      }
+      if (!live) hn = 0.f, cst[ci & 3] = 0.f;
+      store_h(out, f * ldo + (int64_t)dir * H + u, lo_off, out_kind, live ? hn : pad_value);
+      pre[u] = hn;  // parked until every thread has read the old h (GRU) -- pre[0..H) is not read again this step
+    }
+    __syncthreads();
+    for (int u = tid; u < H; u += blockDim.x) h[u] = pre[u];
+    __syncthreads();
+  }
+}
+
+static int launch_rnn_generic(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
+                              int out_kind, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens,
+                              float pad_value) {
+  const int G = is_lstm ? 4 : 3;
+  FTB_REQUIRE(H % 4 == 0 && H >= 4 && H <= 2048, FTB_ERR_UNSUPPORTED, "rnn_bidir: hidden size %d (multiples of 4 up to 2048)", H);
+  FTB_REQUIRE(is_lstm || b_hn, FTB_ERR_INVALID, "rnn_bidir: GRU needs b_hn");
+  const size_t smem = sizeof(float) * (size_t)(G + 1) * H;
+  if (ldo <= 0) ldo = 2 * H;
+  if (is_lstm) {
+    FTB_CHECK_CUDA(cudaFuncSetAttribute(rnn_generic_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rnn_generic_kernel<4><<<dim3(B, 2), 512, smem, s>>>(xg, w_hh, b_hn, out, S, H, out_kind, xrow, ldo, lo_off, lens, pad_value);
+  } else {
+    FTB_CHECK_CUDA(cudaFuncSetAttribute(rnn_generic_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rnn_generic_kernel<3><<<dim3(B, 2), 512, smem, s>>>(xg, w_hh, b_hn, out, S, H, out_kind, xrow, ldo, lo_off, lens, pad_value);
+  }
+  FTB_CHECK_LAUNCH();
+  return FTB_OK;
+}
+
 int rnn_cluster(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H, int is_lstm,
                 int out_bf16, cudaStream_t s, const int32_t* xrow, int ldo, int lo_off, const int32_t* lens,
                 float pad_value, int min_chunk);  // rnn_tc.cu
@@ -133,13 +216,14 @@ int rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, 
   const int G = is_lstm ? 4 : 3;
   ProfScope prof(is_lstm ? FAM_RNN_LSTM : (H >= 256 ? FAM_RNN_GRU : FAM_RNN_SMALL), 2.0 * 2 * B * S * (double)G * H * H,
                  (double)B * S * 2 * G * H * 4 + (double)B * S * 2 * H * (out_bf16 ? (lo_off ? 4 : 2) : 4), s);
-  if (!is_lstm && (H == 64 || H == 128)) {
-    FTB_REQUIRE(!xrow && !lo_off && (ldo == 0 || ldo == 2 * H) && pad_value == 0.f, FTB_ERR_UNSUPPORTED,
-                "rnn_bidir: the small-GRU kernel writes plain (B,S,2H) rows");
+  // the register-resident small-GRU kernel writes plain (B,S,2H) rows; anything else at these sizes goes the generic way
+  if (!is_lstm && (H == 64 || H == 128) && !xrow && !lo_off && (ldo == 0 || ldo == 2 * H) && pad_value == 0.f) {
     return H == 64 ? launch_gru_small<64>(xg, w_hh, b_hn, out, B, S, out_bf16, s, lens)
                    : launch_gru_small<128>(xg, w_hh, b_hn, out, B, S, out_bf16, s, lens);
   }
-  return rnn_cluster(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, s, xrow, ldo, lo_off, lens, pad_value, min_chunk);
+  if ((is_lstm && H == 512) || (!is_lstm && H == 256))
+    return rnn_cluster(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, s, xrow, ldo, lo_off, lens, pad_value, min_chunk);
+  return launch_rnn_generic(xg, w_hh, b_hn, out, B, S, H, is_lstm, out_bf16, s, xrow, ldo, lo_off, lens, pad_value);
 }
 
 }  // namespace ftb

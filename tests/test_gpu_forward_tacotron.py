@@ -425,3 +425,19 @@ def test_packed_forward_mel_len_shorter_than_expansion(B):
     bad = dict(batch, mel_len=total + 1)
     with pytest.raises(RuntimeError):
         model({k: v.cuda() for k, v in bad.items()})
+
+
+def test_non_default_layer_sizes_run_and_match_the_oracle():
+    """A checkpoint trained with other sizes than config.yaml's (decoder LSTM 384, postnet CBHG 128 channels, pitch
+    predictor GRU 96) takes the generic kernels (layer-by-layer CBHG tail, generic recurrence) and still matches."""
+    from forwardtacotron_b200.utils.config import default_config
+    cfg = default_config('forward_tacotron')
+    m = cfg['forward_tacotron']['model']
+    m['rnn_dims'] = 384
+    m['postnet_dims'] = 128
+    m['pitch_rnn_dims'] = 96
+    model, _ = synth.synthetic_model('forward_tacotron', config=cfg)
+    model = model.cuda()
+    x = synth.synthetic_tokens(2, 20, seed=13)
+    want = mo.ft_generate(cpu_state_dict(model), x)
+    check_against(model, x, want)

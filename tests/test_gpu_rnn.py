@@ -180,3 +180,13 @@ def test_packed_sequences_equal_per_row_runs(H, lstm, kind):
         torch.cuda.synchronize()
         assert torch.equal(out[b, :n], solo[0]), (b, n)
         assert bool((out[b, n:].float() == torch.tensor(pad, dtype=dt).float()).all())
+
+
+@pytest.mark.parametrize('H,lstm,B,S', [(96, False, 3, 19), (320, True, 2, 25), (192, False, 5, 12)])
+def test_generic_recurrence_for_other_hidden_sizes(H, lstm, B, S):
+    """Hidden sizes outside config.yaml's (64 / 128 / 256 GRUs, 512 LSTM) take the generic fp32 kernel: slow, exact."""
+    sd = make_sd(H, 64, lstm, 3 * H + B)
+    x = torch.randn(B, S, 64, generator=torch.Generator().manual_seed(4)) * 0.5
+    want = mo.rnn_explicit(sd, 'rnn', x, 'lstm' if lstm else 'gru')
+    got = run_kernel(sd, x, H, lstm)
+    assert float((got - want).abs().max()) < 2e-5
