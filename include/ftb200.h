@@ -188,7 +188,9 @@ int ftb_linear_pair(const void* x_pair, const void* w_packed, int B, int S, int 
  * H in {64,128}: one CTA per (row, direction), one thread per gate row with its W_hh row in registers, exact fp32.
  * H = 256 (GRU): cluster of 4 CTAs, W_hh resident in registers as 16-bit mma.sync fragments.
  * H = 512 (LSTM): cluster of 16 CTAs, W_hh resident in shared memory as the tcgen05 A operand.
- * Both exchange the hidden state through distributed shared memory. */
+ * Both exchange the hidden state through distributed shared memory.
+ * Any other H that is a multiple of 4 up to 2048 (checkpoints trained with non-default sizes): generic fp32 kernel,
+ * one CTA per (row, direction) streaming W_hh from L2 every step -- correct, not fast.  Other H: FTB_ERR_UNSUPPORTED. */
 int ftb_rnn_bidir(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int H,
                   int is_lstm, int out_bf16, void* stream);
 /* As ftb_rnn_bidir with two extensions the models use (nn.LSTM after LengthRegulator, forward_tacotron.py:317-321):

@@ -80,9 +80,11 @@ def test_cluster_rnn(H, lstm, B, S):
 
 
 def test_unsupported_size_is_an_error():
-    with pytest.raises(_lib.FtbError, match='no kernel'):
-        z = torch.zeros(8, device='cuda')
-        _lib.check(_lib.lib().ftb_rnn_bidir(_lib.ptr(z), _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), 1, 1, 96, 0, 0, None))
+    # the generic recurrence takes every hidden size that is a multiple of 4 up to 2048; anything else raises
+    for H in (98, 4096):
+        with pytest.raises(_lib.FtbError, match='hidden size'):
+            z = torch.zeros(8, device='cuda')
+            _lib.check(_lib.lib().ftb_rnn_bidir(_lib.ptr(z), _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), 1, 1, H, 0, 0, None))
 
 
 def _lstm_inputs(B, T, S, seed):
