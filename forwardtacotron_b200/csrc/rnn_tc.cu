@@ -111,6 +111,8 @@ struct RtCfg {
   // k-block kb (64 units) is a 128-row x 128-byte tile at kb*16 KB; row m at m*128; the 16-byte chunk c of a row
   // (8 units) sits at chunk position c ^ (m % 8).
   static constexpr uint32_t W_BYTES = 128 * H * 2;
+  static constexpr uint32_t WCOL0 = 256;             // w_tmem: the slice as 128 lanes x H/2 columns behind the accumulators
+  static_assert(KSPLIT * NCOLS <= 256 && H / 2 <= 256, "accumulators + TMEM-resident W slice exceed 512 columns");
   static constexpr int NCG = UC / CW;                // column groups (of the UC columns that can carry data) = warps per TMEM lane quarter
   static constexpr int WARPS = 4 * NCG, THREADS = 32 * WARPS;
   static constexpr int PPT = CW / 4;                 // (unit, utterance) pairs per thread
@@ -150,7 +152,8 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
                   const int32_t* __restrict__ xrow,  // optional (B,S): row of xg that feeds (b, t) -- see rnn_bidir_rows
                   int ldo, int lo_off,               // out row stride; > 0: second 16-bit part h - hi at this offset
                   const int32_t* __restrict__ lens,  // optional (B): row b is a sequence of lens[b] <= S steps
-                  float pad_value) {                 // ... and its output beyond that is pad_value (packed sequences)
+                  float pad_value,                   // ... and its output beyond that is pad_value (packed sequences)
+                  int w_tmem) {                      // W slice as the TMEM-resident A operand instead of shared memory
   using C = RtCfg<G, H, CL, NCOLS, CW, UC>;
   using namespace rt;
   constexpr int THREADS = C::THREADS, WARPS = C::WARPS, PRE_LD = C::PRE_LD, PPT = C::PPT, KSPLIT = C::KSPLIT;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(C::TMEM_COLS)
+                 "r"(w_tmem ? 512u : C::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -207,7 +210,12 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
         v = f16op ? make_uint4(pack_f16x2(a.x, a.y), pack_f16x2(a.z, a.w), pack_f16x2(b.x, b.y), pack_f16x2(b.z, b.w))
                   : make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
       }
-      *reinterpret_cast<uint4*>(wdst + (kc >> 3) * 16384 + (((kc & 7) ^ (m & 7)) << 4)) = v;
+      if (w_tmem) {  // A operand in tensor memory: lane = row m, column WCOL0 + k/2 holds units (k, k+1)
+        const uint32_t r4[4] = {v.x, v.y, v.z, v.w};
+        tmem_st4(tmem_base + ((uint32_t)(q * 32) << 16) + C::WCOL0 + kc * 4, r4);
+      } else {
+        *reinterpret_cast<uint4*>(wdst + (kc >> 3) * 16384 + (((kc & 7) ^ (m & 7)) << 4)) = v;
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the UMMA reads
     // clear the accumulators (step 0 reads them without any MMA: h_{-1} = 0)
@@ -406,8 +414,11 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {  // the issuer's first MMA of a step overwrites its accumulator
             const uint32_t ks = 2 * r + j;
-            umma_ss_bf16(d_acc, adesc_sw128(wa0 + (ks >> 2) * 16384 + (ks & 3) * 32), bdesc_kmajor(hbn + r * C::SL + j * 256, 512),
-                         idesc, (i >= NISS || j > 0) ? 1u : 0u);
+            const uint64_t bd = bdesc_kmajor(hbn + r * C::SL + j * 256, 512);
+            if (w_tmem)
+              umma_ts_bf16(d_acc, tmem_base + C::WCOL0 + ks * 8, bd, idesc, (i >= NISS || j > 0) ? 1u : 0u);
+            else
+              umma_ss_bf16(d_acc, adesc_sw128(wa0 + (ks >> 2) * 16384 + (ks & 3) * 32), bd, idesc, (i >= NISS || j > 0) ? 1u : 0u);
           }
         }
         umma_commit(dfull);
@@ -420,7 +431,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(w_tmem ? 512u : C::TMEM_COLS) : "memory");
   }
   cluster.sync();  // no CTA exits while a peer may still address its shared memory
 }
@@ -457,7 +468,8 @@ static int launch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, 
   }
   FTB_REQUIRE(max_active > 0, FTB_ERR_UNSUPPORTED, "a cluster of %d CTAs cannot be scheduled on this device", CL);
   if (ldo <= 0) ldo = 2 * H;
-  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16, bc, xrow, ldo, lo_off, lens, pad_value));
+  static const int w_tmem = getenv("FTB_LSTM_W_TMEM") ? atoi(getenv("FTB_LSTM_W_TMEM")) : 1;  // 0: W slice in shared memory (SS MMAs)
+  FTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xg, w_hh, b_hn, out, B, S, out_bf16, bc, xrow, ldo, lo_off, lens, pad_value, w_tmem));
   count_launch();
   return FTB_OK;
 }
