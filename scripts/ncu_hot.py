@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Top stall-sample SASS instructions of an ncu report (source page).  usage: ncu_hot.py rep [N]"""
+"""Top stall-sample SASS instructions of an ncu report (source page).  usage: ncu_hot.py rep [N] [--order PCT]
+--order PCT: also list, in program order, every instruction holding at least PCT % of the samples."""
 import csv, subprocess, sys
 raw = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
@@ -21,3 +22,10 @@ print('by reason: ' + ', '.join(f'{k[6:]} {100*v/tot:.1f}%' for k, v in sorted(a
 for s, idx, r in sorted(data, key=lambda d: -d[0])[:n]:
     why = max(stalls, key=lambda h: int(r[ci[h]] or 0))
     print(f'{100*s/tot:5.1f}% #{idx:5d} {why[6:]:12s} {r[ci["Source"]].strip()[:80]}')
+if '--order' in sys.argv:
+    pct = float(sys.argv[sys.argv.index('--order') + 1])
+    print(f'--- program order, >= {pct} % of samples')
+    for s, idx, r in sorted(data, key=lambda d: d[1]):
+        if 100 * s / tot >= pct:
+            why = max(stalls, key=lambda h: int(r[ci[h]] or 0))
+            print(f'{100*s/tot:5.1f}% #{idx:5d} {why[6:]:12s} {r[ci["Source"]].strip()[:90]}')
