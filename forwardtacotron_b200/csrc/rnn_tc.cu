@@ -80,6 +80,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ uint64_t pack_u32x2(uint32_t lo, uint32_t hi) {
+  uint64_t v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+  return v;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t v;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(a), "l"(b));
+  return v;
+}
 // 512-byte slice: own shared memory -> the same offset in a peer CTA, completing bytes on the peer's mbarrier
 __device__ __forceinline__ void bulk_push(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -97,10 +107,10 @@ __device__ long long* g_rnn_dbg = nullptr;
     if (dbg && s < 64) dbg[s * 8 + (slot)] = clock64();                                   \
   } while (0)
 
-template <int G, int H, int CL, int NCOLS, int CW, int UC>
+template <int G, int H, int CL, int NCOLS, int CW, int UC, int KS = 8>
 struct RtCfg {
   static constexpr int HC = H / CL;                  // hidden units per CTA
-  static constexpr int KSPLIT = 8;                   // accumulators = MMA-issuing warps: accumulator a receives the MMAs of
+  static constexpr int KSPLIT = KS;                  // accumulators = MMA-issuing warps: accumulator a receives the MMAs of
                                                      // ring slices a, a + KSPLIT, ... from ONE thread in a fixed order, and
                                                      // the gate warps add the accumulators in a fixed order, so the result
                                                      // is bit-reproducible (16 issuers into 2 shared accumulators were 8 %
@@ -143,8 +153,8 @@ struct RtCfg {
 // small N is (measured, scripts/rnn_phase_timing.py), so the 2*CL MMAs of a step are issued by up to 16 threads in
 // parallel: warp w owns slices w, w + WARPS, ... (ring order from the own slice), waits for exactly those slices
 // to land and issues their MMAs into its own accumulator (the first one of a step overwrites it).
-template <int G, int H, int CL, int NCOLS, int CW, int UC>
-__global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
+template <int G, int H, int CL, int NCOLS, int CW, int UC, int KS = 8>
+__global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC, KS>::THREADS, 1)
     rnn_tc_kernel(const float* __restrict__ xg,    // (B,S,2,G*H)
                   const float* __restrict__ w_hh,  // (2,G*H,H)
                   const float* __restrict__ b_hn,  // (2,H) GRU only
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
                   const int32_t* __restrict__ lens,  // optional (B): row b is a sequence of lens[b] <= S steps
                   float pad_value,                   // ... and its output beyond that is pad_value (packed sequences)
                   int w_tmem) {                      // W slice as the TMEM-resident A operand instead of shared memory
-  using C = RtCfg<G, H, CL, NCOLS, CW, UC>;
+  using C = RtCfg<G, H, CL, NCOLS, CW, UC, KS>;
   using namespace rt;
   constexpr int THREADS = C::THREADS, WARPS = C::WARPS, PRE_LD = C::PRE_LD, PPT = C::PPT, KSPLIT = C::KSPLIT;
   constexpr int NISS = KSPLIT < WARPS ? KSPLIT : WARPS;  // issuing warps 0..NISS-1
@@ -314,19 +324,29 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
     {
       uint32_t r[KSPLIT][CW];
 #pragma unroll
-      for (int a = 0; a < KSPLIT; ++a)
+      for (int a = 0; a < KSPLIT; ++a) {
+        if constexpr (CW == 8) {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(r[a][0]), "=r"(r[a][1]), "=r"(r[a][2]), "=r"(r[a][3]), "=r"(r[a][4]), "=r"(r[a][5]), "=r"(r[a][6]),
+                         "=r"(r[a][7])
+                       : "r"(tacc + a * NCOLS));
+        } else {
 #pragma unroll
-        for (int i = 0; i < CW; i += 4)
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(r[a][i]), "=r"(r[a][i + 1]), "=r"(r[a][i + 2]), "=r"(r[a][i + 3])
-                       : "r"(tacc + a * NCOLS + i));
+          for (int i = 0; i < CW; i += 4)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(r[a][i]), "=r"(r[a][i + 1]), "=r"(r[a][i + 2]), "=r"(r[a][i + 3])
+                         : "r"(tacc + a * NCOLS + i));
+        }
+      }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // the accumulators are added in a fixed order, two columns per instruction (add.rn.f32x2: same rounding as scalar adds)
 #pragma unroll
-      for (int i = 0; i < CW; ++i) {
-        float v = __uint_as_float(r[0][i]);
+      for (int i = 0; i < CW; i += 2) {
+        uint64_t v = pack_u32x2(r[0][i], r[0][i + 1]);
 #pragma unroll
-        for (int a = 1; a < KSPLIT; ++a) v += __uint_as_float(r[a][i]);
-        acc[i] = v;
+        for (int a = 1; a < KSPLIT; ++a) v = add_f32x2(v, pack_u32x2(r[a][i], r[a][i + 1]));
+        acc[i] = __uint_as_float((uint32_t)v);
+        acc[i + 1] = __uint_as_float((uint32_t)(v >> 32));
       }
     }
     RNN_STAMP(3);
@@ -347,7 +367,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
       }
     }
     __syncwarp();
-    float hn[PPT];
+    float hn[PPT], hout[PPT];
 #pragma unroll
     for (int e = 0; e < PPT; ++e) {
       if (G == 4) {  // LSTM, gate order i, f, g, o; biases folded into xg
@@ -366,8 +386,7 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
       const bool live = t < len[e];
       if (!live) hn[e] = 0.f, cst[e] = 0.f;
       hprev[e] = hn[e];
-      if (ok[e]) store_h(out, op[e], lo_off, out_bf16, live ? hn[e] : pad_value);
-      op[e] += ostep;
+      hout[e] = live ? hn[e] : pad_value;  // stored at the end of the step, in the shadow of the exchange
 #pragma unroll
       for (int g = 0; g < G; ++g) xcur[e][g] = xnext[e][g];
     }
@@ -426,6 +445,12 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
       }
       __syncwarp();
     }
+    // the step's outputs leave while the MMAs of the next step run (nothing on the chip waits for them)
+#pragma unroll
+    for (int e = 0; e < PPT; ++e) {
+      if (ok[e]) store_h(out, op[e], lo_off, out_bf16, hout[e]);
+      op[e] += ostep;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -436,12 +461,12 @@ __global__ void __launch_bounds__(RtCfg<G, H, CL, NCOLS, CW, UC>::THREADS, 1)
   cluster.sync();  // no CTA exits while a peer may still address its shared memory
 }
 
-template <int G, int H, int CL, int NCOLS, int CW, int UC>
+template <int G, int H, int CL, int NCOLS, int CW, int UC, int KS = 8>
 static int launch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
                          int bc, cudaStream_t s, int* max_clusters, const int32_t* xrow = nullptr, int ldo = 0,
                          int lo_off = 0, const int32_t* lens = nullptr, float pad_value = 0.f) {
-  using C = RtCfg<G, H, CL, NCOLS, CW, UC>;
-  auto kern = rnn_tc_kernel<G, H, CL, NCOLS, CW, UC>;
+  using C = RtCfg<G, H, CL, NCOLS, CW, UC, KS>;
+  auto kern = rnn_tc_kernel<G, H, CL, NCOLS, CW, UC, KS>;
   static bool configured = false;
   static int max_active = 0;
   cudaLaunchConfig_t cfg = {};
