@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
     __syncthreads();
     // 4. gate maths (fp32), new h -> staging + global
     const float* xc = xs + cur * G * PAIRS;
+    float hout[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
       const int idx = tid + p * NT;
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
         hprev[p] = hn;
         reinterpret_cast<unsigned short*>(hstage)[n * HC + u] =
             F16 ? __half_as_ushort(__float2half_rn(hn)) : __bfloat16_as_ushort(__float2bfloat16_rn(hn));
-        if (pvalid[p]) store_h(out, optr[p] + (int64_t)t * ldo, lo_off, out_bf16, hn);
+        hout[p] = hn;  // stored after the push: nothing on the chip waits for the global copy
       }
     }
     __syncthreads();
@@ -314,6 +315,9 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
         st_async_16(hbuf_u32 + rb + off, v, bar0 + rb + bar_off);
       }
     }
+#pragma unroll
+    for (int p = 0; p < PPT; ++p)
+      if (tid + p * NT < PAIRS && pvalid[p]) store_h(out, optr[p] + (int64_t)t * ldo, lo_off, out_bf16, hout[p]);
   }
   cluster.sync();  // no CTA exits while a peer may still address its shared memory
 }

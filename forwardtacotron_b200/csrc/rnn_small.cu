@@ -97,7 +97,15 @@ __global__ void __launch_bounds__(3 * H) gru_small_kernel(const float* __restric
       const float n = tanhf(xb0 + r * gh[2 * H + tid]);
       const float hn = (1.f - z) * n + z * h[tid];
       h[tid] = hn;
-      const int64_t o = ((int64_t)b * S_full + t) * (2 * H) + dir * H + tid;
+    }
+    xa0 = xa1, xb0 = xb1;
+    xa1 = xa2, xb1 = xb2;
+    __syncthreads();
+    // the n-row threads have nothing to do after the first barrier: they write h_t out while the r-row threads (the
+    // critical path of a step) already run the next dot product; h[u] is not rewritten before the next first barrier
+    if (gate == 2) {
+      const float hn = h[u];
+      const int64_t o = ((int64_t)b * S_full + t) * (2 * H) + dir * H + u;
       if (out_bf16 == 2)
         ((__half*)out)[o] = __float2half_rn(hn);
       else if (out_bf16)
@@ -105,9 +113,6 @@ __global__ void __launch_bounds__(3 * H) gru_small_kernel(const float* __restric
       else
         ((float*)out)[o] = hn;
     }
-    xa0 = xa1, xb0 = xb1;
-    xa1 = xa2, xb1 = xb2;
-    __syncthreads();
   }
 }
 
