@@ -522,8 +522,8 @@ static int dispatch_rnn_tc(const float* xg, const float* w_hh, const float* b_hn
   if (2 * cdiv(B, 8) <= m8) return launch_rnn_tc<G, H, CL, 16, 4, 8>(xg, w_hh, b_hn, out, B, S, out_bf16, 8, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
   if (2 * cdiv(B, 16) <= m16) return launch_rnn_tc<G, H, CL, 16, 8, 16>(xg, w_hh, b_hn, out, B, S, out_bf16, 16, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
   const int min_chunk = min_chunk_call > 0 ? min_chunk_call : g_lstm_min_chunk.load(std::memory_order_relaxed);
-  if (min_chunk <= 24 && 2 * cdiv(B, 24) <= m32) return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 24, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
-  return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, 32, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
+  const int chunk = (min_chunk <= 24 && 2 * cdiv(B, 24) <= m32) ? 24 : 32;
+  return launch_rnn_tc<G, H, CL, 32, 8, 32>(xg, w_hh, b_hn, out, B, S, out_bf16, chunk, s, nullptr, xrow, ldo, lo_off, lens, pad_value);
 }
 
 int rnn_gru256_mma(const float* xg, const float* w_hh, const float* b_hn, void* out, int B, int S, int out_bf16,
