@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence (1 GPU): launch list + full captures of the kernels of one short bench run (single lane, the launches of
 # one generate() back to back), each only after the plain run exits 0.  Output stays small (<64 MiB).
-# usage: bash scripts/gpu_profile.sh [tag]
+# usage: [ONLY="lstm gru"] bash scripts/gpu_profile.sh [tag]
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r02}
@@ -16,12 +16,15 @@ summ() {  # the text summaries are what travels back (gpurun returns at most 64 
   if [ $(stat -c %s gpurun_out/prof_$1_$TAG.ncu-rep) -gt 5000000 ]; then rm -f gpurun_out/prof_$1_$TAG.ncu-rep; fi
   rm -f gpurun_out/ncu_$1_$TAG.log
 }
+want() { [ -z "${ONLY:-}" ] || [[ " $ONLY " == *" $1 "* ]]; }
 cap() {  # name kernel-regex skip count
+  want $1 || return 0
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -o gpurun_out/prof_$1_$TAG -f $CMD > gpurun_out/ncu_$1_$TAG.log 2>&1
   echo "$1 capture rc=$?"
   summ $1
 }
 capm() {  # as cap, matching the MANGLED name (template arguments are not part of ncu's default function name)
+  want $1 || return 0
   ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:$2 -s $3 -c $4 -o gpurun_out/prof_$1_$TAG -f $CMD > gpurun_out/ncu_$1_$TAG.log 2>&1
   echo "$1 capture rc=$?"
   summ $1
@@ -38,13 +41,13 @@ cap lenidx length_index_kernel 3 1
 capm gemm conv_gemm_tc_kernelILi3E 51 17
 capm split conv_gemm_tc_kernelILi2E 13 2
 CMD="python bench.py --stft-only"
-$CMD > gpurun_out/plain_stft.log 2>&1 && cap stft stft_mel 3 1
+want stft && $CMD > gpurun_out/plain_stft.log 2>&1 && cap stft stft_mel 3 1
 CMD="python scripts/fp_profile.py"
 # FastPitch.generate (cfg3), per generate: prenet + postnet = 8 x attention_umma_kernel<128>, 8 x <64> (pitch / energy),
 # 4 x fp32 SIMT attention (duration predictor); the frame- and phoneme-rate transformer GEMMs run as CTA pairs:
 # 16 x conv_gemm_tc_kernel<3, true> (qkv, conv1) and 16 x <4, true> (out_proj / conv2 with the fused LayerNorm): those and
 # the LayerNorm launches are captured by scripts/gpu_profile_fp.sh (launch counts are taken from a first pass)
-$CMD > gpurun_out/plain_fp.log 2>&1 && {
+{ want attn || want attnf32; } && $CMD > gpurun_out/plain_fp.log 2>&1 && {
   capm attn attention_umma_kernelILi128E 20 1
   cap attnf32 attention_kernel 8 1
 }
