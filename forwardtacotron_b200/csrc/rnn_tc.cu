@@ -2,11 +2,15 @@
 // (The kernel template also instantiates for the H=256 GRU; the CBHG GRUs run on rnn_mma.cu, see there.)
 //
 // One thread-block cluster of CL = 16 CTAs owns (direction, chunk of <= 32 utterances) for all S steps.  CTA `rank`
-// owns 32 hidden units = 128 gate rows of W_hh (row 4*u + gate), resident in shared memory for the whole kernel as
-// the SWIZZLE_128B A operand of tcgen05.mma.  Per step:
-//   1. every warp: wait for the accumulators (mbarrier fed by tcgen05.commit), tcgen05.ld its window, clear it,
-//      regroup the 4 gates of a unit inside the warp, fp32 gate maths with the input pre-activations prefetched one
-//      step ahead, write h_t to global and -- as bf16 -- into the own 32-unit slice of the NEXT step's B operand;
+// owns 32 hidden units = 128 gate rows of W_hh (row 4*u + gate), resident for the whole kernel in TENSOR MEMORY as
+// the A operand of tcgen05.mma (128 lanes x 256 columns behind the accumulators; FTB_LSTM_W_TMEM=0 keeps the earlier
+// SWIZZLE_128B shared-memory operand, whose 128 KB per step through the tensor pipe cost ~0.4 k clk of every step).
+// Per step:
+//   1. every warp: wait for the accumulators (mbarrier fed by tcgen05.commit), tcgen05.ld its window, add the eight
+//      accumulators in a fixed order, regroup the 4 gates of a unit inside the warp, fp32 gate maths with the input
+//      pre-activations prefetched one step ahead, write h_t -- as a 16-bit value -- into the own 32-unit slice of the
+//      NEXT step's B operand (the global copy of h_t is stored at the END of the step, behind the exchange: between
+//      the gate maths and the push it cost ~0.3 k clk of every step);
 //   2. block barrier; one cp.async.bulk (shared::cta -> shared::cluster) per peer pushes that slice into the peer's
 //      B buffer and completes bytes on the peer's per-slice mbarrier (armed by the consumer);
 //   3. warps 0..7 are the MMA issuers of the next step: issuer a waits for ring slices a, a + 8 and issues their
