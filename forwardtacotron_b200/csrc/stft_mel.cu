@@ -20,7 +20,12 @@
 namespace ftb {
 
 namespace mel {
-constexpr int VL = 8;              // taps per virtual mel row
+#ifndef FTB_MEL_VL
+#define FTB_MEL_VL 9
+#endif
+constexpr int VL = FTB_MEL_VL;     // taps per virtual mel row.  Odd: the pieces of a long triangle start VL bins apart, and with 8
+                                   // the lanes of a round hit 4 banks (3 wavefronts per load on average); 9 also makes it 4 rounds, not 5
+constexpr int MAX_PIECES = 8;      // virtual rows per mel row the second phase adds without a loop (33 taps / VL = 4 here)
 constexpr int PART_OFF = NCP;      // virtual-row partial sums: floats [PART_OFF, 2 NCP) of the warp's buffer
 constexpr int MAX_VR = NCP;
 constexpr int GROUPS = 8;          // 8-frame groups per CTA: amortises the table prologue
@@ -149,7 +154,12 @@ __global__ void __launch_bounds__(mel::WARPS * 32, 3)
     for (int m = lane; m < tb.n_mels; m += 32) {
       const int first = s_rfirst[m], cnt = s_rcnt[m];
       float acc = 0.f;
-      for (int i = 0; i < cnt; ++i) acc += part[first + i];
+      if (cnt <= MAX_PIECES) {  // same order of additions as the loop
+#pragma unroll
+        for (int i = 0; i < MAX_PIECES; ++i) acc += i < cnt ? part[first + i] : 0.f;
+      } else {
+        for (int i = 0; i < cnt; ++i) acc += part[first + i];
+      }
       dst[(int64_t)m * nframes] = normalize ? logf(fmaxf(acc, 1e-5f)) : acc;
     }
     __syncwarp();
