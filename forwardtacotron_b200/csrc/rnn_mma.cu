@@ -62,6 +62,14 @@ __device__ __forceinline__ void st_async_16(uint32_t remote_addr, const uint4& v
                : "memory");
 }
 __device__ __forceinline__ void rnn_mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_or_trap(bar, parity); }
+// Optional step-phase timing (developer tool, scripts/gru_phase_timing.py): thread 0 of CTA (0,0,0) records SM clock stamps
+// of the first 64 steps.  Slots: 0 step start, 1 h landed, 2 MMAs done, 3 after the first block barrier, 4 gate maths done,
+// 5 after the second block barrier, 6 pushed.
+__device__ long long* g_gru_dbg = nullptr;
+#define GRU_STAMP(slot)                                       \
+  do {                                                        \
+    if (dbg && s < 64) dbg[s * 8 + (slot)] = clock64();       \
+  } while (0)
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const float* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -202,9 +210,11 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
   const uint32_t dsm_base = map_to_cta(hbuf_u32, 0) - hbuf_u32;
   const uint32_t dsm_stride = map_to_cta(hbuf_u32, 1) - map_to_cta(hbuf_u32, 0);
 
+  long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) ? g_gru_dbg : nullptr;
   for (int s = 0; s < S; ++s) {
     const int cur = s & 1;
     const int t = dir ? S - 1 - s : s;
+    GRU_STAMP(0);
     if (s + 1 < S) prefetch_x(s + 1);
     // 1. h_{t-1} has landed?
     if (s > 0) {
@@ -214,6 +224,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * cur), "r"(C::TX_BYTES)
                      : "memory");
     }
+    GRU_STAMP(1);
     // 2. W_slice . h_{t-1}
     float acc[2][NTL][4];
 #pragma unroll
@@ -255,6 +266,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
         }
       }
     }
+    GRU_STAMP(2);
     // 3. accumulators -> smem (rows = local gate rows, cols = utterances)
     {
       const int r0 = warp * 16 + (lane >> 2), c0 = 2 * (lane & 3);
@@ -271,6 +283,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
     else
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    GRU_STAMP(3);
     // 4. gate maths (fp32), new h -> staging + global
     const float* xc = xs + cur * G * PAIRS;
     float hout[PPT];
@@ -300,7 +313,9 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
         hout[p] = hn;  // stored after the push: nothing on the chip waits for the global copy
       }
     }
+    GRU_STAMP(4);
     __syncthreads();
+    GRU_STAMP(5);
     // 5. push this CTA's slice of h_t into every CTA's next-step buffer; each 16-byte st.async
     //    completes bytes on the destination CTA's mbarrier for that buffer
     if (s + 1 < S && tid < C::PUSH_GROUPS * C::PER_DST) {
@@ -315,6 +330,7 @@ __global__ void __launch_bounds__(RnnCfg<G, H, CL, BC>::NT, 1)
         st_async_16(hbuf_u32 + rb + off, v, bar0 + rb + bar_off);
       }
     }
+    GRU_STAMP(6);
 #pragma unroll
     for (int p = 0; p < PPT; ++p)
       if (tid + p * NT < PAIRS && pvalid[p]) store_h(out, optr[p] + (int64_t)t * ldo, lo_off, out_bf16, hout[p]);
@@ -406,3 +422,7 @@ int rnn_gru256_mma(const float* xg, const float* w_hh, const float* b_hn, void* 
 FTB_DEFINE_TIMEOUT_READER(rnn_mma_timeouts)
 
 }  // namespace ftb
+
+extern "C" int ftb_debug_gru_timing(long long* device_buf) {
+  return cudaMemcpyToSymbol(ftb::g_gru_dbg, &device_buf, sizeof(device_buf)) == cudaSuccess ? 0 : -2;
+}
