@@ -18,6 +18,9 @@ LIB = CSRC / 'libftb200.so'
 OBJ_DIR = CSRC / 'build'
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC']
+# developer builds: FTB_NVCC_DEFINES="FTB_PHASE_TIMING" compiles the clock stamps of the scripts/*_phase_timing.py tools in
+# (they are compiled OUT by default: a clock64() read is a scheduling barrier and cost the GRU-256 step 8 %)
+NVCC_FLAGS += ['-D' + d for d in os.environ.get('FTB_NVCC_DEFINES', '').split() if d]
 
 
 def _nvcc() -> str:

@@ -129,10 +129,14 @@ __device__ __forceinline__ float ex2(float x) {
 // Optional phase timing (developer tool, scripts/attn_phase_timing.py): when set, one softmax thread of CTA (0,0,0)
 // records SM clock stamps of its first 16 key tiles, 10 slots per tile.
 __device__ long long* g_attn_dbg = nullptr;
+#ifdef FTB_PHASE_TIMING
 #define ATTN_STAMP(slot)                                              \
   do {                                                                \
     if (dbg && j < 16) dbg[j * 10 + (slot)] = clock64();              \
   } while (0)
+#else
+#define ATTN_STAMP(slot) do { } while (0)
+#endif
 
 template <int HD, bool FP16>
 __global__ void __launch_bounds__(au::THREADS, 2) attention_umma_kernel(const __grid_constant__ AttnArgs a) {
@@ -152,7 +156,9 @@ __global__ void __launch_bounds__(au::THREADS, 2) attention_umma_kernel(const __
   float* xch = reinterpret_cast<float*>(sm + OFF_BAR + 160);  // [tile parity][column half][128 rows] partial row maxima
   float* lsum = xch + 4 * BQ;                                  // [column half][128 rows] partial row sums (end of the loop)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef FTB_PHASE_TIMING
   const long long t_entry = clock64();
+#endif
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int S = a.S, E = a.E;
   const int nt = (S + BKV - 1) / BKV;
@@ -248,7 +254,9 @@ __global__ void __launch_bounds__(au::THREADS, 2) attention_umma_kernel(const __
     const float scale = a.scale_log2;
     float m_ref = -INFINITY, l = 0.f;
     long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0) ? g_attn_dbg : nullptr;
+#ifdef FTB_PHASE_TIMING
     if (dbg) dbg[160] = t_entry, dbg[161] = clock64();
+#endif
     for (int j = 0; j < nt; ++j) {
       ATTN_STAMP(0);
       uint32_t masked = 0, any_masked;
@@ -361,7 +369,9 @@ __global__ void __launch_bounds__(au::THREADS, 2) attention_umma_kernel(const __
       if (lane == 0) mbar_arrive(p_full);
       ATTN_STAMP(9);
     }
+#ifdef FTB_PHASE_TIMING
     if (dbg) dbg[162] = clock64();
+#endif
     // ---- normalise and store: O row / l, each warp its half of the head-dim columns
     lsum[hf * BQ + row] = l;
     asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
@@ -386,10 +396,14 @@ __global__ void __launch_bounds__(au::THREADS, 2) attention_umma_kernel(const __
       }
     }
   }
+#ifdef FTB_PHASE_TIMING
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0 && g_attn_dbg) g_attn_dbg[163] = clock64();
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+#ifdef FTB_PHASE_TIMING
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0 && g_attn_dbg) g_attn_dbg[164] = clock64();
+#endif
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");

@@ -66,10 +66,14 @@ static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory li
 // 2 all MMAs issued + committed, 3 epilogue warp 0 sees the accumulator, 4 epilogue warp 0 done, 5 producer issued the
 // unit's last weight load.
 __device__ long long* g_tail_dbg = nullptr;
+#ifdef FTB_PHASE_TIMING
 #define TAIL_STAMP(unit, slot)                                             \
   do {                                                                     \
     if (dbg && (unit) < 128) dbg[(unit) * 8 + (slot)] = clock64();         \
   } while (0)
+#else
+#define TAIL_STAMP(unit, slot) do { } while (0)
+#endif
 
 struct alignas(64) TailArgs {
   CUtensorMap map_x;                     // (ld2, M) 16-bit, box 64 x 128

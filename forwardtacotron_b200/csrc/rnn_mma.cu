@@ -66,10 +66,14 @@ __device__ __forceinline__ void rnn_mbar_wait(uint32_t bar, uint32_t parity) { m
 // of the first 64 steps.  Slots: 0 step start, 1 h landed, 2 MMAs done, 3 after the first block barrier, 4 gate maths done,
 // 5 after the second block barrier, 6 pushed.
 __device__ long long* g_gru_dbg = nullptr;
+#ifdef FTB_PHASE_TIMING
 #define GRU_STAMP(slot)                                       \
   do {                                                        \
     if (dbg && s < 64) dbg[s * 8 + (slot)] = clock64();       \
   } while (0)
+#else
+#define GRU_STAMP(slot) do { } while (0)
+#endif
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const float* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }

@@ -106,10 +106,14 @@ __device__ __forceinline__ void bulk_push(uint32_t dst_cluster, uint32_t src_cta
 // SM clock stamps of the first 64 steps.  Slots per step: 2 accumulator ready, 3 TMEM read, 4 gate maths + stores done,
 // 5 after fences + barrier, 6 pushes issued, 7 own slices landed and next step's MMAs issued.
 __device__ long long* g_rnn_dbg = nullptr;
+#ifdef FTB_PHASE_TIMING
 #define RNN_STAMP(slot)                                                                  \
   do {                                                                                   \
     if (dbg && s < 64) dbg[s * 8 + (slot)] = clock64();                                   \
   } while (0)
+#else
+#define RNN_STAMP(slot) do { } while (0)
+#endif
 
 template <int G, int H, int CL, int NCOLS, int CW, int UC, int KS = 8>
 struct RtCfg {

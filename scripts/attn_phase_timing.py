@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Developer tool: per-tile phase clocks of one softmax thread of the tcgen05 attention kernel (CTA 0)."""
+"""Developer tool (needs a build with FTB_NVCC_DEFINES=FTB_PHASE_TIMING: rm -rf forwardtacotron_b200/csrc/build && FTB_NVCC_DEFINES=FTB_PHASE_TIMING python __graft_entry__.py build): per-tile phase clocks of one softmax thread of the tcgen05 attention kernel (CTA 0)."""
 import ctypes as C
 import sys
 import torch

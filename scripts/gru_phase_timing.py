@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Developer tool: per-step phase clocks of the GRU-256 cluster kernel (CTA 0 of cluster 0)."""
+"""Developer tool (needs a build with FTB_NVCC_DEFINES=FTB_PHASE_TIMING: rm -rf forwardtacotron_b200/csrc/build && FTB_NVCC_DEFINES=FTB_PHASE_TIMING python __graft_entry__.py build): per-step phase clocks of the GRU-256 cluster kernel (CTA 0 of cluster 0)."""
 import ctypes as C
 import sys
 import torch

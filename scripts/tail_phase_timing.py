@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Developer tool: per-unit phase clocks of the fused CBHG tail kernel (CTA 0, first 128 accumulator units of the
+"""Developer tool (needs a build with FTB_NVCC_DEFINES=FTB_PHASE_TIMING: rm -rf forwardtacotron_b200/csrc/build && FTB_NVCC_DEFINES=FTB_PHASE_TIMING python __graft_entry__.py build): per-unit phase clocks of the fused CBHG tail kernel (CTA 0, first 128 accumulator units of the
 postnet launch of one cfg2-sized generate()).  Unit = 256 accumulator columns of one layer of one 128-row tile:
 1 (pre_highway) + 4 x 2 (highways) + 6 (GRU input projection) = 15 units of 256 columns per tile."""
 import ctypes as C
