@@ -21,8 +21,8 @@
 //                2^8 rescales its O row in place (tcgen05.ld / st) before P_j is released -- otherwise the old reference
 //                maximum is kept (p <= 256 fits the 16-bit types), so most tiles touch O only through the MMA.  Tiles
 //                without a masked key take shorter instruction sequences (the softmax warps are issue-bound).
-// The S x S score matrix never exists in memory.  Measured (cfg3 postnet layer, B 128 x S 1954, 2 heads x 128): 604-646 us =
-// 780-830 TFLOP/s; the one-CTA-per-SM version with four softmax warps and three score buffers took 834 us, the mma.sync
+// The S x S score matrix never exists in memory.  Measured (cfg3 postnet layer, B 128 x S 1954, 2 heads x 128): 571-578 us =
+// 870 TFLOP/s; the one-CTA-per-SM version with four softmax warps and three score buffers took 834 us, the mma.sync
 // kernel of attention.cu (FA2 style, 64-query tiles) 2.4 ms.  scripts/attn_phase_timing.py prints the per-tile phases.
 #include <cmath>
 
